@@ -1,0 +1,178 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = os.path.join(ROOT, "oracle", "liboracle.so")
+    srcs = [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(ROOT, "oracle"))
+            if "_ref" not in dp and "absl_shim" not in dp for f in fs if f.endswith((".cc", ".h"))]
+    if (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"])
+    L = C.CDLL(so)
+    vp, i64p, dp, fp, cp = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_char_p
+    L.orc_load_game.restype = vp
+    L.orc_load_game.argtypes = [cp, C.c_int, C.POINTER(cp), dp]
+    for f in ("orc_num_distinct_actions", "orc_num_players", "orc_max_game_length",
+              "orc_observation_tensor_size", "orc_information_state_tensor_size", "orc_max_chance_outcomes"):
+        getattr(L, f).restype = C.c_int
+        getattr(L, f).argtypes = [vp]
+    for f in ("orc_min_utility", "orc_max_utility"):
+        getattr(L, f).restype = C.c_double
+        getattr(L, f).argtypes = [vp]
+    L.orc_free_game.argtypes = [vp]
+    L.orc_new_initial_state.restype = vp
+    L.orc_new_initial_state.argtypes = [vp]
+    L.orc_clone.restype = vp
+    L.orc_clone.argtypes = [vp]
+    L.orc_free_state.argtypes = [vp]
+    L.orc_current_player.argtypes = [vp]
+    L.orc_is_terminal.argtypes = [vp]
+    L.orc_legal_actions.argtypes = [vp, i64p, C.c_int]
+    L.orc_apply_action.argtypes = [vp, C.c_int64]
+    L.orc_returns.argtypes = [vp, dp]
+    L.orc_observation_tensor.argtypes = [vp, C.c_int, fp]
+    L.orc_information_state_tensor.argtypes = [vp, C.c_int, fp]
+    L.orc_to_string.argtypes = [vp, cp, C.c_int]
+    L.orc_information_state_string.argtypes = [vp, C.c_int, cp, C.c_int]
+    L.orc_observation_string.argtypes = [vp, C.c_int, cp, C.c_int]
+    L.orc_chance_outcomes.argtypes = [vp, i64p, dp, C.c_int]
+    L.orc_history.argtypes = [vp, i64p, C.c_int]
+    L.orc_error.argtypes = [vp, cp, C.c_int]
+    _LIB = L
+    return L
+
+
+def parse_game_string(s):
+    """'go(board_size=7,komi=4.5)' -> ('go', {'board_size': 7.0, 'komi': 4.5})."""
+    s = s.strip()
+    if "(" not in s:
+        return s, {}
+    name, rest = s.split("(", 1)
+    rest = rest.rstrip(")")
+    params = {}
+    for kv in rest.split(","):
+        if not kv.strip():
+            continue
+        k, v = kv.split("=")
+        v = v.strip()
+        params[k.strip()] = {"True": 1.0, "true": 1.0, "False": 0.0, "false": 0.0}.get(v, None)
+        if params[k.strip()] is None:
+            params[k.strip()] = float(v)
+    return name, params
+
+
+class OracleGame:
+    def __init__(self, game_string, **kw):
+        name, params = parse_game_string(game_string)
+        params.update({k: float(v) for k, v in kw.items()})
+        self.name, self.params = name, params
+        L = lib()
+        keys = (C.c_char_p * len(params))(*[k.encode() for k in params])
+        vals = (C.c_double * len(params))(*[params[k] for k in params])
+        self._g = L.orc_load_game(name.encode(), len(params), keys, vals)
+        if not self._g:
+            raise ValueError("oracle: unknown game " + game_string)
+        self.num_distinct_actions = L.orc_num_distinct_actions(self._g)
+        self.num_players = L.orc_num_players(self._g)
+        self.max_game_length = L.orc_max_game_length(self._g)
+        self.observation_tensor_size = L.orc_observation_tensor_size(self._g)
+        self.information_state_tensor_size = L.orc_information_state_tensor_size(self._g)
+        self.max_chance_outcomes = L.orc_max_chance_outcomes(self._g)
+
+    def new_initial_state(self):
+        return OracleState(self, lib().orc_new_initial_state(self._g))
+
+    def __del__(self):
+        try:
+            lib().orc_free_game(self._g)
+        except Exception:
+            pass
+
+
+class OracleState:
+    def __init__(self, game, ptr):
+        self.game, self._s = game, ptr
+
+    def __del__(self):
+        try:
+            lib().orc_free_state(self._s)
+        except Exception:
+            pass
+
+    def clone(self):
+        return OracleState(self.game, lib().orc_clone(self._s))
+
+    def current_player(self):
+        return lib().orc_current_player(self._s)
+
+    def is_terminal(self):
+        return bool(lib().orc_is_terminal(self._s))
+
+    def is_chance_node(self):
+        return self.current_player() == -1
+
+    def legal_actions(self):
+        cap = max(self.game.num_distinct_actions, self.game.max_chance_outcomes, 1) + 8
+        buf = (C.c_int64 * cap)()
+        n = lib().orc_legal_actions(self._s, buf, cap)
+        return list(buf[:n])
+
+    def apply_action(self, a):
+        if lib().orc_apply_action(self._s, int(a)):
+            buf = C.create_string_buffer(256)
+            lib().orc_error(self._s, buf, 256)
+            raise RuntimeError("oracle: " + buf.value.decode())
+
+    def returns(self):
+        buf = (C.c_double * self.game.num_players)()
+        lib().orc_returns(self._s, buf)
+        return list(buf)
+
+    def observation_tensor(self, player=0):
+        import numpy as np
+        out = np.zeros(self.game.observation_tensor_size, dtype=np.float32)
+        lib().orc_observation_tensor(self._s, player, out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out
+
+    def information_state_tensor(self, player=0):
+        import numpy as np
+        out = np.zeros(self.game.information_state_tensor_size, dtype=np.float32)
+        lib().orc_information_state_tensor(self._s, player, out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out
+
+    def _str(self, fn, *args):
+        buf = C.create_string_buffer(4096)
+        fn(self._s, *args, buf, 4096)
+        return buf.value.decode()
+
+    def to_string(self):
+        return self._str(lib().orc_to_string)
+
+    __str__ = to_string
+
+    def information_state_string(self, player=0):
+        return self._str(lib().orc_information_state_string, player)
+
+    def observation_string(self, player=0):
+        return self._str(lib().orc_observation_string, player)
+
+    def chance_outcomes(self):
+        cap = self.game.max_chance_outcomes + 8
+        a = (C.c_int64 * cap)()
+        p = (C.c_double * cap)()
+        n = lib().orc_chance_outcomes(self._s, a, p, cap)
+        return [(a[i], p[i]) for i in range(n)]
+
+    def history(self):
+        cap = 1024
+        buf = (C.c_int64 * cap)()
+        n = lib().orc_history(self._s, buf, cap)
+        return list(buf[:n])
