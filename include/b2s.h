@@ -1,0 +1,176 @@
+/* b2s.h — C ABI of the B200-native batched game-simulation and search engine.
+ *
+ * This is the drop-in boundary for ONE hot path of google-deepmind/open_spiel: the per-game
+ * State transition functions (ApplyAction / LegalActions / IsTerminal / Returns /
+ * ObservationTensor) of tic_tac_toe, connect_four, breakthrough, hex, go, kuhn_poker and
+ * leduc_poker, and the MCTSBot / CFRSolver loops that drive them.  Everything here runs as
+ * hand-written sm_100a CUDA over struct-of-arrays batches of packed states resident in HBM.
+ * There is no CPU fallback: every entry point fails (non-zero status) when no CUDA device exists.
+ *
+ * Shape follows the reference's own C-ABI precedent, open_spiel/go/go_open_spiel.h:21-70
+ * (opaque handles, caller-allocated output buffers), extended with an error channel because a
+ * batch call must not exit() the process the way SpielFatalError (spiel_utils.cc:119-135) does.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; b2s_last_error() gives the message
+ *    (thread-local).  Nothing throws, nothing calls exit().
+ *  - "_d" pointers are DEVICE pointers on the batch's device, "_h" pointers are HOST pointers.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls with
+ *    device pointers only enqueue work.  The *_host entry points copy, run and synchronise.
+ *  - a batch is not thread-safe; distinct batches are independent.
+ *  - actions are int32 (the reference's Action is int64, spiel_utils.h:134; all seven games have
+ *    fewer than 2^15 distinct actions).  Action -1 (kInvalidAction, spiel_globals.h:82) means
+ *    "leave this lane untouched" in batched calls — the reference has no batched call, so this is
+ *    an extension; its own ApplyAction CHECKs action != -1 (spiel.cc:441-451).
+ *  - an illegal action, or any action on a terminal state, leaves the lane unchanged and is counted;
+ *    b2s_error_count() reports how many lanes were rejected since the last reset (the reference
+ *    would have SPIEL_CHECK-aborted inside DoApplyAction, e.g. connect_four.cc:131-133).
+ *  - returns are float32 on the device: every value the seven games can return (+-1, 0, -0, and
+ *    Leduc's half-integers, Kuhn's small integers) is exactly representable, so widening to the
+ *    reference's double (spiel.h:470) is bit-exact, sign of zero included.
+ */
+#ifndef B2S_H_
+#define B2S_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- games ------------------------------------------------------------------------------- */
+
+/* Replaces GameRegisterer::CreateByName lookup, open_spiel/spiel.cc:150-170.
+ * Returns a small non-negative id for a supported short_name, -1 otherwise. */
+int b2s_game_id(const char* short_name);
+enum {
+  B2S_TIC_TAC_TOE = 0, B2S_CONNECT_FOUR = 1, B2S_BREAKTHROUGH = 2, B2S_HEX = 3, B2S_GO = 4,
+  B2S_KUHN_POKER = 5, B2S_LEDUC_POKER = 6, B2S_NUM_GAMES = 7
+};
+
+/* Game parameters (replaces GameParameters, open_spiel/game_parameters.h:31-120, for the seven
+ * games).  Unset fields (< 0 / NaN) take the reference defaults. Names match the reference's
+ * parameter_specification (e.g. connect_four.cc:50-54, go.cc:55-63, hex.cc:48-55). */
+typedef struct b2s_params {
+  int32_t rows;            /* connect_four, breakthrough; hex num_rows */
+  int32_t columns;         /* connect_four, breakthrough; hex num_cols */
+  int32_t x_in_row;        /* connect_four */
+  int32_t egocentric_obs_tensor; /* connect_four */
+  int32_t board_size;      /* hex, go */
+  int32_t swap;            /* hex */
+  int32_t plain_obs_tensor;/* hex */
+  int32_t handicap;        /* go */
+  int32_t max_game_length; /* go */
+  int32_t players;         /* kuhn_poker, leduc_poker (2 only on device) */
+  int32_t starting_player; /* leduc_poker */
+  int32_t reserved[5];
+  double komi;             /* go */
+  double reserved_d[3];
+} b2s_params;
+void b2s_params_default(b2s_params* p);   /* all fields "unset" */
+
+/* What Game::{NumDistinctActions,NumPlayers,MaxGameLength,ObservationTensorSize,...} return
+ * (open_spiel/spiel.h:927-1190), plus the batch layout facts a caller needs to size buffers. */
+typedef struct b2s_game_info {
+  int32_t game_id;
+  int32_t num_players;
+  int32_t num_distinct_actions;
+  int32_t max_game_length;
+  int32_t max_chance_outcomes;
+  int32_t observation_tensor_size;
+  int32_t information_state_tensor_size;   /* 0 when the game provides none */
+  int32_t mask_words;                      /* ceil(max(num_distinct_actions, max_chance_outcomes)/32) */
+  int32_t state_bytes;                     /* bytes of packed state per lane (excluding history) */
+  int32_t history_bytes;                   /* extra per-lane bytes (go: superko hash history) */
+  double min_utility, max_utility;
+  int32_t obs_shape[4];                    /* ObservationTensorShape, zero padded */
+  int32_t reserved[4];
+} b2s_game_info;
+int b2s_game_info_get(int game_id, const b2s_params* params, b2s_game_info* out);
+
+/* ---- batches of states ------------------------------------------------------------------- */
+
+/* A batch = `capacity` packed State objects (open_spiel/spiel.h:301-916) of one game, SoA in HBM. */
+int  b2s_batch_create(int game_id, const b2s_params* params, int64_t capacity, int device, void** out_batch);
+void b2s_batch_destroy(void* batch);
+int  b2s_batch_info(void* batch, b2s_game_info* out);
+int64_t b2s_batch_capacity(void* batch);
+
+/* Game::NewInitialState (spiel.h:941) for lanes [0, n). Clears the error counter. */
+int b2s_reset(void* batch, int64_t n, void* stream);
+
+/* State::ApplyAction (spiel.cc:441-451) on lanes [0, n). */
+int b2s_apply_actions(void* batch, const int32_t* actions_d, int64_t n, void* stream);
+
+/* State::LegalActionsMask (spiel.cc:518-524) as bit masks: mask_words uint32 per lane, bit a of
+ * word a/32 set iff action a is legal for the player to move (all zero at terminal states).  At a
+ * chance node the mask holds the available chance outcomes. */
+int b2s_legal_mask(void* batch, uint32_t* mask_words_d, int64_t n, void* stream);
+
+/* State::LegalActions (spiel.h:388): ascending action ids, `stride` int16 slots per lane
+ * (stride >= max legal count), counts_d[i] = number of legal actions of lane i. */
+int b2s_legal_list(void* batch, int16_t* actions_d, int32_t* counts_d, int32_t stride, int64_t n, void* stream);
+
+/* State::CurrentPlayer / IsTerminal / Returns (spiel.h:330,447,470).  Any output may be NULL.
+ * current_player: >=0 player, -1 chance (kChancePlayerId), -4 terminal (kTerminalPlayerId).
+ * returns_d is [n][num_players] float32. */
+int b2s_status(void* batch, int8_t* current_player_d, uint8_t* terminal_d, float* returns_d, int64_t n, void* stream);
+
+/* State::ObservationTensor(player) (spiel.cc:908-925): [n][observation_tensor_size] float32,
+ * CHW row-major as utils/tensor_view.h:32-54.  player = -1 observes as the player to move
+ * (player 0 at terminal / chance nodes). */
+int b2s_observation(void* batch, int player, float* obs_d, int64_t n, void* stream);
+/* State::InformationStateTensor(player) (kuhn_poker, leduc_poker). */
+int b2s_information_state(void* batch, int player, float* out_d, int64_t n, void* stream);
+
+/* Fused env step: ApplyAction, then IsTerminal, Returns and the next LegalActionsMask in one pass
+ * over the state.  Outputs may be NULL. */
+int b2s_step_fused(void* batch, const int32_t* actions_d, uint32_t* mask_words_d, uint8_t* terminal_d,
+                   float* returns_d, int64_t n, void* stream);
+/* Same call with HOST buffers (pinned or pageable): copies actions in, runs, copies results out,
+ * synchronises.  This is the end-to-end entry a CPU-side caller (the State adapter, an RL env
+ * loop such as python/rl_environment.py:337-431) uses. */
+int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_words_h, uint8_t* terminal_h,
+                        float* returns_h, int64_t n);
+
+/* Number of lanes whose action was rejected since the last b2s_reset (synchronises the stream);
+ * first_bad_lane (nullable) receives the lowest-numbered such lane seen first, or -1. */
+int b2s_error_count(void* batch, int64_t* count, int64_t* first_bad_lane, void* stream);
+
+/* Scalar bridge for a host-side State adapter: raw packed lane `idx` (state_bytes + history_bytes). */
+int b2s_state_get(void* batch, int64_t idx, void* host_blob, size_t cap);
+int b2s_state_set(void* batch, int64_t idx, const void* host_blob, size_t len);
+/* Copies lane `src` of `src_batch` into lanes [dst_begin, dst_begin+count) of `dst_batch` (Clone). */
+int b2s_broadcast_state(void* dst_batch, int64_t dst_begin, int64_t count, void* src_batch, int64_t src, void* stream);
+
+/* Lane-range State::Clone (spiel.h:740): dst[dst_begin+i] = src[src_begin+i], i in [0,count). */
+int b2s_copy_states(void* dst_batch, int64_t dst_begin, void* src_batch, int64_t src_begin, int64_t count, void* stream);
+
+/* Random playouts to terminal from every lane's current state (the inner loop of
+ * RandomRolloutEvaluator::Evaluate, algorithms/mcts.cc:43-72, and of examples/benchmark_game.cc:32-115):
+ * uniform over legal actions (and over chance outcomes) from a Philox4x32-10 counter stream keyed
+ * by (seed, lane + lane_offset, ply).  The batch states are advanced in place to their terminal
+ * states.  returns_d [n][num_players] float32 and plies_d [n] int32 (plies played) may be NULL. */
+int b2s_rollout(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, float* returns_d, int32_t* plies_d, void* stream);
+
+/* ---- pinned host memory helpers (for the *_host entry points) ----------------------------- */
+int  b2s_host_alloc(void** out, size_t bytes);
+void b2s_host_free(void* p);
+int  b2s_device_alloc(int device, void** out, size_t bytes);
+void b2s_device_free(int device, void* p);
+int  b2s_memcpy_h2d(int device, void* dst_d, const void* src_h, size_t bytes, void* stream);
+int  b2s_memcpy_d2h(int device, void* dst_h, const void* src_d, size_t bytes, void* stream);
+int  b2s_stream_synchronize(int device, void* stream);
+int  b2s_device_count(void);
+
+/* Launch accounting: number of kernels this library has launched in this process. */
+int64_t b2s_launch_count(void);
+
+const char* b2s_last_error(void);
+const char* b2s_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H_ */

@@ -1,0 +1,362 @@
+// extern "C" layer (include/b2s.h) over the per-game kernel tables.  Host logic only: argument checks,
+// buffer ownership, stream plumbing.  No CPU fallback anywhere: without a CUDA device every call fails.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "batch_kernels.cuh"
+
+namespace b2s {
+
+long long g_launches = 0;
+static thread_local std::string g_err;
+
+static int fail(const std::string& m) { g_err = m; return 1; }
+static int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return 2;
+}
+#define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e, #x); } while (0)
+
+struct Batch {
+  GameOps* ops = nullptr;
+  b2s_game_info info;
+  long long cap = 0;
+  int device = 0;
+  void* planes = nullptr;
+  u64* hist = nullptr;
+  ErrBuf* err = nullptr;
+  // staging for the *_host entry points
+  int* act_d = nullptr; u32* mask_d = nullptr; unsigned char* term_d = nullptr; float* rets_d = nullptr;
+  cudaStream_t hs = nullptr;
+  Ctx ctx() const { Ctx c; c.planes = planes; c.cap = cap; c.hist = hist; c.err = err; return c; }
+  ~Batch() {
+    if (planes) cudaFree(planes);
+    if (hist) cudaFree(hist);
+    if (err) cudaFree(err);
+    if (act_d) cudaFree(act_d);
+    if (mask_d) cudaFree(mask_d);
+    if (term_d) cudaFree(term_d);
+    if (rets_d) cudaFree(rets_d);
+    if (hs) cudaStreamDestroy(hs);
+    delete ops;
+  }
+};
+
+static GameOps* make_ops(int id) {
+  switch (id) {
+    case B2S_TIC_TAC_TOE: return make_ops_tic_tac_toe();
+    case B2S_CONNECT_FOUR: return make_ops_connect_four();
+    case B2S_BREAKTHROUGH: return make_ops_breakthrough();
+    case B2S_HEX: return make_ops_hex();
+    case B2S_GO: return make_ops_go();
+    case B2S_KUHN_POKER: return make_ops_kuhn_poker();
+    case B2S_LEDUC_POKER: return make_ops_leduc_poker();
+  }
+  return nullptr;
+}
+
+static int check(void* b, long long n) {
+  if (!b) return fail("null batch");
+  Batch* B = (Batch*)b;
+  if (n < 0 || n > B->cap) return fail("n out of range for batch capacity");
+  CU(cudaSetDevice(B->device));
+  return 0;
+}
+static int post() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  return 0;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" {
+
+const char* b2s_last_error(void) { return g_err.c_str(); }
+const char* b2s_version(void) { return "b2s 0.1 (sm_100a)"; }
+int64_t b2s_launch_count(void) { return g_launches; }
+
+int b2s_game_id(const char* name) {
+  static const char* names[B2S_NUM_GAMES] = {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go",
+                                             "kuhn_poker", "leduc_poker"};
+  if (!name) return -1;
+  for (int i = 0; i < B2S_NUM_GAMES; ++i) if (!strcmp(name, names[i])) return i;
+  return -1;
+}
+
+void b2s_params_default(b2s_params* p) {
+  memset(p, 0xff, sizeof *p);          // every int field = -1 ("unset")
+  p->komi = NAN;
+  for (double& d : p->reserved_d) d = NAN;
+}
+
+int b2s_game_info_get(int game_id, const b2s_params* params, b2s_game_info* out) {
+  GameOps* ops = make_ops(game_id);
+  if (!ops) return fail("unsupported game id");
+  b2s_params p;
+  if (params) p = *params; else b2s_params_default(&p);
+  b2s_game_info gi;
+  memset(&gi, 0, sizeof gi);
+  const char* e = ops->configure(p, gi);
+  delete ops;
+  if (e) return fail(e);
+  *out = gi;
+  return 0;
+}
+
+int b2s_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int b2s_batch_create(int game_id, const b2s_params* params, int64_t capacity, int device, void** out_batch) {
+  if (!out_batch) return fail("null out_batch");
+  *out_batch = nullptr;
+  if (capacity <= 0) return fail("capacity must be positive");
+  if (b2s_device_count() <= 0) return fail("no CUDA device: the b2s device path has no CPU fallback");
+  GameOps* ops = make_ops(game_id);
+  if (!ops) return fail("unsupported game id");
+  b2s_params p;
+  if (params) p = *params; else b2s_params_default(&p);
+  Batch* B = new Batch;
+  B->ops = ops;
+  memset(&B->info, 0, sizeof B->info);
+  const char* e = ops->configure(p, B->info);
+  if (e) { delete B; return fail(e); }
+  B->cap = capacity;
+  B->device = device;
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "cudaSetDevice"); }
+  size_t bytes = ops->chunk_bytes() * (size_t)ops->chunks() * (size_t)capacity;
+  ce = cudaMalloc(&B->planes, bytes);
+  if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "cudaMalloc(state planes)"); }
+  if (B->info.history_bytes > 0) {
+    ce = cudaMalloc((void**)&B->hist, (size_t)B->info.history_bytes * (size_t)capacity);
+    if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "cudaMalloc(history)"); }
+  }
+  ce = cudaMalloc((void**)&B->err, sizeof(ErrBuf));
+  if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "cudaMalloc(err)"); }
+  ops->reset(B->ctx(), capacity, 0);
+  ce = cudaDeviceSynchronize();
+  if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "initial reset"); }
+  *out_batch = B;
+  return 0;
+}
+
+void b2s_batch_destroy(void* batch) {
+  if (!batch) return;
+  Batch* B = (Batch*)batch;
+  cudaSetDevice(B->device);
+  delete B;
+}
+
+int b2s_batch_info(void* batch, b2s_game_info* out) {
+  if (!batch || !out) return fail("null argument");
+  *out = ((Batch*)batch)->info;
+  return 0;
+}
+int64_t b2s_batch_capacity(void* batch) { return batch ? ((Batch*)batch)->cap : 0; }
+
+int b2s_reset(void* batch, int64_t n, void* stream) {
+  if (int r = check(batch, n)) return r;
+  Batch* B = (Batch*)batch;
+  B->ops->reset(B->ctx(), n, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_apply_actions(void* batch, const int32_t* actions_d, int64_t n, void* stream) {
+  if (int r = check(batch, n)) return r;
+  if (!actions_d) return fail("null actions");
+  Batch* B = (Batch*)batch;
+  B->ops->apply(B->ctx(), actions_d, n, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_legal_mask(void* batch, uint32_t* mask_words_d, int64_t n, void* stream) {
+  if (int r = check(batch, n)) return r;
+  if (!mask_words_d) return fail("null mask");
+  Batch* B = (Batch*)batch;
+  B->ops->legal_mask(B->ctx(), mask_words_d, n, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_legal_list(void* batch, int16_t* actions_d, int32_t* counts_d, int32_t stride, int64_t n, void* stream) {
+  if (int r = check(batch, n)) return r;
+  if (!actions_d || !counts_d || stride <= 0) return fail("bad legal_list arguments");
+  Batch* B = (Batch*)batch;
+  B->ops->legal_list(B->ctx(), actions_d, counts_d, stride, n, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_status(void* batch, int8_t* cur_d, uint8_t* term_d, float* rets_d, int64_t n, void* stream) {
+  if (int r = check(batch, n)) return r;
+  Batch* B = (Batch*)batch;
+  B->ops->status(B->ctx(), cur_d, term_d, rets_d, n, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_observation(void* batch, int player, float* obs_d, int64_t n, void* stream) {
+  if (int r = check(batch, n)) return r;
+  Batch* B = (Batch*)batch;
+  if (!obs_d) return fail("null obs");
+  if (player >= B->info.num_players) return fail("player out of range");
+  const char* e = B->ops->obs(B->ctx(), player, 0, obs_d, n, (cudaStream_t)stream);
+  if (e) return fail(e);
+  return post();
+}
+
+int b2s_information_state(void* batch, int player, float* out_d, int64_t n, void* stream) {
+  if (int r = check(batch, n)) return r;
+  Batch* B = (Batch*)batch;
+  if (!out_d) return fail("null out");
+  if (player >= B->info.num_players) return fail("player out of range");
+  const char* e = B->ops->obs(B->ctx(), player, 1, out_d, n, (cudaStream_t)stream);
+  if (e) return fail(e);
+  return post();
+}
+
+int b2s_step_fused(void* batch, const int32_t* actions_d, uint32_t* mask_d, uint8_t* term_d, float* rets_d, int64_t n, void* stream) {
+  if (int r = check(batch, n)) return r;
+  if (!actions_d) return fail("null actions");
+  Batch* B = (Batch*)batch;
+  B->ops->step_fused(B->ctx(), actions_d, mask_d, term_d, rets_d, n, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h, uint8_t* term_h, float* rets_h, int64_t n) {
+  if (int r = check(batch, n)) return r;
+  if (!actions_h) return fail("null actions");
+  Batch* B = (Batch*)batch;
+  if (!B->hs) {
+    CU(cudaStreamCreateWithFlags(&B->hs, cudaStreamNonBlocking));
+    CU(cudaMalloc((void**)&B->act_d, sizeof(int) * B->cap));
+    CU(cudaMalloc((void**)&B->mask_d, sizeof(u32) * (size_t)B->info.mask_words * B->cap));
+    CU(cudaMalloc((void**)&B->term_d, B->cap));
+    CU(cudaMalloc((void**)&B->rets_d, sizeof(float) * (size_t)B->info.num_players * B->cap));
+  }
+  cudaStream_t st = B->hs;
+  CU(cudaMemcpyAsync(B->act_d, actions_h, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  B->ops->step_fused(B->ctx(), B->act_d, mask_h ? B->mask_d : nullptr, term_h ? B->term_d : nullptr,
+                     rets_h ? B->rets_d : nullptr, n, st);
+  if (int r = post()) return r;
+  if (mask_h) CU(cudaMemcpyAsync(mask_h, B->mask_d, sizeof(u32) * (size_t)B->info.mask_words * n, cudaMemcpyDeviceToHost, st));
+  if (term_h) CU(cudaMemcpyAsync(term_h, B->term_d, n, cudaMemcpyDeviceToHost, st));
+  if (rets_h) CU(cudaMemcpyAsync(rets_h, B->rets_d, sizeof(float) * (size_t)B->info.num_players * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int b2s_error_count(void* batch, int64_t* count, int64_t* first_bad_lane, void* stream) {
+  if (int r = check(batch, 0)) return r;
+  Batch* B = (Batch*)batch;
+  ErrBuf e;
+  CU(cudaMemcpyAsync(&e, B->err, sizeof e, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  if (count) *count = (int64_t)e.count;
+  if (first_bad_lane) *first_bad_lane = e.count ? e.first : -1;
+  return 0;
+}
+
+// Packed lane blob: the kChunks chunks in plane order, then (go) the history column.
+int b2s_state_get(void* batch, int64_t idx, void* host_blob, size_t cap) {
+  if (int r = check(batch, 0)) return r;
+  Batch* B = (Batch*)batch;
+  if (idx < 0 || idx >= B->cap) return fail("lane out of range");
+  size_t cb = B->ops->chunk_bytes();
+  size_t need = cb * B->ops->chunks() + B->info.history_bytes;
+  if (cap < need) return fail("blob too small");
+  CU(cudaDeviceSynchronize());
+  char* out = (char*)host_blob;
+  for (int k = 0; k < B->ops->chunks(); ++k)
+    CU(cudaMemcpy(out + k * cb, (char*)B->planes + ((size_t)k * B->cap + idx) * cb, cb, cudaMemcpyDeviceToHost));
+  if (B->info.history_bytes)
+    CU(cudaMemcpy2D(out + cb * B->ops->chunks(), sizeof(u64), B->hist + idx, sizeof(u64) * B->cap, sizeof(u64),
+                    B->info.history_bytes / sizeof(u64), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int b2s_state_set(void* batch, int64_t idx, const void* host_blob, size_t len) {
+  if (int r = check(batch, 0)) return r;
+  Batch* B = (Batch*)batch;
+  if (idx < 0 || idx >= B->cap) return fail("lane out of range");
+  size_t cb = B->ops->chunk_bytes();
+  size_t need = cb * B->ops->chunks() + B->info.history_bytes;
+  if (len != need) return fail("blob size mismatch");
+  CU(cudaDeviceSynchronize());
+  const char* in = (const char*)host_blob;
+  for (int k = 0; k < B->ops->chunks(); ++k)
+    CU(cudaMemcpy((char*)B->planes + ((size_t)k * B->cap + idx) * cb, in + k * cb, cb, cudaMemcpyHostToDevice));
+  if (B->info.history_bytes)
+    CU(cudaMemcpy2D(B->hist + idx, sizeof(u64) * B->cap, in + cb * B->ops->chunks(), sizeof(u64), sizeof(u64),
+                    B->info.history_bytes / sizeof(u64), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int b2s_broadcast_state(void* dst_batch, int64_t dst_begin, int64_t count, void* src_batch, int64_t src, void* stream) {
+  if (int r = check(dst_batch, 0)) return r;
+  if (!src_batch) return fail("null src batch");
+  Batch* D = (Batch*)dst_batch;
+  Batch* S = (Batch*)src_batch;
+  if (D->info.game_id != S->info.game_id || D->device != S->device ||
+      memcmp(&D->info, &S->info, sizeof(b2s_game_info)) != 0)
+    return fail("broadcast: batches differ in game/params/device");
+  if (dst_begin < 0 || count < 0 || dst_begin + count > D->cap || src < 0 || src >= S->cap) return fail("broadcast: range");
+  D->ops->broadcast(D->ctx(), dst_begin, count, S->ctx(), src, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_copy_states(void* dst_batch, int64_t dst_begin, void* src_batch, int64_t src_begin, int64_t count, void* stream) {
+  if (int r = check(dst_batch, 0)) return r;
+  if (!src_batch) return fail("null src batch");
+  Batch* D = (Batch*)dst_batch;
+  Batch* S = (Batch*)src_batch;
+  if (D->device != S->device || memcmp(&D->info, &S->info, sizeof(b2s_game_info)) != 0)
+    return fail("copy: batches differ in game/params/device");
+  if (dst_begin < 0 || src_begin < 0 || count < 0 || dst_begin + count > D->cap || src_begin + count > S->cap)
+    return fail("copy: range");
+  D->ops->copy(D->ctx(), dst_begin, S->ctx(), src_begin, count, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_rollout(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, float* rets_d, int32_t* plies_d, void* stream) {
+  if (int r = check(batch, n)) return r;
+  Batch* B = (Batch*)batch;
+  B->ops->rollout(B->ctx(), seed, lane_offset, rets_d, plies_d, n, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_host_alloc(void** out, size_t bytes) {
+  if (!out) return fail("null out");
+  CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return 0;
+}
+void b2s_host_free(void* p) { if (p) cudaFreeHost(p); }
+int b2s_device_alloc(int device, void** out, size_t bytes) {
+  if (!out) return fail("null out");
+  CU(cudaSetDevice(device));
+  CU(cudaMalloc(out, bytes));
+  return 0;
+}
+void b2s_device_free(int device, void* p) { if (p) { cudaSetDevice(device); cudaFree(p); } }
+int b2s_memcpy_h2d(int device, void* dst_d, const void* src_h, size_t bytes, void* stream) {
+  CU(cudaSetDevice(device));
+  CU(cudaMemcpyAsync(dst_d, src_h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int b2s_memcpy_d2h(int device, void* dst_h, const void* src_d, size_t bytes, void* stream) {
+  CU(cudaSetDevice(device));
+  CU(cudaMemcpyAsync(dst_h, src_d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+int b2s_stream_synchronize(int device, void* stream) {
+  CU(cudaSetDevice(device));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,319 @@
+// Generic batched kernels, templated on a per-game rule core ("Rules").  One lane = one State.
+// All kernels are HBM-streaming: one coalesced load of the packed state per lane, a handful of
+// integer ops, coalesced stores.  Grid = ceil(n / block); blocks of 256 threads.
+#pragma once
+#include <new>
+
+#include "common.cuh"
+
+namespace b2s {
+
+constexpr int kBlock = 256;
+
+extern long long g_launches;   // api.cu
+
+// ---- kernels -------------------------------------------------------------------------------------
+
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_reset(Ctx ctx, typename R::Cfg cfg, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i == 0) { ctx.err->count = 0; ctx.err->first = 0x7fffffffffffffffLL; }
+  if (i >= n) return;
+  typename R::S s;
+  R::init(s, cfg, ctx, i);
+  R::store(s, ctx, i);
+}
+
+// State::ApplyAction over the batch (spiel.cc:441-451).
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_apply(Ctx ctx, typename R::Cfg cfg, const int* __restrict__ actions, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  int a = __ldg(actions + i);
+  if (a == -1) return;
+  typename R::S s;
+  R::load(s, ctx, i);
+  if (R::terminal(s, cfg) || !R::apply(s, a, cfg, ctx, i)) { flag_error(ctx.err, i); return; }
+  R::store(s, ctx, i);
+}
+
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_legal_mask(Ctx ctx, typename R::Cfg cfg, u32* __restrict__ mask, int mask_words, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  typename R::S s;
+  R::load(s, ctx, i);
+  u32 m[R::kMaskWords];
+  R::legal(s, cfg, m);
+  if (R::kMaskWords == 1) {
+    mask[i] = m[0];
+  } else {
+    for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+  }
+}
+
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_legal_list(Ctx ctx, typename R::Cfg cfg, short* __restrict__ out, int* __restrict__ counts, int stride, int mask_words, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  typename R::S s;
+  R::load(s, ctx, i);
+  u32 m[R::kMaskWords];
+  R::legal(s, cfg, m);
+  int k = 0;
+  for (int w = 0; w < mask_words; ++w) {
+    u32 bits = m[w];
+    while (bits) {
+      int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (k < stride) out[i * stride + k] = (short)(w * 32 + b);
+      ++k;
+    }
+  }
+  counts[i] = k;
+}
+
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_status(Ctx ctx, typename R::Cfg cfg, signed char* __restrict__ cur, unsigned char* __restrict__ term, float* __restrict__ rets, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  typename R::S s;
+  R::load(s, ctx, i);
+  int cp = R::cur_player(s, cfg);
+  if (cur) cur[i] = (signed char)cp;
+  if (term) term[i] = cp == kTerminalPlayerId ? 1 : 0;
+  if (rets) {
+    float r[R::kPlayers];
+    R::returns(s, cfg, r);
+    if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
+    else for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+  }
+}
+
+// ApplyAction + IsTerminal + Returns + next LegalActionsMask in one pass.
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_step_fused(Ctx ctx, typename R::Cfg cfg, const int* __restrict__ actions, u32* __restrict__ mask, int mask_words, unsigned char* __restrict__ term, float* __restrict__ rets, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  int a = __ldg(actions + i);
+  typename R::S s;
+  R::load(s, ctx, i);
+  if (a != -1) {
+    if (R::terminal(s, cfg) || !R::apply(s, a, cfg, ctx, i)) flag_error(ctx.err, i);
+    else R::store(s, ctx, i);
+  }
+  bool t = R::terminal(s, cfg);
+  if (term) term[i] = t ? 1 : 0;
+  if (rets) {
+    float r[R::kPlayers];
+    R::returns(s, cfg, r);
+    if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
+    else for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+  }
+  if (mask) {
+    u32 m[R::kMaskWords];
+    if (t) { for (int w = 0; w < R::kMaskWords; ++w) m[w] = 0; }
+    else R::legal_nonterminal(s, cfg, m);
+    if (R::kMaskWords == 1) mask[i] = m[0];
+    else for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+  }
+}
+
+// ObservationTensor / InformationStateTensor.  A warp owns 32 consecutive lanes: every thread packs
+// its own state's tensor into shared memory (game-specific compact form), then the warp streams the
+// 32*size floats of its tile out as fully coalesced 16-byte stores.
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, int player, int which, float* __restrict__ out, int size, u32 magic, long long n) {
+  __shared__ typename R::ObsPack packs[kBlock];
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (i < n) {
+    typename R::S s;
+    R::load(s, ctx, i);
+    int pl = player;
+    if (pl < 0) { pl = R::cur_player(s, cfg); if (pl < 0) pl = 0; }
+    R::obs_pack(s, cfg, pl, which, packs[threadIdx.x]);
+  }
+  __syncwarp();
+  long long tile0 = ((long long)blockIdx.x * kBlock + warp * 32);   // first lane of this warp's tile
+  if (tile0 >= n) return;
+  int lanes_here = (int)((n - tile0) < 32 ? (n - tile0) : 32);
+  int total = lanes_here * size;                                       // floats in this tile
+  float* base = out + tile0 * size;                                    // 16B aligned: 32*size*4 % 16 == 0
+  const typename R::ObsPack* wp = packs + warp * 32;
+  int nvec = total >> 2;
+  for (int q = lane; q < nvec; q += 32) {
+    int e0 = q << 2;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int e = e0 + j;
+      int st = (int)(((u64)e * magic) >> 32);        // e / size (magic verified on the host for the range)
+      int within = e - st * size;
+      v[j] = R::obs_elem(wp[st], cfg, within);
+    }
+    reinterpret_cast<float4*>(base)[q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  for (int e = (nvec << 2) + lane; e < total; e += 32) {               // ragged tail of the last tile
+    int st = (int)(((u64)e * magic) >> 32);
+    base[e] = R::obs_elem(wp[st], cfg, e - st * size);
+  }
+}
+
+// Random playout to terminal (mcts.cc:43-72 inner loop; benchmark_game.cc:32-115).
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_rollout(Ctx ctx, typename R::Cfg cfg, u64 seed, long long lane_offset, int mask_words, int max_plies, float* __restrict__ rets, int* __restrict__ plies, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  typename R::S s;
+  R::load(s, ctx, i);
+  int ply = 0;
+  while (!R::terminal(s, cfg) && ply < max_plies) {
+    u32 m[R::kMaskWords];
+    R::legal_nonterminal(s, cfg, m);
+    int cnt = 0;
+    for (int w = 0; w < mask_words; ++w) cnt += __popc(m[w]);
+    u32 k = philox_uniform(seed, (u64)(i + lane_offset), (u32)ply, (u32)cnt);
+    int a = nth_set_bit(m, mask_words, (int)k);
+    R::apply(s, a, cfg, ctx, i);
+    ++ply;
+  }
+  R::store(s, ctx, i);
+  if (plies) plies[i] = ply;
+  if (rets) {
+    float r[R::kPlayers];
+    R::returns(s, cfg, r);
+    for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+  }
+}
+
+// Clone: copy lane `src` of one batch into lanes [dst0, dst0+count) of another.
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_broadcast(Ctx dst, long long dst0, long long count, Ctx srcctx, long long src, typename R::Cfg cfg) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= count) return;
+  typename R::S s;
+  R::load(s, srcctx, src);
+  R::store(s, dst, dst0 + i);
+  R::copy_history(dst, dst0 + i, srcctx, src, s, cfg);
+}
+
+// Clone a lane range: dst[dst0 + i] = src[src0 + i].
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_copy(Ctx dst, long long dst0, Ctx srcctx, long long src0, long long count, typename R::Cfg cfg) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= count) return;
+  typename R::S s;
+  R::load(s, srcctx, src0 + i);
+  R::store(s, dst, dst0 + i);
+  R::copy_history(dst, dst0 + i, srcctx, src0 + i, s, cfg);
+}
+
+// ---- host-side per-game dispatch table --------------------------------------------------------------
+
+struct Batch;   // api.cu
+
+struct GameOps {
+  virtual ~GameOps() {}
+  virtual const char* configure(const b2s_params& p, b2s_game_info& gi) = 0;
+  virtual size_t chunk_bytes() const = 0;
+  virtual int chunks() const = 0;
+  virtual void reset(const Ctx&, long long n, cudaStream_t) = 0;
+  virtual void apply(const Ctx&, const int* a, long long n, cudaStream_t) = 0;
+  virtual void legal_mask(const Ctx&, u32* m, long long n, cudaStream_t) = 0;
+  virtual void legal_list(const Ctx&, short* out, int* counts, int stride, long long n, cudaStream_t) = 0;
+  virtual void status(const Ctx&, signed char* cur, unsigned char* term, float* rets, long long n, cudaStream_t) = 0;
+  virtual const char* obs(const Ctx&, int player, int which, float* out, long long n, cudaStream_t) = 0;
+  virtual void step_fused(const Ctx&, const int* a, u32* m, unsigned char* term, float* rets, long long n, cudaStream_t) = 0;
+  virtual void rollout(const Ctx&, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t) = 0;
+  virtual void broadcast(const Ctx& dst, long long dst0, long long count, const Ctx& src, long long srclane, cudaStream_t) = 0;
+  virtual void copy(const Ctx& dst, long long dst0, const Ctx& src, long long src0, long long count, cudaStream_t) = 0;
+  b2s_game_info info;
+};
+
+inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+// magic M with floor(e*M >> 32) == e / d for all 0 <= e < limit (checked exhaustively).
+inline bool make_magic(int d, int limit, u32* out) {
+  u64 M = ((1ull << 32) + d - 1) / d;
+  if (M >> 32) { if (d == 1) { *out = 0; return false; } }
+  for (int e = 0; e < limit; ++e)
+    if ((int)(((u64)e * M) >> 32) != e / d) return false;
+  *out = (u32)M;
+  return true;
+}
+
+template <class R>
+struct GameOpsT : GameOps {
+  typename R::Cfg cfg;
+  const char* configure(const b2s_params& p, b2s_game_info& gi) override {
+    const char* e = R::make_cfg(p, cfg, gi);
+    if (e) return e;
+    int width = gi.num_distinct_actions > gi.max_chance_outcomes ? gi.num_distinct_actions : gi.max_chance_outcomes;
+    gi.mask_words = (width + 31) / 32;
+    if (gi.mask_words > R::kMaskWords) return "action space too large for the device path";
+    gi.state_bytes = (int)(sizeof(typename R::Chunk) * R::kChunks);
+    gi.game_id = R::kGameId;
+    info = gi;
+    return nullptr;
+  }
+  size_t chunk_bytes() const override { return sizeof(typename R::Chunk); }
+  int chunks() const override { return R::kChunks; }
+  void reset(const Ctx& c, long long n, cudaStream_t st) override {
+    long long m = n > 0 ? n : 1;
+    k_reset<R><<<grid_for(m), kBlock, 0, st>>>(c, cfg, n); ++g_launches;
+  }
+  void apply(const Ctx& c, const int* a, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    k_apply<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, a, n); ++g_launches;
+  }
+  void legal_mask(const Ctx& c, u32* m, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    k_legal_mask<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, m, info.mask_words, n); ++g_launches;
+  }
+  void legal_list(const Ctx& c, short* out, int* counts, int stride, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    k_legal_list<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, out, counts, stride, info.mask_words, n); ++g_launches;
+  }
+  void status(const Ctx& c, signed char* cur, unsigned char* term, float* rets, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    k_status<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, cur, term, rets, n); ++g_launches;
+  }
+  const char* obs(const Ctx& c, int player, int which, float* out, long long n, cudaStream_t st) override {
+    int size = which == 0 ? info.observation_tensor_size : info.information_state_tensor_size;
+    if (size <= 0) return "game provides no such tensor";
+    if (which == 1 && !R::kHasInfoState) return "game provides no information state tensor";
+    if (n <= 0) return nullptr;
+    u32 magic;
+    if (!make_magic(size, 32 * size, &magic)) return "internal: no division magic";
+    k_obs<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, player, which, out, size, magic, n); ++g_launches;
+    return nullptr;
+  }
+  void step_fused(const Ctx& c, const int* a, u32* m, unsigned char* term, float* rets, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    k_step_fused<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, a, m, info.mask_words, term, rets, n); ++g_launches;
+  }
+  void rollout(const Ctx& c, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    k_rollout<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, seed, lane_offset, info.mask_words, info.max_game_length + 4, rets, plies, n); ++g_launches;
+  }
+  void broadcast(const Ctx& dst, long long dst0, long long count, const Ctx& src, long long srclane, cudaStream_t st) override {
+    if (count <= 0) return;
+    k_broadcast<R><<<grid_for(count), kBlock, 0, st>>>(dst, dst0, count, src, srclane, cfg); ++g_launches;
+  }
+  void copy(const Ctx& dst, long long dst0, const Ctx& src, long long src0, long long count, cudaStream_t st) override {
+    if (count <= 0) return;
+    k_copy<R><<<grid_for(count), kBlock, 0, st>>>(dst, dst0, src, src0, count, cfg); ++g_launches;
+  }
+};
+
+// one factory per game, defined in game_<name>.cu
+GameOps* make_ops_tic_tac_toe();
+GameOps* make_ops_connect_four();
+GameOps* make_ops_breakthrough();
+GameOps* make_ops_hex();
+GameOps* make_ops_go();
+GameOps* make_ops_kuhn_poker();
+GameOps* make_ops_leduc_poker();
+
+}  // namespace b2s

@@ -1,0 +1,84 @@
+// Shared device/host helpers for the batched game kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2s.h"
+
+namespace b2s {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// Sentinels: reference open_spiel/spiel_globals.h:26-56,82.
+constexpr int kChancePlayerId = -1;
+constexpr int kTerminalPlayerId = -4;
+
+// Per-batch error record written by kernels when an action is rejected.
+struct ErrBuf {
+  u64 count;        // lanes rejected since last reset
+  long long first;  // a rejected lane index (min over racing writers), -1 if none
+};
+
+__device__ __forceinline__ void flag_error(ErrBuf* e, long long lane) {
+  atomicAdd(&e->count, 1ull);
+  atomicMin(&e->first, lane);
+}
+
+// Everything a kernel needs to find lane i's packed state.
+struct Ctx {
+  void* planes;       // kChunks planes of `cap` chunks each (SoA)
+  long long cap;
+  u64* hist;          // go: [max_len+1][cap] zobrist history, else nullptr
+  ErrBuf* err;
+};
+
+// ---- Philox4x32-10 counter RNG (Salmon et al. 2011), key = seed, counter = (lane, ply) ----------
+struct Philox {
+  u32 c[4];
+  u32 k[2];
+};
+__host__ __device__ __forceinline__ void philox_round(u32 (&c)[4], const u32 (&k)[2]) {
+  const u32 M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  u64 p0 = (u64)M0 * c[0], p1 = (u64)M1 * c[2];
+  u32 hi0 = (u32)(p0 >> 32), lo0 = (u32)p0, hi1 = (u32)(p1 >> 32), lo1 = (u32)p1;
+  u32 n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+// Four 32-bit words for (seed, lane, ply).
+__host__ __device__ __forceinline__ void philox4(u64 seed, u64 lane, u32 ply, u32 stream, u32 (&out)[4]) {
+  u32 c[4] = {(u32)lane, (u32)(lane >> 32), ply, stream};
+  u32 k[2] = {(u32)seed, (u32)(seed >> 32)};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k);
+    k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+// Unbiased uniform integer in [0, n) from the (seed, lane, ply) block: Lemire's multiply-shift with
+// rejection; the four words of the block are tried in order, then the block for stream+1, ...
+__host__ __device__ __forceinline__ u32 philox_uniform(u64 seed, u64 lane, u32 ply, u32 n) {
+  u32 thresh = (u32)(0u - n) % n;
+  for (u32 stream = 0;; ++stream) {
+    u32 r[4];
+    philox4(seed, lane, ply, stream, r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      u64 m = (u64)r[j] * n;
+      if ((u32)m >= thresh) return (u32)(m >> 32);
+    }
+  }
+}
+
+// k-th (0-based) set bit position of a multi-word mask; returns -1 if fewer bits.
+__device__ __forceinline__ int nth_set_bit(const u32* words, int nwords, int k) {
+  for (int w = 0; w < nwords; ++w) {
+    int c = __popc(words[w]);
+    if (k < c) return w * 32 + (int)__fns(words[w], 0, k + 1);
+    k -= c;
+  }
+  return -1;
+}
+
+}  // namespace b2s

@@ -1,0 +1,149 @@
+// breakthrough rule core on bitboards.  Semantics: reference open_spiel/games/breakthrough/breakthrough.cc
+// (ctor :121-144, DoApplyAction :154-194, LegalActions :219-258, IsTerminal :308-310, Returns :312-320,
+// ObservationTensor :286-342).  Packed: two 64-bit boards (black = player 0, moving to higher rows; white =
+// player 1), bit = row*cols+col, 16 B per state.  Action id = ((r*cols+c)*6+dir)*2+capture (mixed-base rank
+// over {rows, cols, 6, 2}, spiel_utils.cc:50-63).
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+
+struct BreakthroughRules {
+  static constexpr int kGameId = B2S_BREAKTHROUGH;
+  typedef uint4 Chunk;                 // {black.lo, black.hi, white.lo, white.hi}
+  static constexpr int kChunks = 1;
+  static constexpr int kMaskWords = 24;   // 64 cells * 12
+  static constexpr int kObsWords = 3;
+  static constexpr int kPlayers = 2;
+  static constexpr bool kHasInfoState = false;
+
+  struct Cfg {
+    int rows, cols, cells;
+    u64 board, last_row, first_row, not_col0, not_collast;
+    u64 init_black, init_white;
+  };
+  // The player to move is not derivable from the position (captures change the piece counts) and an 8x8
+  // board uses all 64 bits of both words, so the mover is folded into the stored pair: the white word is
+  // stored complemented when player 1 is to move.  Boards are disjoint, so (black & stored_white) == 0 means
+  // player 0 to move; otherwise black & ~white == black != 0 (black only runs out of pieces on white's
+  // capture, after which player 0 is to move and the game is over anyway).
+  struct S { u64 b, w; int mover; };
+
+  static __host__ const char* make_cfg(const b2s_params& p, Cfg& c, b2s_game_info& gi) {
+    c.rows = p.rows >= 0 ? p.rows : 8;     // breakthrough.h:41-42
+    c.cols = p.columns >= 0 ? p.columns : 8;
+    if (c.rows < 2 || c.cols < 2) return "breakthrough: rows, columns must be > 1";
+    if (c.rows * c.cols > 64) return "breakthrough: rows*columns must fit 64 bits for the device path";
+    c.cells = c.rows * c.cols;
+    c.board = c.cells == 64 ? ~0ull : ((1ull << c.cells) - 1);
+    u64 row0 = (c.cols == 64 ? ~0ull : ((1ull << c.cols) - 1));
+    c.first_row = row0;
+    c.last_row = row0 << ((c.rows - 1) * c.cols);
+    c.not_col0 = 0; c.not_collast = 0;
+    for (int r = 0; r < c.rows; ++r)
+      for (int col = 0; col < c.cols; ++col) {
+        if (col != 0) c.not_col0 |= 1ull << (r * c.cols + col);
+        if (col != c.cols - 1) c.not_collast |= 1ull << (r * c.cols + col);
+      }
+    c.init_black = row0; c.init_white = c.last_row;
+    if (c.rows >= 6) { c.init_black |= row0 << c.cols; c.init_white |= row0 << ((c.rows - 2) * c.cols); }
+    gi.num_players = 2;
+    gi.num_distinct_actions = c.cells * 12;                       // breakthrough.cc:388-390
+    gi.max_game_length = 2 * (2 * c.rows - 3) * c.cols + 1;       // breakthrough.h:118-120
+    gi.observation_tensor_size = 3 * c.cells;
+    gi.obs_shape[0] = 3; gi.obs_shape[1] = c.rows; gi.obs_shape[2] = c.cols;
+    gi.min_utility = -1; gi.max_utility = 1;
+    return nullptr;
+  }
+  __device__ static __forceinline__ void load(S& s, const Ctx& ctx, long long i) {
+    uint4 v = reinterpret_cast<const uint4*>(ctx.planes)[i];
+    s.b = ((u64)v.y << 32) | v.x;
+    u64 w = ((u64)v.w << 32) | v.z;
+    s.mover = (s.b & w) != 0 ? 1 : 0;
+    s.w = s.mover ? ~w : w;
+  }
+  __device__ static __forceinline__ void store(const S& s, const Ctx& ctx, long long i) {
+    u64 w = s.mover ? ~s.w : s.w;
+    reinterpret_cast<uint4*>(ctx.planes)[i] = make_uint4((u32)s.b, (u32)(s.b >> 32), (u32)w, (u32)(w >> 32));
+  }
+  __device__ static __forceinline__ void init(S& s, const Cfg& c, const Ctx&, long long) { s.b = c.init_black; s.w = c.init_white; s.mover = 0; }
+  __device__ static __forceinline__ void copy_history(const Ctx&, long long, const Ctx&, long long, const S&, const Cfg&) {}
+
+  // winner: 0 / 1 / -1
+  __device__ static __forceinline__ int winner(const S& s, const Cfg& c) {
+    u64 w = s.w & c.board;
+    if ((s.b & c.last_row) || w == 0) return 0;
+    if ((w & c.first_row) || s.b == 0) return 1;
+    return -1;
+  }
+  __device__ static __forceinline__ bool terminal(const S& s, const Cfg& c) { return winner(s, c) >= 0; }
+  __device__ static __forceinline__ int cur_player(const S& s, const Cfg& c) { return terminal(s, c) ? kTerminalPlayerId : s.mover; }
+  __device__ static __forceinline__ void returns(const S& s, const Cfg& c, float* r) {
+    int w = winner(s, c);
+    r[0] = w == 0 ? 1.f : w == 1 ? -1.f : 0.f;
+    r[1] = w == 1 ? 1.f : w == 0 ? -1.f : 0.f;
+  }
+  __device__ static __forceinline__ void legal_nonterminal(const S& s, const Cfg& c, u32* m) {
+    for (int i = 0; i < kMaskWords; ++i) m[i] = 0;
+    u64 white = s.w & c.board;
+    u64 mine = s.mover == 0 ? s.b : white, theirs = s.mover == 0 ? white : s.b;
+    u64 empty = ~(s.b | white) & c.board;
+    u64 pcs = mine;
+    while (pcs) {
+      int cell = __ffsll((long long)pcs) - 1;
+      pcs &= pcs - 1;
+      int r = cell / c.cols, col = cell - r * c.cols;
+      int rp = s.mover == 0 ? r + 1 : r - 1;
+      if (rp < 0 || rp >= c.rows) continue;
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        int cp = col + o - 1;
+        if (cp < 0 || cp >= c.cols) continue;
+        u64 tb = 1ull << (rp * c.cols + cp);
+        int dir = s.mover * 3 + o;
+        int a = (cell * 6 + dir) * 2;
+        if (empty & tb) m[a >> 5] |= 1u << (a & 31);
+        else if (o != 1 && (theirs & tb)) { a += 1; m[a >> 5] |= 1u << (a & 31); }
+      }
+    }
+  }
+  __device__ static __forceinline__ void legal(const S& s, const Cfg& c, u32* m) {
+    if (terminal(s, c)) { for (int i = 0; i < kMaskWords; ++i) m[i] = 0; return; }
+    legal_nonterminal(s, c, m);
+  }
+  __device__ static __forceinline__ bool apply(S& s, int a, const Cfg& c, const Ctx&, long long) {
+    if (a < 0 || a >= c.cells * 12) return false;
+    int cap = a & 1, dir = (a >> 1) % 6, cell = a / 12;
+    if (dir / 3 != s.mover) return false;
+    int r = cell / c.cols, col = cell - r * c.cols;
+    int rp = dir < 3 ? r + 1 : r - 1, cp = col + (dir % 3) - 1;
+    if (rp < 0 || rp >= c.rows || cp < 0 || cp >= c.cols) return false;
+    u64 from = 1ull << cell, to = 1ull << (rp * c.cols + cp);
+    u64 white = s.w & c.board;
+    u64 mine = s.mover == 0 ? s.b : white, theirs = s.mover == 0 ? white : s.b;
+    if (!(mine & from)) return false;
+    bool target_enemy = (theirs & to) != 0, target_empty = ((s.b | white) & to) == 0;
+    if (cap) { if (!target_enemy || (dir % 3) == 1) return false; }
+    else if (!target_empty) return false;
+    mine = (mine & ~from) | to;
+    theirs &= ~to;
+    if (s.mover == 0) { s.b = mine; s.w = theirs; } else { s.w = mine; s.b = theirs; }
+    s.mover ^= 1;
+    return true;
+  }
+  struct ObsPack { u64 w[kObsWords]; };
+  // planes 0 = black, 1 = white, 2 = empty; [plane][r][c] — breakthrough.cc:286-342
+  __device__ static __forceinline__ void obs_pack(const S& s, const Cfg& c, int, int, ObsPack& p) {
+    u64 pl[3] = {s.b, s.w & c.board, ~(s.b | s.w) & c.board};
+    p.w[0] = p.w[1] = p.w[2] = 0;
+    if (c.cells == 64) { p.w[0] = pl[0]; p.w[1] = pl[1]; p.w[2] = pl[2]; return; }
+    int e = 0;
+    for (int k = 0; k < 3; ++k)
+      for (int cell = 0; cell < c.cells; ++cell, ++e) p.w[e >> 6] |= ((pl[k] >> cell) & 1ull) << (e & 63);
+  }
+  __device__ static __forceinline__ float obs_elem(const ObsPack& p, const Cfg&, int e) {
+    return (float)((p.w[e >> 6] >> (e & 63)) & 1ull);
+  }
+};
+
+}  // namespace b2s

@@ -1,0 +1,152 @@
+// connect_four rule core on bitboards.  Semantics: reference open_spiel/games/connect_four/connect_four.cc
+// (DoApplyAction :130-145, LegalActions :147-156, HasLine :163-196, IsTerminal :277-279, Returns :281-285,
+// ObservationTensor :299-328).  Representation is ours: two 64-bit boards, column-major with one sentinel
+// bit above every column (bit = col*(rows+1)+row, row 0 = bottom) so the four line directions are plain
+// shifts with no wrap-around.  Everything else (player to move, outcome) is derived, 16 B per state.
+#pragma once
+#include "common.cuh"
+
+namespace b2s {
+
+struct ConnectFourRules {
+  static constexpr int kGameId = B2S_CONNECT_FOUR;
+  typedef uint4 Chunk;                 // one 128-bit chunk: {x.lo,x.hi,o.lo,o.hi}
+  static constexpr int kChunks = 1;
+  static constexpr int kMaskWords = 1;
+  static constexpr int kObsWords = 3;  // 3*rows*cols <= 189 bits
+  static constexpr int kPlayers = 2;
+  static constexpr bool kHasInfoState = false;
+
+  struct Cfg {
+    int rows, cols, k, ego;
+    int h1;            // rows + 1
+    u64 top;           // top playable cell of every column
+    u64 board;         // all playable cells
+  };
+  struct S { u64 x, o; };   // player 0 ("x", kCross) / player 1 ("o", kNought) stones
+
+  static __host__ const char* make_cfg(const b2s_params& p, Cfg& c, b2s_game_info& gi) {
+    c.rows = p.rows >= 0 ? p.rows : 6;            // connect_four.h:45-50 defaults
+    c.cols = p.columns >= 0 ? p.columns : 7;
+    c.k = p.x_in_row >= 0 ? p.x_in_row : 4;
+    c.ego = p.egocentric_obs_tensor > 0 ? 1 : 0;
+    if (c.rows < 1 || c.cols < 1 || c.k < 1) return "connect_four: rows, columns, x_in_row must be positive";
+    if ((c.rows + 1) * c.cols > 64 || c.cols > 32)
+      return "connect_four: (rows+1)*columns must fit 64 bits for the device path";
+    c.h1 = c.rows + 1;
+    c.top = 0; c.board = 0;
+    for (int col = 0; col < c.cols; ++col) {
+      c.top |= 1ull << (col * c.h1 + c.rows - 1);
+      c.board |= ((1ull << c.rows) - 1) << (col * c.h1);
+    }
+    gi.num_players = 2;
+    gi.num_distinct_actions = c.cols;              // connect_four.h:179
+    gi.max_game_length = c.rows * c.cols;          // connect_four.h:200
+    gi.max_chance_outcomes = 0;
+    gi.observation_tensor_size = 3 * c.rows * c.cols;
+    gi.obs_shape[0] = 3; gi.obs_shape[1] = c.rows; gi.obs_shape[2] = c.cols;
+    gi.information_state_tensor_size = 0;
+    gi.min_utility = -1; gi.max_utility = 1;
+    return nullptr;
+  }
+
+  __device__ static __forceinline__ void load(S& s, const Ctx& ctx, long long i) {
+    uint4 v = reinterpret_cast<const uint4*>(ctx.planes)[i];
+    s.x = ((u64)v.y << 32) | v.x;
+    s.o = ((u64)v.w << 32) | v.z;
+  }
+  __device__ static __forceinline__ void store(const S& s, const Ctx& ctx, long long i) {
+    reinterpret_cast<uint4*>(ctx.planes)[i] = make_uint4((u32)s.x, (u32)(s.x >> 32), (u32)s.o, (u32)(s.o >> 32));
+  }
+  __device__ static __forceinline__ void init(S& s, const Cfg&, const Ctx&, long long) { s.x = 0; s.o = 0; }
+  __device__ static __forceinline__ void copy_history(const Ctx&, long long, const Ctx&, long long, const S&, const Cfg&) {}
+
+  __device__ static __forceinline__ bool has_line(u64 b, const Cfg& c) {
+    if (c.k == 4) {
+      const int d1 = c.h1, d2 = c.h1 + 1, d3 = c.h1 - 1;
+      u64 m;
+      m = b & (b >> 1);  if (m & (m >> 2)) return true;
+      m = b & (b >> d1); if (m & (m >> (2 * d1))) return true;
+      m = b & (b >> d2); if (m & (m >> (2 * d2))) return true;
+      m = b & (b >> d3); if (m & (m >> (2 * d3))) return true;
+      return false;
+    }
+    const int d[4] = {1, c.h1, c.h1 + 1, c.h1 - 1};
+    for (int j = 0; j < 4; ++j) {
+      u64 m = b;
+      bool ok = true;
+      for (int i = 1; i < c.k; ++i) {
+        int sh = i * d[j];
+        if (sh >= 64) { ok = false; break; }
+        m &= b >> sh;
+      }
+      if (ok && m) return true;
+    }
+    return false;
+  }
+  __device__ static __forceinline__ int mover(const S& s) { return __popcll(s.x | s.o) & 1; }
+  // outcome: 0 = p0 won, 1 = p1 won, 2 = unknown, 3 = draw (connect_four.h:58-63)
+  __device__ static __forceinline__ int outcome(const S& s, const Cfg& c) {
+    int last = 1 - mover(s);            // only the player who just moved can have completed a line
+    if (has_line(last == 0 ? s.x : s.o, c)) return last;
+    if (((s.x | s.o) & c.top) == c.top) return 3;
+    return 2;
+  }
+  __device__ static __forceinline__ bool terminal(const S& s, const Cfg& c) { return outcome(s, c) != 2; }
+  __device__ static __forceinline__ int cur_player(const S& s, const Cfg& c) {
+    return terminal(s, c) ? kTerminalPlayerId : mover(s);
+  }
+  __device__ static __forceinline__ void returns(const S& s, const Cfg& c, float* r) {
+    int oc = outcome(s, c);
+    r[0] = oc == 0 ? 1.f : oc == 1 ? -1.f : 0.f;
+    r[1] = oc == 1 ? 1.f : oc == 0 ? -1.f : 0.f;
+  }
+  // Legal columns of a NON-terminal state.
+  __device__ static __forceinline__ void legal_nonterminal(const S& s, const Cfg& c, u32* m) {
+    u64 free_top = ~(s.x | s.o) & c.top;
+    u32 out = 0;
+    for (int col = 0; col < c.cols; ++col) out |= (u32)((free_top >> (col * c.h1 + c.rows - 1)) & 1ull) << col;
+    m[0] = out;
+  }
+  __device__ static __forceinline__ void legal(const S& s, const Cfg& c, u32* m) {
+    if (terminal(s, c)) { m[0] = 0; return; }
+    legal_nonterminal(s, c, m);
+  }
+  // Apply to a NON-terminal state; false = illegal (state untouched).
+  __device__ static __forceinline__ bool apply(S& s, int a, const Cfg& c, const Ctx&, long long) {
+    if (a < 0 || a >= c.cols) return false;
+    u64 occ = s.x | s.o;
+    int base = a * c.h1;
+    if ((occ >> (base + c.rows - 1)) & 1ull) return false;
+    u64 colmask = ((1ull << c.rows) - 1) << base;
+    u64 bit = (occ & colmask) + (1ull << base);
+    if (mover(s) == 0) s.x |= bit; else s.o |= bit;
+    return true;
+  }
+
+  // Observation tensor as a packed bit string in output (CHW) order.
+  struct ObsPack { u64 w[kObsWords]; };
+  __device__ static __forceinline__ void obs_pack(const S& s, const Cfg& c, int player, int /*which*/, ObsPack& p) {
+    u64 planes[3];
+    if (c.ego) {                         // PlayerRelative, connect_four.cc:299-310
+      planes[0] = player == 0 ? s.o : s.x;
+      planes[1] = player == 0 ? s.x : s.o;
+    } else {                             // StateToPlayer, connect_four.cc:75-86
+      planes[0] = s.x; planes[1] = s.o;
+    }
+    planes[2] = ~(s.x | s.o) & c.board;
+    p.w[0] = p.w[1] = p.w[2] = 0;
+    int e = 0;
+    for (int pl = 0; pl < 3; ++pl)
+      for (int r = 0; r < c.rows; ++r)
+        for (int col = 0; col < c.cols; ++col, ++e) {
+          u64 bit = (planes[pl] >> (col * c.h1 + r)) & 1ull;
+          p.w[e >> 6] |= bit << (e & 63);
+        }
+  }
+  __device__ static __forceinline__ float obs_elem(const ObsPack& p, const Cfg&, int e) {
+    return (float)((p.w[e >> 6] >> (e & 63)) & 1ull);
+  }
+};
+
+}  // namespace b2s

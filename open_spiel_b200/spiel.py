@@ -1,0 +1,396 @@
+"""Host-side mirror of open_spiel::Game / State (open_spiel/spiel.h:301-1255) over the C ABI."""
+import ctypes as C
+import math
+import re
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B2SError, GameInfo, Params, check, lib
+
+kChancePlayerId = -1      # spiel_globals.h:26-56
+kTerminalPlayerId = -4
+kInvalidAction = -1
+
+_NAMES = ["tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker"]
+
+
+def registered_names():
+    """Short names this library serves (cf. pyspiel.registered_names, pyspiel.cc:737)."""
+    return list(_NAMES)
+
+
+def _parse_game_string(s):
+    """'go(board_size=9,komi=7.5)' -> ('go', {...}); grammar of game_parameters.cc GameParametersFromString."""
+    s = s.strip()
+    m = re.match(r"^([\w]+)(?:\((.*)\))?$", s)
+    if not m:
+        raise B2SError("cannot parse game string: " + s)
+    name, body = m.group(1), m.group(2)
+    params = {}
+    if body:
+        for kv in body.split(","):
+            if not kv.strip():
+                continue
+            k, v = kv.split("=", 1)
+            v = v.strip()
+            if v in ("True", "true"):
+                params[k.strip()] = True
+            elif v in ("False", "false"):
+                params[k.strip()] = False
+            else:
+                try:
+                    params[k.strip()] = int(v)
+                except ValueError:
+                    try:
+                        params[k.strip()] = float(v)
+                    except ValueError:
+                        params[k.strip()] = v
+    return name, params
+
+
+_PARAM_FIELDS = {
+    "connect_four": {"rows": "rows", "columns": "columns", "x_in_row": "x_in_row",
+                     "egocentric_obs_tensor": "egocentric_obs_tensor"},
+    "breakthrough": {"rows": "rows", "columns": "columns"},
+    "hex": {"board_size": "board_size", "num_cols": "columns", "num_rows": "rows", "swap": "swap",
+            "plain_obs_tensor": "plain_obs_tensor"},
+    "go": {"board_size": "board_size", "komi": "komi", "handicap": "handicap",
+           "max_game_length": "max_game_length"},
+    "kuhn_poker": {"players": "players"},
+    "leduc_poker": {"players": "players", "starting_player": "starting_player"},
+    "tic_tac_toe": {},
+}
+
+
+def load_game(game_string, params=None):
+    """pyspiel.load_game (pyspiel.cc:720-735 -> spiel.cc:255-297)."""
+    name, p = _parse_game_string(game_string)
+    if params:
+        p.update(params)
+    return Game(name, p)
+
+
+class Game:
+    """Mirror of open_spiel::Game for the seven device games."""
+
+    def __init__(self, name, params=None, device=0):
+        L = lib()
+        self._name = name
+        self._params = dict(params or {})
+        gid = L.b2s_game_id(name.encode())
+        if gid < 0:
+            raise B2SError("Unknown game '%s'. Available games are: %s" % (name, ", ".join(_NAMES)))
+        self._gid = gid
+        self._cparams = Params()
+        L.b2s_params_default(C.byref(self._cparams))
+        fields = _PARAM_FIELDS[name]
+        for k, v in self._params.items():
+            if k not in fields:
+                raise B2SError("Unknown parameter '%s' for game %s" % (k, name))   # spiel.cc:65-89
+            if fields[k] == "komi":
+                self._cparams.komi = float(v)
+            else:
+                setattr(self._cparams, fields[k], int(v))
+        self._info = GameInfo()
+        check(L.b2s_game_info_get(gid, C.byref(self._cparams), C.byref(self._info)))
+        self.device = device
+
+    # -- Game API (spiel.h:927-1190) --
+    def get_type_short_name(self):
+        return self._name
+
+    def num_distinct_actions(self):
+        return self._info.num_distinct_actions
+
+    def num_players(self):
+        return self._info.num_players
+
+    def max_game_length(self):
+        return self._info.max_game_length
+
+    def max_chance_outcomes(self):
+        return self._info.max_chance_outcomes
+
+    def min_utility(self):
+        return self._info.min_utility
+
+    def max_utility(self):
+        return self._info.max_utility
+
+    def observation_tensor_size(self):
+        return self._info.observation_tensor_size
+
+    def observation_tensor_shape(self):
+        return [d for d in self._info.obs_shape if d > 0]
+
+    def information_state_tensor_size(self):
+        return self._info.information_state_tensor_size
+
+    def get_parameters(self):
+        return dict(self._params)
+
+    def new_initial_state(self):
+        return State(self)
+
+    def new_batch(self, n, device=None):
+        return BatchedState(self, n, self.device if device is None else device)
+
+    def __str__(self):
+        if not self._params:
+            return self._name + "()"
+        return self._name + "(" + ",".join("%s=%s" % (k, self._params[k]) for k in sorted(self._params)) + ")"
+
+
+class BatchedState:
+    """`n` States of one game, struct-of-arrays in HBM.  The batched extension the kernels exist for.
+
+    Tensor arguments/results are torch CUDA tensors on the batch's device; work is enqueued on the
+    current torch stream.
+    """
+
+    def __init__(self, game, n, device=0):
+        if not torch.cuda.is_available():
+            raise B2SError("no CUDA device: open_spiel_b200 has no CPU fallback")
+        self.game, self.n, self.device = game, int(n), int(device)
+        self._h = C.c_void_p()
+        check(lib().b2s_batch_create(game._gid, C.byref(game._cparams), self.n, self.device, C.byref(self._h)))
+        self.info = game._info
+        self._dev = torch.device("cuda", self.device)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().b2s_batch_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self._dev).cuda_stream)
+
+    def _n(self, n):
+        return self.n if n is None else int(n)
+
+    def reset(self, n=None):
+        check(lib().b2s_reset(self._h, self._n(n), self._stream()))
+
+    def apply_actions(self, actions, n=None):
+        assert actions.dtype == torch.int32 and actions.is_cuda and actions.is_contiguous()
+        check(lib().b2s_apply_actions(self._h, actions.data_ptr(), self._n(n), self._stream()))
+
+    def legal_actions_mask_words(self, out=None, n=None):
+        n = self._n(n)
+        if out is None:
+            out = torch.empty((n, self.info.mask_words), dtype=torch.int32, device=self._dev)
+        check(lib().b2s_legal_mask(self._h, out.data_ptr(), n, self._stream()))
+        return out
+
+    def legal_actions_mask(self, n=None):
+        """Dense 0/1 mask [n, A] as State::LegalActionsMask (spiel.cc:518-524) would give."""
+        words = self.legal_actions_mask_words(n=n)
+        width = max(self.info.num_distinct_actions, self.info.max_chance_outcomes)
+        bits = torch.arange(32, device=self._dev, dtype=torch.int32)
+        dense = ((words.unsqueeze(-1) >> bits) & 1).reshape(words.shape[0], -1)[:, :width]
+        return dense
+
+    def legal_actions_list(self, stride=None, n=None):
+        n = self._n(n)
+        stride = stride or max(self.info.num_distinct_actions, self.info.max_chance_outcomes)
+        acts = torch.full((n, stride), -1, dtype=torch.int16, device=self._dev)
+        counts = torch.empty((n,), dtype=torch.int32, device=self._dev)
+        check(lib().b2s_legal_list(self._h, acts.data_ptr(), counts.data_ptr(), stride, n, self._stream()))
+        return acts, counts
+
+    def status(self, n=None):
+        n = self._n(n)
+        cur = torch.empty((n,), dtype=torch.int8, device=self._dev)
+        term = torch.empty((n,), dtype=torch.uint8, device=self._dev)
+        rets = torch.empty((n, self.info.num_players), dtype=torch.float32, device=self._dev)
+        check(lib().b2s_status(self._h, cur.data_ptr(), term.data_ptr(), rets.data_ptr(), n, self._stream()))
+        return cur, term, rets
+
+    def observation_tensor(self, player=-1, out=None, n=None):
+        n = self._n(n)
+        if out is None:
+            out = torch.empty((n, self.info.observation_tensor_size), dtype=torch.float32, device=self._dev)
+        check(lib().b2s_observation(self._h, int(player), out.data_ptr(), n, self._stream()))
+        return out
+
+    def information_state_tensor(self, player=-1, out=None, n=None):
+        n = self._n(n)
+        if out is None:
+            out = torch.empty((n, self.info.information_state_tensor_size), dtype=torch.float32, device=self._dev)
+        check(lib().b2s_information_state(self._h, int(player), out.data_ptr(), n, self._stream()))
+        return out
+
+    def step(self, actions, mask_out=None, terminal_out=None, returns_out=None, n=None):
+        """Fused ApplyAction + IsTerminal + Returns + next legal mask."""
+        n = self._n(n)
+        assert actions.dtype == torch.int32 and actions.is_cuda
+        if mask_out is None:
+            mask_out = torch.empty((n, self.info.mask_words), dtype=torch.int32, device=self._dev)
+        if terminal_out is None:
+            terminal_out = torch.empty((n,), dtype=torch.uint8, device=self._dev)
+        if returns_out is None:
+            returns_out = torch.empty((n, self.info.num_players), dtype=torch.float32, device=self._dev)
+        check(lib().b2s_step_fused(self._h, actions.data_ptr(), mask_out.data_ptr(), terminal_out.data_ptr(),
+                                   returns_out.data_ptr(), n, self._stream()))
+        return mask_out, terminal_out, returns_out
+
+    def step_host(self, actions_h, mask_h, terminal_h, returns_h, n=None):
+        """Same step with HOST tensors (ideally pinned): H2D + kernel + D2H + sync inside the call."""
+        n = self._n(n)
+        check(lib().b2s_step_fused_host(self._h, actions_h.data_ptr(),
+                                        mask_h.data_ptr() if mask_h is not None else None,
+                                        terminal_h.data_ptr() if terminal_h is not None else None,
+                                        returns_h.data_ptr() if returns_h is not None else None, n))
+
+    def rollout(self, seed, lane_offset=0, n=None):
+        n = self._n(n)
+        rets = torch.empty((n, self.info.num_players), dtype=torch.float32, device=self._dev)
+        plies = torch.empty((n,), dtype=torch.int32, device=self._dev)
+        check(lib().b2s_rollout(self._h, int(seed), int(lane_offset), n, rets.data_ptr(), plies.data_ptr(), self._stream()))
+        return rets, plies
+
+    def error_count(self):
+        cnt, first = C.c_int64(), C.c_int64()
+        check(lib().b2s_error_count(self._h, C.byref(cnt), C.byref(first), self._stream()))
+        return cnt.value, first.value
+
+    def check_errors(self):
+        cnt, first = self.error_count()
+        if cnt:
+            raise B2SError("%d lane(s) rejected an illegal action (first lane %d)" % (cnt, first))
+
+    def state_blob(self, idx):
+        size = self.info.state_bytes + self.info.history_bytes
+        buf = (C.c_uint8 * size)()
+        check(lib().b2s_state_get(self._h, int(idx), buf, size))
+        return bytes(buf)
+
+    def set_state_blob(self, idx, blob):
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        check(lib().b2s_state_set(self._h, int(idx), buf, len(blob)))
+
+    def broadcast_from(self, src_batch, src_lane, dst_begin=0, count=None):
+        count = self.n - dst_begin if count is None else count
+        check(lib().b2s_broadcast_state(self._h, dst_begin, count, src_batch._h, int(src_lane), self._stream()))
+
+
+    def copy_from(self, src_batch, src_begin=0, dst_begin=0, count=None):
+        count = min(self.n - dst_begin, src_batch.n - src_begin) if count is None else count
+        check(lib().b2s_copy_states(self._h, dst_begin, src_batch._h, src_begin, count, self._stream()))
+
+
+class State:
+    """Mirror of open_spiel::State (scalar API) backed by a one-lane device batch.
+
+    Every call launches a kernel and synchronises: this adapter exists for API/parity tests and for code
+    that is written against the scalar State interface; throughput comes from BatchedState.
+    """
+
+    def __init__(self, game, _batch=None, _history=None):
+        self._game = game
+        self._b = _batch if _batch is not None else BatchedState(game, 1, game.device)
+        self._history = list(_history or [])      # [(player, action)] as State::history_ (spiel.h:911)
+        self._act = torch.empty((1,), dtype=torch.int32, device=self._b._dev)
+
+    def get_game(self):
+        return self._game
+
+    def current_player(self):
+        cur, _, _ = self._b.status()
+        return int(cur.item())
+
+    def is_terminal(self):
+        _, term, _ = self._b.status()
+        return bool(term.item())
+
+    def is_chance_node(self):
+        return self.current_player() == kChancePlayerId
+
+    def legal_actions(self, player=None):
+        cur = self.current_player()
+        if cur == kTerminalPlayerId or (player is not None and player != cur):
+            return []
+        acts, counts = self._b.legal_actions_list()
+        k = int(counts.item())
+        return [int(a) for a in acts[0, :k].tolist()]
+
+    def legal_actions_mask(self, player=None):
+        cur = self.current_player()
+        width = self._game.num_distinct_actions() if cur != kChancePlayerId else self._game.max_chance_outcomes()
+        if player is not None and player != cur:
+            return [0] * width
+        return [int(v) for v in self._b.legal_actions_mask()[0, :width].tolist()]
+
+    def apply_action(self, action):
+        if action == kInvalidAction:
+            raise B2SError("ApplyAction: action == kInvalidAction")      # spiel.cc:443
+        player = self.current_player()
+        self._act[0] = int(action)
+        self._b.apply_actions(self._act)
+        cnt, _ = self._b.error_count()
+        if cnt:
+            self._b._reset_errors()
+            raise B2SError("illegal action %d for state\n%s" % (action, self))
+        self._history.append((player, int(action)))
+
+    def returns(self):
+        _, _, rets = self._b.status()
+        return [float(v) for v in rets[0].tolist()]
+
+    def rewards(self):
+        # default State::Rewards (spiel.h:489-495): zeros until terminal, then Returns()
+        if self.is_terminal():
+            return self.returns()
+        return [0.0] * self._game.num_players()
+
+    def player_return(self, player):
+        return self.returns()[player]
+
+    def observation_tensor(self, player=None):
+        if player is None:
+            player = max(self.current_player(), 0)
+        return self._b.observation_tensor(player)[0].cpu().numpy()
+
+    def information_state_tensor(self, player=None):
+        if player is None:
+            player = max(self.current_player(), 0)
+        return self._b.information_state_tensor(player)[0].cpu().numpy()
+
+    def history(self):
+        return [a for _, a in self._history]
+
+    def full_history(self):
+        return list(self._history)
+
+    def move_number(self):
+        return len(self._history)
+
+    def clone(self):
+        nb = BatchedState(self._game, 1, self._game.device)
+        nb.broadcast_from(self._b, 0, 0, 1)
+        return State(self._game, nb, self._history)
+
+    def child(self, action):
+        c = self.clone()
+        c.apply_action(action)
+        return c
+
+    def serialize(self):
+        """State::Serialize default format: one action per line (spiel.cc:411-430)."""
+        return "".join("%d\n" % a for _, a in self._history)
+
+    def __str__(self):
+        return "<b200 %s state, history=%s>" % (self._game.get_type_short_name(), self.history())
+
+
+def _reset_errors(self):
+    # clear the error counter without touching states: reset zero lanes
+    check(lib().b2s_reset(self._h, 0, self._stream()))
+
+
+BatchedState._reset_errors = _reset_errors

@@ -1,0 +1,167 @@
+"""GPU parity: every batched State function vs the CPU oracle, bit-exact, on seeded random games."""
+import json
+import os
+import glob
+
+import numpy as np
+import pytest
+import torch
+
+import open_spiel_b200 as b2
+from oracle_lib import OracleGame
+from parity import lockstep, mask_words_to_lists
+
+pytestmark = pytest.mark.gpu
+
+GAMES = [
+    ("tic_tac_toe", 512),
+    ("connect_four", 512),
+    ("connect_four(rows=4,columns=5,x_in_row=3)", 256),       # connect_four_test.cc:319-395 sizes
+    ("connect_four(rows=5,columns=6)", 256),
+    ("connect_four(rows=7,columns=8,x_in_row=5)", 256),
+    ("connect_four(egocentric_obs_tensor=True)", 128),
+    ("breakthrough", 256),
+    ("breakthrough(rows=6,columns=6)", 128),
+    ("breakthrough(rows=5,columns=4)", 128),
+]
+
+
+@pytest.mark.parametrize("game_string,lanes", GAMES, ids=[g for g, _ in GAMES])
+def test_lockstep_random_games(game_string, lanes):
+    steps = lockstep(game_string, n_lanes=lanes, seed=1234)
+    assert steps > lanes
+
+
+def test_illegal_and_noop_actions_connect_four():
+    g = b2.load_game("connect_four")
+    b = g.new_batch(8)
+    dev = b._dev
+    # fill column 0 on lanes 0..3 (6 stones), then a 7th drop must be rejected and leave the lane intact
+    for _ in range(6):
+        b.apply_actions(torch.tensor([0, 0, 0, 0, -1, -1, -1, -1], dtype=torch.int32, device=dev))
+    assert b.error_count()[0] == 0
+    before = [b.state_blob(i) for i in range(8)]
+    b.apply_actions(torch.tensor([0, 7, -2, 1, -1, -1, -1, -1], dtype=torch.int32, device=dev))
+    cnt, first = b.error_count()
+    assert cnt == 3 and first == 0
+    after = [b.state_blob(i) for i in range(8)]
+    assert before[0] == after[0] and before[1] == after[1] and before[2] == after[2]
+    assert before[3] != after[3]
+    assert before[4:] == after[4:]          # -1 lanes untouched
+    b.reset()
+    assert b.error_count()[0] == 0
+
+
+def test_actions_on_terminal_states_are_rejected():
+    # connect_four_test.cc:38-58 FastLoss: 3,3,4,4,2,2,1 -> x wins
+    g = b2.load_game("connect_four")
+    b = g.new_batch(4)
+    for a in [3, 3, 4, 4, 2, 2, 1]:
+        b.apply_actions(torch.full((4,), a, dtype=torch.int32, device=b._dev))
+    cur, term, rets = b.status()
+    assert term.tolist() == [1] * 4 and cur.tolist() == [-4] * 4
+    assert rets.tolist() == [[1.0, -1.0]] * 4
+    assert b.legal_actions_mask_words().flatten().tolist() == [0] * 4
+    b.apply_actions(torch.full((4,), 0, dtype=torch.int32, device=b._dev))
+    assert b.error_count()[0] == 4
+
+
+def test_scalar_state_adapter_reads_like_pyspiel():
+    game = b2.load_game("tic_tac_toe")
+    state = game.new_initial_state()
+    assert state.current_player() == 0 and not state.is_terminal()
+    assert state.legal_actions() == list(range(9))
+    state.apply_action(4)
+    assert state.legal_actions() == [0, 1, 2, 3, 5, 6, 7, 8]
+    clone = state.clone()
+    state.apply_action(0)
+    assert clone.history() == [4] and state.history() == [4, 0]
+    assert clone.legal_actions() == [0, 1, 2, 3, 5, 6, 7, 8]
+    with pytest.raises(b2.SpielError):
+        state.apply_action(4)
+    for a in [3, 1, 5]:       # x: 4,3,5 -> middle row
+        state.apply_action(a)
+    assert state.is_terminal() and state.returns() == [1.0, -1.0]
+    assert state.current_player() == -4 and state.legal_actions() == []
+    assert state.serialize() == "4\n0\n3\n1\n5\n"
+
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "playthroughs", "*.json")))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-5] for p in GOLD])
+def test_device_replays_reference_playthrough(path):
+    """The reference's own golden traces (integration_tests/playthrough_test.py:73-98), replayed on the GPU."""
+    gold = json.load(open(path, encoding="utf-8"))
+    try:
+        game = b2.load_game(gold["game"])
+        state = game.new_initial_state()
+    except b2.SpielError as e:
+        pytest.skip(str(e))
+    hdr = gold["header"]
+    assert game.num_distinct_actions() == int(hdr["NumDistinctActions"])
+    assert game.max_game_length() == int(hdr["MaxGameLength"])
+    for k, g in enumerate(gold["states"]):
+        if g["detailed"]:
+            assert state.is_terminal() == g["is_terminal"]
+            assert state.current_player() == g["current_player"]
+            assert state.history() == g["history"]
+            if "legal_actions" in g:
+                assert state.legal_actions() == g["legal_actions"]
+            if "returns" in g:
+                r = state.returns()
+                assert r == g["returns"]
+                assert [np.signbit(x) for x in r] == [t.startswith("-") for t in g["returns_text"]]
+            for name, vals in g["tensors"].items():
+                p = int(name[name.index("(") + 1:name.index(")")])
+                t = state.observation_tensor(p) if name.startswith("Observation") else state.information_state_tensor(p)
+                np.testing.assert_array_equal(t, np.array(vals, dtype=np.float32), err_msg=name)
+        if k < len(gold["actions"]):
+            state.apply_action(gold["actions"][k])
+    assert state.is_terminal()
+
+
+def test_rollout_matches_oracle_given_same_random_stream():
+    """b2s_rollout = uniform-random playout; the oracle replays it with the same Philox words."""
+    from philox_ref import philox_uniform
+    for gs in ["connect_four", "tic_tac_toe", "breakthrough"]:
+        game = b2.load_game(gs)
+        n = 256
+        b = game.new_batch(n)
+        rets, plies = b.rollout(seed=0x5EED, lane_offset=1000)
+        rets, plies = rets.cpu().numpy(), plies.cpu().numpy()
+        og = OracleGame(gs)
+        for i in range(n):
+            st = og.new_initial_state()
+            ply = 0
+            while not st.is_terminal():
+                la = st.legal_actions()
+                st.apply_action(la[philox_uniform(0x5EED, 1000 + i, ply, len(la))])
+                ply += 1
+            assert ply == plies[i], (gs, i)
+            assert st.returns() == rets[i].tolist(), (gs, i)
+        _, term, rets2 = b.status()
+        assert term.all() and np.array_equal(rets2.cpu().numpy(), rets)
+
+
+def test_full_size_properties_connect_four():
+    """BASELINE config 2 size (1M lanes): size-independent properties."""
+    game = b2.load_game("connect_four")
+    n = 1 << 20
+    b = game.new_batch(n)
+    rets, plies = b.rollout(seed=7)
+    cur, term, rets2 = b.status()
+    assert bool(term.all()) and bool((cur == -4).all())
+    assert torch.equal(rets, rets2)
+    assert bool((rets.sum(dim=1) == 0).all())                       # zero-sum
+    assert int(plies.min()) >= 7 and int(plies.max()) <= 42         # shortest win is 7 plies
+    draws = (rets[:, 0] == 0)
+    assert bool((plies[draws] == 42).all())                         # draws only on a full board
+    assert int(b.legal_actions_mask_words().abs().sum()) == 0
+    # a deterministic replay of the same seed gives bit-identical states
+    b2_ = game.new_batch(n)
+    b2_.rollout(seed=7)
+    assert torch.equal(b.observation_tensor(0, n=4096), b2_.observation_tensor(0, n=4096))
+    # observation planes partition the board: exactly one plane set per cell
+    obs = b.observation_tensor(0, n=65536).reshape(-1, 3, 42)
+    assert bool((obs.sum(dim=1) == 1).all())
