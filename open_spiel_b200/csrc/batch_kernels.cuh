@@ -24,31 +24,49 @@ __global__ void __launch_bounds__(kBlock) k_reset(Ctx ctx, typename R::Cfg cfg, 
   R::store(s, ctx, i);
 }
 
-// State::ApplyAction over the batch (spiel.cc:441-451).
-template <class R>
+// State::ApplyAction over the batch (spiel.cc:441-451).  Each thread owns ILP lanes, block-strided so every
+// access stays coalesced; all loads (action + packed state) are issued before any compute so that a thread
+// has ILP independent 128-bit requests in flight (the kernel is a pure HBM stream).
+template <class R, int ILP>
 __global__ void __launch_bounds__(kBlock) k_apply(Ctx ctx, typename R::Cfg cfg, const int* __restrict__ actions, long long n) {
-  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  int a = __ldg(actions + i);
-  if (a == -1) return;
-  typename R::S s;
-  R::load(s, ctx, i);
-  if (R::terminal(s, cfg) || !R::apply(s, a, cfg, ctx, i)) { flag_error(ctx.err, i); return; }
-  R::store(s, ctx, i);
+  long long base = (long long)blockIdx.x * (kBlock * ILP) + threadIdx.x;
+  int a[ILP];
+  typename R::S s[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    a[j] = -1;
+    if (i < n) { a[j] = __ldg(actions + i); R::load(s[j], ctx, i); }
+  }
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    if (a[j] == -1) continue;
+    if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) { flag_error(ctx.err, i); continue; }
+    R::store(s[j], ctx, i);
+  }
 }
 
-template <class R>
+template <class R, int ILP>
 __global__ void __launch_bounds__(kBlock) k_legal_mask(Ctx ctx, typename R::Cfg cfg, u32* __restrict__ mask, int mask_words, long long n) {
-  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  typename R::S s;
-  R::load(s, ctx, i);
-  u32 m[R::kMaskWords];
-  R::legal(s, cfg, m);
-  if (R::kMaskWords == 1) {
-    mask[i] = m[0];
-  } else {
-    for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+  long long base = (long long)blockIdx.x * (kBlock * ILP) + threadIdx.x;
+  typename R::S s[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    if (i < n) R::load(s[j], ctx, i);
+  }
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    if (i >= n) continue;
+    u32 m[R::kMaskWords];
+    R::legal(s[j], cfg, m);
+    if (R::kMaskWords == 1) {
+      mask[i] = m[0];
+    } else {
+      for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+    }
   }
 }
 
@@ -73,49 +91,66 @@ __global__ void __launch_bounds__(kBlock) k_legal_list(Ctx ctx, typename R::Cfg 
   counts[i] = k;
 }
 
-template <class R>
+template <class R, int ILP>
 __global__ void __launch_bounds__(kBlock) k_status(Ctx ctx, typename R::Cfg cfg, signed char* __restrict__ cur, unsigned char* __restrict__ term, float* __restrict__ rets, long long n) {
-  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  typename R::S s;
-  R::load(s, ctx, i);
-  int cp = R::cur_player(s, cfg);
-  if (cur) cur[i] = (signed char)cp;
-  if (term) term[i] = cp == kTerminalPlayerId ? 1 : 0;
-  if (rets) {
-    float r[R::kPlayers];
-    R::returns(s, cfg, r);
-    if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
-    else for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+  long long base = (long long)blockIdx.x * (kBlock * ILP) + threadIdx.x;
+  typename R::S s[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    if (i < n) R::load(s[j], ctx, i);
+  }
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    if (i >= n) continue;
+    int cp = R::cur_player(s[j], cfg);
+    if (cur) cur[i] = (signed char)cp;
+    if (term) term[i] = cp == kTerminalPlayerId ? 1 : 0;
+    if (rets) {
+      float r[R::kPlayers];
+      R::returns(s[j], cfg, r);
+      if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
+      else for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+    }
   }
 }
 
 // ApplyAction + IsTerminal + Returns + next LegalActionsMask in one pass.
-template <class R>
+template <class R, int ILP>
 __global__ void __launch_bounds__(kBlock) k_step_fused(Ctx ctx, typename R::Cfg cfg, const int* __restrict__ actions, u32* __restrict__ mask, int mask_words, unsigned char* __restrict__ term, float* __restrict__ rets, long long n) {
-  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
-  int a = __ldg(actions + i);
-  typename R::S s;
-  R::load(s, ctx, i);
-  if (a != -1) {
-    if (R::terminal(s, cfg) || !R::apply(s, a, cfg, ctx, i)) flag_error(ctx.err, i);
-    else R::store(s, ctx, i);
+  long long base = (long long)blockIdx.x * (kBlock * ILP) + threadIdx.x;
+  int a[ILP];
+  typename R::S s[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    a[j] = -1;
+    if (i < n) { a[j] = __ldg(actions + i); R::load(s[j], ctx, i); }
   }
-  bool t = R::terminal(s, cfg);
-  if (term) term[i] = t ? 1 : 0;
-  if (rets) {
-    float r[R::kPlayers];
-    R::returns(s, cfg, r);
-    if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
-    else for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
-  }
-  if (mask) {
-    u32 m[R::kMaskWords];
-    if (t) { for (int w = 0; w < R::kMaskWords; ++w) m[w] = 0; }
-    else R::legal_nonterminal(s, cfg, m);
-    if (R::kMaskWords == 1) mask[i] = m[0];
-    else for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    if (i >= n) continue;
+    if (a[j] != -1) {
+      if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) flag_error(ctx.err, i);
+      else R::store(s[j], ctx, i);
+    }
+    bool t = R::terminal(s[j], cfg);
+    if (term) term[i] = t ? 1 : 0;
+    if (rets) {
+      float r[R::kPlayers];
+      R::returns(s[j], cfg, r);
+      if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
+      else for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+    }
+    if (mask) {
+      u32 m[R::kMaskWords];
+      if (t) { for (int w = 0; w < R::kMaskWords; ++w) m[w] = 0; }
+      else R::legal_nonterminal(s[j], cfg, m);
+      if (R::kMaskWords == 1) mask[i] = m[0];
+      else for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+    }
   }
 }
 
@@ -231,7 +266,7 @@ struct GameOps {
   b2s_game_info info;
 };
 
-inline unsigned grid_for(long long n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+inline unsigned grid_for(long long n, int ilp = 1) { return (unsigned)((n + (long long)kBlock * ilp - 1) / ((long long)kBlock * ilp)); }
 
 // magic M with floor(e*M >> 32) == e / d for all 0 <= e < limit (checked exhaustively).
 inline bool make_magic(int d, int limit, u32* out) {
@@ -265,11 +300,11 @@ struct GameOpsT : GameOps {
   }
   void apply(const Ctx& c, const int* a, long long n, cudaStream_t st) override {
     if (n <= 0) return;
-    k_apply<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, a, n); ++g_launches;
+    k_apply<R, R::kIlp><<<grid_for(n, R::kIlp), kBlock, 0, st>>>(c, cfg, a, n); ++g_launches;
   }
   void legal_mask(const Ctx& c, u32* m, long long n, cudaStream_t st) override {
     if (n <= 0) return;
-    k_legal_mask<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, m, info.mask_words, n); ++g_launches;
+    k_legal_mask<R, R::kIlp><<<grid_for(n, R::kIlp), kBlock, 0, st>>>(c, cfg, m, info.mask_words, n); ++g_launches;
   }
   void legal_list(const Ctx& c, short* out, int* counts, int stride, long long n, cudaStream_t st) override {
     if (n <= 0) return;
@@ -277,7 +312,7 @@ struct GameOpsT : GameOps {
   }
   void status(const Ctx& c, signed char* cur, unsigned char* term, float* rets, long long n, cudaStream_t st) override {
     if (n <= 0) return;
-    k_status<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, cur, term, rets, n); ++g_launches;
+    k_status<R, R::kIlp><<<grid_for(n, R::kIlp), kBlock, 0, st>>>(c, cfg, cur, term, rets, n); ++g_launches;
   }
   const char* obs(const Ctx& c, int player, int which, float* out, long long n, cudaStream_t st) override {
     int size = which == 0 ? info.observation_tensor_size : info.information_state_tensor_size;
@@ -291,7 +326,7 @@ struct GameOpsT : GameOps {
   }
   void step_fused(const Ctx& c, const int* a, u32* m, unsigned char* term, float* rets, long long n, cudaStream_t st) override {
     if (n <= 0) return;
-    k_step_fused<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, a, m, info.mask_words, term, rets, n); ++g_launches;
+    k_step_fused<R, R::kIlp><<<grid_for(n, R::kIlp), kBlock, 0, st>>>(c, cfg, a, m, info.mask_words, term, rets, n); ++g_launches;
   }
   void rollout(const Ctx& c, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t st) override {
     if (n <= 0) return;

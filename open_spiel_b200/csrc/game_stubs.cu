@@ -1,8 +1,5 @@
 // Games whose device rule cores are not built yet return no ops table (b2s_batch_create fails loudly).
 #include "batch_kernels.cuh"
 namespace b2s {
-GameOps* make_ops_hex() { return nullptr; }
 GameOps* make_ops_go() { return nullptr; }
-GameOps* make_ops_kuhn_poker() { return nullptr; }
-GameOps* make_ops_leduc_poker() { return nullptr; }
 }  // namespace b2s

@@ -15,6 +15,7 @@ struct BreakthroughRules {
   static constexpr int kMaskWords = 24;   // 64 cells * 12
   static constexpr int kObsWords = 3;
   static constexpr int kPlayers = 2;
+  static constexpr int kIlp = 2;      // lanes per thread in the streaming kernels
   static constexpr bool kHasInfoState = false;
 
   struct Cfg {
@@ -56,15 +57,15 @@ struct BreakthroughRules {
     return nullptr;
   }
   __device__ static __forceinline__ void load(S& s, const Ctx& ctx, long long i) {
-    uint4 v = reinterpret_cast<const uint4*>(ctx.planes)[i];
-    s.b = ((u64)v.y << 32) | v.x;
-    u64 w = ((u64)v.w << 32) | v.z;
+    ulonglong2 v = reinterpret_cast<const ulonglong2*>(ctx.planes)[i];   // one 128-bit load
+    s.b = v.x;
+    u64 w = v.y;
     s.mover = (s.b & w) != 0 ? 1 : 0;
     s.w = s.mover ? ~w : w;
   }
   __device__ static __forceinline__ void store(const S& s, const Ctx& ctx, long long i) {
     u64 w = s.mover ? ~s.w : s.w;
-    reinterpret_cast<uint4*>(ctx.planes)[i] = make_uint4((u32)s.b, (u32)(s.b >> 32), (u32)w, (u32)(w >> 32));
+    reinterpret_cast<ulonglong2*>(ctx.planes)[i] = make_ulonglong2(s.b, w);
   }
   __device__ static __forceinline__ void init(S& s, const Cfg& c, const Ctx&, long long) { s.b = c.init_black; s.w = c.init_white; s.mover = 0; }
   __device__ static __forceinline__ void copy_history(const Ctx&, long long, const Ctx&, long long, const S&, const Cfg&) {}

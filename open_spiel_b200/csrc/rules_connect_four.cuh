@@ -15,6 +15,7 @@ struct ConnectFourRules {
   static constexpr int kMaskWords = 1;
   static constexpr int kObsWords = 3;  // 3*rows*cols <= 189 bits
   static constexpr int kPlayers = 2;
+  static constexpr int kIlp = 8;      // lanes per thread in the streaming kernels
   static constexpr bool kHasInfoState = false;
 
   struct Cfg {
@@ -51,12 +52,12 @@ struct ConnectFourRules {
   }
 
   __device__ static __forceinline__ void load(S& s, const Ctx& ctx, long long i) {
-    uint4 v = reinterpret_cast<const uint4*>(ctx.planes)[i];
-    s.x = ((u64)v.y << 32) | v.x;
-    s.o = ((u64)v.w << 32) | v.z;
+    ulonglong2 v = reinterpret_cast<const ulonglong2*>(ctx.planes)[i];   // one 128-bit load
+    s.x = v.x;
+    s.o = v.y;
   }
   __device__ static __forceinline__ void store(const S& s, const Ctx& ctx, long long i) {
-    reinterpret_cast<uint4*>(ctx.planes)[i] = make_uint4((u32)s.x, (u32)(s.x >> 32), (u32)s.o, (u32)(s.o >> 32));
+    reinterpret_cast<ulonglong2*>(ctx.planes)[i] = make_ulonglong2(s.x, s.o);
   }
   __device__ static __forceinline__ void init(S& s, const Cfg&, const Ctx&, long long) { s.x = 0; s.o = 0; }
   __device__ static __forceinline__ void copy_history(const Ctx&, long long, const Ctx&, long long, const S&, const Cfg&) {}

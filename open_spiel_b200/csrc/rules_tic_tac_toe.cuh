@@ -14,6 +14,7 @@ struct TicTacToeRules {
   static constexpr int kMaskWords = 1;
   static constexpr int kObsWords = 1;
   static constexpr int kPlayers = 2;
+  static constexpr int kIlp = 4;      // lanes per thread in the streaming kernels
   static constexpr bool kHasInfoState = false;
   struct Cfg { int dummy; };
   struct S { u32 b; };

@@ -1,0 +1,161 @@
+// TEST INFRASTRUCTURE ONLY.  Our own C ABI over the UNMODIFIED reference (open_spiel::Game / State /
+// MCTSBot / CFRSolver), built by oracle/ref_build.mk into oracle/_ref/libspiel_ref_c.so.  It mirrors the
+// orc_* surface of oracle/oracle_c.cc so tests can drive the restatement and the real reference alike.
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "open_spiel/algorithms/cfr.h"
+#include "open_spiel/algorithms/mcts.h"
+#include "open_spiel/algorithms/tabular_exploitability.h"
+#include "open_spiel/spiel.h"
+#include "open_spiel/spiel_utils.h"
+
+using open_spiel::Action;
+using open_spiel::Game;
+using open_spiel::State;
+
+namespace {
+struct GameHolder { std::shared_ptr<const Game> game; };
+thread_local std::string g_err;
+void ThrowingHandler(const std::string& msg) { throw std::runtime_error(msg); }
+struct Init { Init() { open_spiel::SetErrorHandler(ThrowingHandler); } } g_init;
+
+int CopyStr(const std::string& s, char* buf, int cap) {
+  int n = (int)s.size();
+  if (buf && cap > 0) { int m = n < cap - 1 ? n : cap - 1; memcpy(buf, s.data(), m); buf[m] = 0; }
+  return n;
+}
+}  // namespace
+
+#define GUARD(stmt, onerr) try { stmt; } catch (const std::exception& e) { g_err = e.what(); onerr; }
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+void* ref_load_game(const char* game_string) {
+  GUARD(return new GameHolder{open_spiel::LoadGame(std::string(game_string))}, return nullptr);
+}
+void ref_free_game(void* g) { delete (GameHolder*)g; }
+int ref_num_distinct_actions(void* g) { return ((GameHolder*)g)->game->NumDistinctActions(); }
+int ref_num_players(void* g) { return ((GameHolder*)g)->game->NumPlayers(); }
+int ref_max_game_length(void* g) { return ((GameHolder*)g)->game->MaxGameLength(); }
+int ref_max_chance_outcomes(void* g) { return ((GameHolder*)g)->game->MaxChanceOutcomes(); }
+int ref_observation_tensor_size(void* g) { GUARD(return ((GameHolder*)g)->game->ObservationTensorSize(), return 0); }
+int ref_information_state_tensor_size(void* g) {
+  auto& game = ((GameHolder*)g)->game;
+  if (!game->GetType().provides_information_state_tensor) return 0;
+  GUARD(return game->InformationStateTensorSize(), return 0);
+}
+double ref_min_utility(void* g) { return ((GameHolder*)g)->game->MinUtility(); }
+double ref_max_utility(void* g) { return ((GameHolder*)g)->game->MaxUtility(); }
+
+void* ref_new_initial_state(void* g) { GUARD(return ((GameHolder*)g)->game->NewInitialState().release(), return nullptr); }
+void* ref_clone(void* s) { return ((State*)s)->Clone().release(); }
+void ref_free_state(void* s) { delete (State*)s; }
+int ref_current_player(void* s) { return ((State*)s)->CurrentPlayer(); }
+int ref_is_terminal(void* s) { return ((State*)s)->IsTerminal() ? 1 : 0; }
+int ref_legal_actions(void* s, int64_t* out, int cap) {
+  std::vector<Action> v;
+  GUARD(v = ((State*)s)->LegalActions(), return -1);
+  for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+  return (int)v.size();
+}
+int ref_apply_action(void* s, int64_t a) { GUARD(((State*)s)->ApplyAction(a); return 0, return 1); }
+void ref_returns(void* s, double* out) {
+  auto v = ((State*)s)->Returns();
+  for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+}
+int ref_observation_tensor(void* s, int player, float* out, int n) {
+  GUARD(((State*)s)->ObservationTensor(player, absl::MakeSpan(out, n)); return 0, return 1);
+}
+int ref_information_state_tensor(void* s, int player, float* out, int n) {
+  GUARD(((State*)s)->InformationStateTensor(player, absl::MakeSpan(out, n)); return 0, return 1);
+}
+int ref_to_string(void* s, char* buf, int cap) { GUARD(return CopyStr(((State*)s)->ToString(), buf, cap), return -1); }
+int ref_information_state_string(void* s, int player, char* buf, int cap) {
+  GUARD(return CopyStr(((State*)s)->InformationStateString(player), buf, cap), return -1);
+}
+int ref_observation_string(void* s, int player, char* buf, int cap) {
+  GUARD(return CopyStr(((State*)s)->ObservationString(player), buf, cap), return -1);
+}
+int ref_chance_outcomes(void* s, int64_t* actions, double* probs, int cap) {
+  std::vector<std::pair<Action, double>> v;
+  GUARD(v = ((State*)s)->ChanceOutcomes(), return -1);
+  for (int i = 0; i < (int)v.size() && i < cap; ++i) { actions[i] = v[i].first; probs[i] = v[i].second; }
+  return (int)v.size();
+}
+int ref_history(void* s, int64_t* out, int cap) {
+  auto h = ((State*)s)->History();
+  for (int i = 0; i < (int)h.size() && i < cap; ++i) out[i] = h[i];
+  return (int)h.size();
+}
+
+// ---- CFRSolver (algorithms/cfr.h:312-328) -----------------------------------------------------------------
+void* ref_cfr_new(void* g) { GUARD(return new open_spiel::algorithms::CFRSolver(*((GameHolder*)g)->game), return nullptr); }
+void ref_cfr_free(void* c) { delete (open_spiel::algorithms::CFRSolver*)c; }
+int ref_cfr_iterate(void* c, int iters) {
+  GUARD(for (int i = 0; i < iters; ++i) ((open_spiel::algorithms::CFRSolver*)c)->EvaluateAndUpdatePolicy(); return 0, return 1);
+}
+int ref_cfr_num_infostates(void* c) { return (int)((open_spiel::algorithms::CFRSolver*)c)->InfoStateValuesTable().size(); }
+// Table entry for an info-state key: copies up to cap values of each array; returns the number of legal actions, -1 if absent.
+int ref_cfr_get(void* c, const char* key, int64_t* legal, double* regrets, double* cum_policy, double* cur_policy, int cap) {
+  auto& table = ((open_spiel::algorithms::CFRSolver*)c)->InfoStateValuesTable();
+  auto it = table.find(key);
+  if (it == table.end()) return -1;
+  const auto& v = it->second;
+  int n = (int)v.legal_actions.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    legal[i] = v.legal_actions[i];
+    regrets[i] = v.cumulative_regrets[i];
+    cum_policy[i] = v.cumulative_policy[i];
+    cur_policy[i] = v.current_policy[i];
+  }
+  return n;
+}
+// All keys, '\n'-separated (sorted).
+int ref_cfr_keys(void* c, char* buf, int cap) {
+  auto& table = ((open_spiel::algorithms::CFRSolver*)c)->InfoStateValuesTable();
+  std::vector<std::string> keys;
+  for (auto& kv : table) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end());
+  std::string s;
+  for (auto& k : keys) { s += k; s += '\n'; }
+  return CopyStr(s, buf, cap);
+}
+double ref_cfr_exploitability(void* g, void* c) {
+  auto* solver = (open_spiel::algorithms::CFRSolver*)c;
+  GUARD(return open_spiel::algorithms::Exploitability(*((GameHolder*)g)->game, *solver->AveragePolicy()), return -1.0);
+}
+double ref_cfr_nash_conv(void* g, void* c) {
+  auto* solver = (open_spiel::algorithms::CFRSolver*)c;
+  GUARD(return open_spiel::algorithms::NashConv(*((GameHolder*)g)->game, *solver->AveragePolicy()), return -1.0);
+}
+
+// ---- MCTSBot (algorithms/mcts.h:149-230) --------------------------------------------------------------------
+// Runs MCTSearch from `state` and reports the root's children (action, visits, total reward, proven outcome flag).
+int ref_mcts_search(void* g, void* state, double uct_c, int max_simulations, int n_rollouts, int solve, int seed,
+                    int64_t* child_actions, int* child_visits, double* child_rewards, int cap, int64_t* best_action,
+                    int* root_visits) {
+  try {
+    auto game = ((GameHolder*)g)->game;
+    auto evaluator = std::make_shared<open_spiel::algorithms::RandomRolloutEvaluator>(n_rollouts, seed);
+    open_spiel::algorithms::MCTSBot bot(*game, evaluator, uct_c, max_simulations, /*max_memory_mb=*/1000, solve != 0, seed,
+                                        /*verbose=*/false);
+    std::unique_ptr<open_spiel::algorithms::SearchNode> root = bot.MCTSearch(*(State*)state);
+    int n = (int)root->children.size();
+    for (int i = 0; i < n && i < cap; ++i) {
+      child_actions[i] = root->children[i].action;
+      child_visits[i] = root->children[i].explore_count;
+      child_rewards[i] = root->children[i].total_reward;
+    }
+    if (best_action) *best_action = root->BestChild().action;
+    if (root_visits) *root_visits = root->explore_count;
+    return n;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+}  // extern "C"

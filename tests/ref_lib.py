@@ -1,0 +1,155 @@
+"""ctypes binding of oracle/_ref/libspiel_ref_c.so — the UNMODIFIED reference compiled against the abseil
+shim (oracle/ref_build.mk).  Same Python surface as oracle_lib.OracleGame/OracleState.  Test infrastructure."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "oracle", "_ref", "libspiel_ref_c.so")
+_LIB = None
+
+
+def available():
+    return os.path.exists(SO)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(SO)
+        vp, i64p, dp, fp, cp = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_char_p
+        L.ref_last_error.restype = cp
+        L.ref_load_game.restype = vp
+        L.ref_load_game.argtypes = [cp]
+        L.ref_free_game.argtypes = [vp]
+        for f in ("ref_num_distinct_actions", "ref_num_players", "ref_max_game_length", "ref_max_chance_outcomes",
+                  "ref_observation_tensor_size", "ref_information_state_tensor_size"):
+            getattr(L, f).argtypes = [vp]
+        for f in ("ref_min_utility", "ref_max_utility"):
+            getattr(L, f).restype = C.c_double
+            getattr(L, f).argtypes = [vp]
+        L.ref_new_initial_state.restype = vp
+        L.ref_new_initial_state.argtypes = [vp]
+        L.ref_clone.restype = vp
+        L.ref_clone.argtypes = [vp]
+        L.ref_free_state.argtypes = [vp]
+        L.ref_current_player.argtypes = [vp]
+        L.ref_is_terminal.argtypes = [vp]
+        L.ref_legal_actions.argtypes = [vp, i64p, C.c_int]
+        L.ref_apply_action.argtypes = [vp, C.c_int64]
+        L.ref_returns.argtypes = [vp, dp]
+        L.ref_observation_tensor.argtypes = [vp, C.c_int, fp, C.c_int]
+        L.ref_information_state_tensor.argtypes = [vp, C.c_int, fp, C.c_int]
+        L.ref_to_string.argtypes = [vp, cp, C.c_int]
+        L.ref_information_state_string.argtypes = [vp, C.c_int, cp, C.c_int]
+        L.ref_observation_string.argtypes = [vp, C.c_int, cp, C.c_int]
+        L.ref_chance_outcomes.argtypes = [vp, i64p, dp, C.c_int]
+        L.ref_history.argtypes = [vp, i64p, C.c_int]
+        L.ref_cfr_new.restype = vp
+        L.ref_cfr_new.argtypes = [vp]
+        L.ref_cfr_free.argtypes = [vp]
+        L.ref_cfr_iterate.argtypes = [vp, C.c_int]
+        L.ref_cfr_num_infostates.argtypes = [vp]
+        L.ref_cfr_get.argtypes = [vp, cp, i64p, dp, dp, dp, C.c_int]
+        L.ref_cfr_keys.argtypes = [vp, cp, C.c_int]
+        L.ref_cfr_exploitability.restype = C.c_double
+        L.ref_cfr_exploitability.argtypes = [vp, vp]
+        L.ref_cfr_nash_conv.restype = C.c_double
+        L.ref_cfr_nash_conv.argtypes = [vp, vp]
+        L.ref_mcts_search.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, i64p,
+                                      C.POINTER(C.c_int), dp, C.c_int, i64p, C.POINTER(C.c_int)]
+        _LIB = L
+    return _LIB
+
+
+class RefGame:
+    def __init__(self, game_string):
+        L = lib()
+        self._g = L.ref_load_game(game_string.encode())
+        if not self._g:
+            raise ValueError("reference: " + L.ref_last_error().decode())
+        self.name = game_string.split("(")[0]
+        self.num_distinct_actions = L.ref_num_distinct_actions(self._g)
+        self.num_players = L.ref_num_players(self._g)
+        self.max_game_length = L.ref_max_game_length(self._g)
+        self.max_chance_outcomes = L.ref_max_chance_outcomes(self._g)
+        self.observation_tensor_size = L.ref_observation_tensor_size(self._g)
+        self.information_state_tensor_size = L.ref_information_state_tensor_size(self._g)
+
+    def new_initial_state(self):
+        return RefState(self, lib().ref_new_initial_state(self._g))
+
+
+class RefState:
+    def __init__(self, game, ptr):
+        self.game, self._s = game, ptr
+
+    def __del__(self):
+        try:
+            lib().ref_free_state(self._s)
+        except Exception:
+            pass
+
+    def clone(self):
+        return RefState(self.game, lib().ref_clone(self._s))
+
+    def current_player(self):
+        return lib().ref_current_player(self._s)
+
+    def is_terminal(self):
+        return bool(lib().ref_is_terminal(self._s))
+
+    def is_chance_node(self):
+        return self.current_player() == -1
+
+    def legal_actions(self):
+        cap = max(self.game.num_distinct_actions, self.game.max_chance_outcomes, 1) + 8
+        buf = (C.c_int64 * cap)()
+        n = lib().ref_legal_actions(self._s, buf, cap)
+        return list(buf[:n])
+
+    def apply_action(self, a):
+        if lib().ref_apply_action(self._s, int(a)):
+            raise RuntimeError("reference: " + lib().ref_last_error().decode())
+
+    def returns(self):
+        buf = (C.c_double * self.game.num_players)()
+        lib().ref_returns(self._s, buf)
+        return list(buf)
+
+    def observation_tensor(self, player=0):
+        out = np.zeros(self.game.observation_tensor_size, dtype=np.float32)
+        lib().ref_observation_tensor(self._s, player, out.ctypes.data_as(C.POINTER(C.c_float)), out.size)
+        return out
+
+    def information_state_tensor(self, player=0):
+        out = np.zeros(self.game.information_state_tensor_size, dtype=np.float32)
+        lib().ref_information_state_tensor(self._s, player, out.ctypes.data_as(C.POINTER(C.c_float)), out.size)
+        return out
+
+    def _str(self, fn, *args):
+        buf = C.create_string_buffer(8192)
+        fn(self._s, *args, buf, 8192)
+        return buf.value.decode()
+
+    def to_string(self):
+        return self._str(lib().ref_to_string)
+
+    def information_state_string(self, player=0):
+        return self._str(lib().ref_information_state_string, player)
+
+    def observation_string(self, player=0):
+        return self._str(lib().ref_observation_string, player)
+
+    def chance_outcomes(self):
+        cap = self.game.max_chance_outcomes + 8
+        a = (C.c_int64 * cap)()
+        p = (C.c_double * cap)()
+        n = lib().ref_chance_outcomes(self._s, a, p, cap)
+        return [(a[i], p[i]) for i in range(n)]
+
+    def history(self):
+        buf = (C.c_int64 * 2048)()
+        n = lib().ref_history(self._s, buf, 2048)
+        return list(buf[:n])

@@ -23,12 +23,22 @@ GAMES = [
     ("breakthrough", 256),
     ("breakthrough(rows=6,columns=6)", 128),
     ("breakthrough(rows=5,columns=4)", 128),
+    ("hex", 128),
+    ("hex(board_size=5)", 256),
+    ("hex(num_cols=4,num_rows=3)", 128),
+    ("hex(board_size=4,swap=True)", 256),
+    ("hex(board_size=5,plain_obs_tensor=True)", 64),
+    ("hex(num_cols=5,num_rows=3,plain_obs_tensor=True)", 64),
+    ("kuhn_poker", 512),
+    ("leduc_poker", 1024),
+    ("leduc_poker(starting_player=1)", 256),
 ]
+INFO_STATE = {"kuhn_poker", "leduc_poker", "leduc_poker(starting_player=1)"}
 
 
 @pytest.mark.parametrize("game_string,lanes", GAMES, ids=[g for g, _ in GAMES])
 def test_lockstep_random_games(game_string, lanes):
-    steps = lockstep(game_string, n_lanes=lanes, seed=1234)
+    steps = lockstep(game_string, n_lanes=lanes, seed=1234, check_info_state=game_string in INFO_STATE)
     assert steps > lanes
 
 
