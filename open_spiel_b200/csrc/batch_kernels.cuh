@@ -179,13 +179,13 @@ __global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, in
   int nvec = total >> 2;
   for (int q = lane; q < nvec; q += 32) {
     int e0 = q << 2;
+    int st = (int)(((u64)e0 * magic) >> 32);         // e0 / size (magic verified on the host for the range)
+    int within = e0 - st * size;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int e = e0 + j;
-      int st = (int)(((u64)e * magic) >> 32);        // e / size (magic verified on the host for the range)
-      int within = e - st * size;
       v[j] = R::obs_elem(wp[st], cfg, within);
+      if (++within == size) { within = 0; ++st; }     // a float4 may straddle two lanes' tensors
     }
     reinterpret_cast<float4*>(base)[q] = make_float4(v[0], v[1], v[2], v[3]);
   }

@@ -197,40 +197,44 @@ struct HexRules {
   }
   // Observation planes by label value + 4 (hex.h:68-78, hex.cc:392-396):
   // 0 WhiteWin, 1 WhiteWest, 2 WhiteEast, 3 White, 4 Empty, 5 Black, 6 BlackSouth, 7 BlackNorth, 8 BlackWin.
-  struct ObsPack { B128 pl[9]; };
+  struct ObsPack { u64 w[18]; };      // plane k = words 2k (cells 0-63), 2k+1 (cells 64-127)
+  __device__ static __forceinline__ void put(ObsPack& p, int k, B128 v) { p.w[2 * k] = v.lo; p.w[2 * k + 1] = v.hi; }
   __device__ static __forceinline__ void obs_pack(const S& s, const Cfg& c, int, int, ObsPack& p) {
     B128 both = b_and(s.la, s.lb), onlyA = b_andn(s.la, s.lb), onlyB = b_andn(s.lb, s.la), any = b_or(s.la, s.lb);
+    B128 empty = b_andn(c.board, b_or(s.black, s.white)), z = {0, 0};
     if (c.plain) {            // CellStateToPlainPlane, hex.cc:76-93: 0 black, 1 white, 2 empty
-      p.pl[0] = s.black; p.pl[1] = s.white; p.pl[2] = b_andn(c.board, b_or(s.black, s.white));
+      put(p, 0, s.black); put(p, 1, s.white); put(p, 2, empty);
+      for (int k = 3; k < 9; ++k) put(p, k, z);
       return;
     }
-    p.pl[0] = b_and(s.white, both);
-    p.pl[1] = b_and(s.white, onlyA);
-    p.pl[2] = b_and(s.white, onlyB);
-    p.pl[3] = b_andn(s.white, any);
-    p.pl[4] = b_andn(c.board, b_or(s.black, s.white));
-    p.pl[5] = b_andn(s.black, any);
-    p.pl[6] = b_and(s.black, onlyB);
-    p.pl[7] = b_and(s.black, onlyA);
-    p.pl[8] = b_and(s.black, both);
+    put(p, 0, b_and(s.white, both));
+    put(p, 1, b_and(s.white, onlyA));
+    put(p, 2, b_and(s.white, onlyB));
+    put(p, 3, b_andn(s.white, any));
+    put(p, 4, empty);
+    put(p, 5, b_andn(s.black, any));
+    put(p, 6, b_and(s.black, onlyB));
+    put(p, 7, b_and(s.black, onlyA));
+    put(p, 8, b_and(s.black, both));
+  }
+  __device__ static __forceinline__ u32 bit_at(const ObsPack& p, int plane, int cell) {
+    return (u32)(p.w[2 * plane + (cell >> 6)] >> (cell & 63)) & 1u;
   }
   __device__ static __forceinline__ float obs_elem(const ObsPack& p, const Cfg& c, int e) {
+    int plane = (int)(((u64)(u32)e * c.cells_magic) >> 32);
+    int w = e - plane * c.cells;
     if (c.plain) {
       // TensorView<3>{3, num_cols, num_rows} indexed {plane, cell / num_cols, cell % num_cols} (hex.cc:383-388):
       // offset = plane*cells + a*num_rows + b with a = cell / num_cols (< rows), b = cell % num_cols (< cols).
       // On non-square boards several cells alias one offset; the reference stores 1.0 for each, so OR them.
-      int plane = (int)(((u64)e * c.cells_magic) >> 32);
-      int w = e - plane * c.cells;
-      bool on = false;
+      u32 on = 0;
       for (int a = 0; a < c.rows; ++a) {
         int b = w - a * c.rows;
-        if (b >= 0 && b < c.cols) on |= b_test(p.pl[plane], a * c.cols + b);
+        if (b >= 0 && b < c.cols) on |= bit_at(p, plane, a * c.cols + b);
       }
       return on ? 1.f : 0.f;
     }
-    int plane = (int)(((u64)e * c.cells_magic) >> 32);
-    int cell = e - plane * c.cells;
-    return b_test(p.pl[plane], cell) ? 1.f : 0.f;
+    return bit_at(p, plane, w) ? 1.f : 0.f;
   }
 };
 
