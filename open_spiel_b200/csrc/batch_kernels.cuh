@@ -12,6 +12,28 @@ constexpr int kBlock = 256;
 
 extern long long g_launches;   // api.cu
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor drains; pdl_wait() blocks until the predecessor has fully
+// completed and flushed (so data dependencies between consecutive steps stay intact), pdl_launch_dependents()
+// lets the successor's CTAs be scheduled as soon as this grid has issued its loads.  Both are no-ops when the
+// kernel was launched normally.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kBlock);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- kernels -------------------------------------------------------------------------------------
 
 template <class R>
@@ -29,6 +51,7 @@ __global__ void __launch_bounds__(kBlock) k_reset(Ctx ctx, typename R::Cfg cfg, 
 // has ILP independent 128-bit requests in flight (the kernel is a pure HBM stream).
 template <class R, int ILP>
 __global__ void __launch_bounds__(kBlock) k_apply(Ctx ctx, typename R::Cfg cfg, const int* __restrict__ actions, long long n) {
+  pdl_wait();
   long long base = (long long)blockIdx.x * (kBlock * ILP) + threadIdx.x;
   int a[ILP];
   typename R::S s[ILP];
@@ -38,6 +61,7 @@ __global__ void __launch_bounds__(kBlock) k_apply(Ctx ctx, typename R::Cfg cfg, 
     a[j] = -1;
     if (i < n) { a[j] = __ldg(actions + i); R::load(s[j], ctx, i); }
   }
+  pdl_launch_dependents();
 #pragma unroll
   for (int j = 0; j < ILP; ++j) {
     long long i = base + (long long)j * kBlock;
@@ -119,6 +143,7 @@ __global__ void __launch_bounds__(kBlock) k_status(Ctx ctx, typename R::Cfg cfg,
 // ApplyAction + IsTerminal + Returns + next LegalActionsMask in one pass.
 template <class R, int ILP>
 __global__ void __launch_bounds__(kBlock) k_step_fused(Ctx ctx, typename R::Cfg cfg, const int* __restrict__ actions, u32* __restrict__ mask, int mask_words, unsigned char* __restrict__ term, float* __restrict__ rets, long long n) {
+  pdl_wait();
   long long base = (long long)blockIdx.x * (kBlock * ILP) + threadIdx.x;
   int a[ILP];
   typename R::S s[ILP];
@@ -128,6 +153,7 @@ __global__ void __launch_bounds__(kBlock) k_step_fused(Ctx ctx, typename R::Cfg 
     a[j] = -1;
     if (i < n) { a[j] = __ldg(actions + i); R::load(s[j], ctx, i); }
   }
+  pdl_launch_dependents();
 #pragma unroll
   for (int j = 0; j < ILP; ++j) {
     long long i = base + (long long)j * kBlock;
@@ -300,7 +326,7 @@ struct GameOpsT : GameOps {
   }
   void apply(const Ctx& c, const int* a, long long n, cudaStream_t st) override {
     if (n <= 0) return;
-    k_apply<R, R::kIlp><<<grid_for(n, R::kIlp), kBlock, 0, st>>>(c, cfg, a, n); ++g_launches;
+    launch_pdl(k_apply<R, R::kIlp>, grid_for(n, R::kIlp), st, c, cfg, a, n); ++g_launches;
   }
   void legal_mask(const Ctx& c, u32* m, long long n, cudaStream_t st) override {
     if (n <= 0) return;
@@ -326,7 +352,7 @@ struct GameOpsT : GameOps {
   }
   void step_fused(const Ctx& c, const int* a, u32* m, unsigned char* term, float* rets, long long n, cudaStream_t st) override {
     if (n <= 0) return;
-    k_step_fused<R, R::kIlp><<<grid_for(n, R::kIlp), kBlock, 0, st>>>(c, cfg, a, m, info.mask_words, term, rets, n); ++g_launches;
+    launch_pdl(k_step_fused<R, R::kIlp>, grid_for(n, R::kIlp), st, c, cfg, a, m, info.mask_words, term, rets, n); ++g_launches;
   }
   void rollout(const Ctx& c, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t st) override {
     if (n <= 0) return;
