@@ -133,6 +133,7 @@ int b2s_batch_create(int game_id, const b2s_params* params, int64_t capacity, in
   B->device = device;
   cudaError_t ce = cudaSetDevice(device);
   if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "cudaSetDevice"); }
+  ops->device_init();
   size_t bytes = ops->chunk_bytes() * (size_t)ops->chunks() * (size_t)capacity;
   ce = cudaMalloc(&B->planes, bytes);
   if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "cudaMalloc(state planes)"); }

@@ -274,8 +274,13 @@ __global__ void __launch_bounds__(kBlock) k_copy(Ctx dst, long long dst0, Ctx sr
 
 struct Batch;   // api.cu
 
+// optional per-game device-side tables (e.g. go's Zobrist keys): R::device_init() if the rule core has one
+template <class R> auto call_device_init(int) -> decltype(R::device_init(), void()) { R::device_init(); }
+template <class R> void call_device_init(long) {}
+
 struct GameOps {
   virtual ~GameOps() {}
+  virtual void device_init() = 0;     // called with the batch's device current
   virtual const char* configure(const b2s_params& p, b2s_game_info& gi) = 0;
   virtual size_t chunk_bytes() const = 0;
   virtual int chunks() const = 0;
@@ -318,6 +323,7 @@ struct GameOpsT : GameOps {
     info = gi;
     return nullptr;
   }
+  void device_init() override { call_device_init<R>(0); }
   size_t chunk_bytes() const override { return sizeof(typename R::Chunk); }
   int chunks() const override { return R::kChunks; }
   void reset(const Ctx& c, long long n, cudaStream_t st) override {

@@ -81,4 +81,23 @@ __device__ __forceinline__ int nth_set_bit(const u32* words, int nwords, int k) 
   return -1;
 }
 
+// ---- 128-bit bitboards (hex: up to 121 cells; go: 9 rows x 10-bit stride) ------------------------------------
+struct B128 {
+  u64 lo, hi;
+};
+__host__ __device__ __forceinline__ B128 b_and(B128 a, B128 b) { return {a.lo & b.lo, a.hi & b.hi}; }
+__host__ __device__ __forceinline__ B128 b_or(B128 a, B128 b) { return {a.lo | b.lo, a.hi | b.hi}; }
+__host__ __device__ __forceinline__ B128 b_andn(B128 a, B128 b) { return {a.lo & ~b.lo, a.hi & ~b.hi}; }   // a & ~b
+__host__ __device__ __forceinline__ bool b_any(B128 a) { return (a.lo | a.hi) != 0; }
+__host__ __device__ __forceinline__ B128 b_shl(B128 a, int s) {   // 0 < s < 64
+  return {a.lo << s, (a.hi << s) | (a.lo >> (64 - s))};
+}
+__host__ __device__ __forceinline__ B128 b_shr(B128 a, int s) {
+  return {(a.lo >> s) | (a.hi << (64 - s)), a.hi >> s};
+}
+__host__ __device__ __forceinline__ B128 b_bit(int i) { return i < 64 ? B128{1ull << i, 0} : B128{0, 1ull << (i - 64)}; }
+__host__ __device__ __forceinline__ bool b_test(B128 a, int i) { return i < 64 ? (a.lo >> i) & 1ull : (a.hi >> (i - 64)) & 1ull; }
+__device__ __forceinline__ int b_popc(B128 a) { return __popcll(a.lo) + __popcll(a.hi); }
+__device__ __forceinline__ int b_ffs(B128 a) { return a.lo ? __ffsll((long long)a.lo) - 1 : 64 + __ffsll((long long)a.hi) - 1; }
+
 }  // namespace b2s

@@ -29,6 +29,13 @@ GAMES = [
     ("hex(board_size=4,swap=True)", 256),
     ("hex(board_size=5,plain_obs_tensor=True)", 64),
     ("hex(num_cols=5,num_rows=3,plain_obs_tensor=True)", 64),
+    ("go(board_size=9)", 96),
+    ("go(board_size=5)", 256),
+    ("go(board_size=7,komi=4.5)", 64),
+    ("go(board_size=9,max_game_length=40)", 64),
+    ("go(board_size=3,komi=0.5)", 256),
+    ("go(board_size=4,komi=0.5)", 256),
+    ("go(board_size=2,komi=0.5)", 128),
     ("kuhn_poker", 512),
     ("leduc_poker", 1024),
     ("leduc_poker(starting_player=1)", 256),
@@ -134,7 +141,8 @@ def test_device_replays_reference_playthrough(path):
 def test_rollout_matches_oracle_given_same_random_stream():
     """b2s_rollout = uniform-random playout; the oracle replays it with the same Philox words."""
     from philox_ref import philox_uniform
-    for gs in ["connect_four", "tic_tac_toe", "breakthrough"]:
+    for gs in ["connect_four", "tic_tac_toe", "breakthrough", "hex(board_size=5)", "go(board_size=5)", "kuhn_poker",
+               "leduc_poker"]:
         game = b2.load_game(gs)
         n = 256
         b = game.new_batch(n)
