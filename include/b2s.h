@@ -154,6 +154,38 @@ int b2s_copy_states(void* dst_batch, int64_t dst_begin, void* src_batch, int64_t
  * states.  returns_d [n][num_players] float32 and plies_d [n] int32 (plies played) may be NULL. */
 int b2s_rollout(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, float* returns_d, int32_t* plies_d, void* stream);
 
+/* ---- MCTS ---------------------------------------------------------------------------------- */
+
+/* Replaces algorithms::MCTSBot (open_spiel/algorithms/mcts.h:149-230) with a RandomRolloutEvaluator
+ * (mcts.h:97-111) for n independent search roots at once: one tree per root, UCT selection, optional
+ * MCTS-Solver, run entirely on the device.  Field meaning = the MCTSBot constructor arguments
+ * (mcts.h:161-169): uct_c, max_simulations, solve, seed; n_rollouts = RandomRolloutEvaluator's.
+ * Deterministic perfect-information games only (tic_tac_toe, connect_four, breakthrough, hex, go).
+ * The reference's max_memory_mb garbage collection is not reproduced: max_nodes_total bounds the node
+ * arena shared by all trees (0 = size from free device memory); a tree that cannot allocate stops and is
+ * counted by b2s_error_count. */
+typedef struct b2s_mcts_config {
+  int32_t max_simulations;
+  int32_t n_rollouts;
+  int32_t solve;
+  int32_t reserved;
+  double uct_c;
+  uint64_t seed;
+  int64_t tree_index_offset;   /* tree i uses random stream (seed, i + tree_index_offset): shard roots across GPUs */
+  int64_t max_nodes_total;
+} b2s_mcts_config;
+/* MCTSBot::MCTSearch (mcts.cc:353-467) from lanes [0, n_trees) of roots_batch.  Outputs (device):
+ * visit_counts_d [n][A] int32 and total_reward_d [n][A] double = explore_count / total_reward of the root's
+ * children by action id (0 for illegal actions); outcome_p0_d [n][A] float = proven outcome for player 0 or
+ * NaN (nullable); best_action_d [n] = SearchNode::BestChild (mcts.cc:127-143), -1 for terminal roots;
+ * sims_run_d [n] = simulations actually run (the search stops early when the root is proven) (nullable).
+ * Synchronises `stream` before returning. */
+int b2s_mcts_search(void* roots_batch, int64_t n_trees, const b2s_mcts_config* cfg, int32_t* visit_counts_d,
+                    double* total_reward_d, float* outcome_p0_d, int32_t* best_action_d, int32_t* sims_run_d,
+                    void* stream);
+/* Arena nodes (32 B each) consumed by the last b2s_mcts_search on this batch. */
+int b2s_mcts_nodes_used(void* roots_batch, int64_t* nodes);
+
 /* ---- pinned host memory helpers (for the *_host entry points) ----------------------------- */
 int  b2s_host_alloc(void** out, size_t bytes);
 void b2s_host_free(void* p);

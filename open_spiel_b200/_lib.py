@@ -36,6 +36,12 @@ class GameInfo(C.Structure):
     ]
 
 
+class MctsConfig(C.Structure):
+    _fields_ = [("max_simulations", C.c_int32), ("n_rollouts", C.c_int32), ("solve", C.c_int32),
+                ("reserved", C.c_int32), ("uct_c", C.c_double), ("seed", C.c_uint64),
+                ("tree_index_offset", C.c_int64), ("max_nodes_total", C.c_int64)]
+
+
 # name -> (restype, argtypes); the complete export list of include/b2s.h
 _VP, _I64, _I32, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64
 SIGNATURES = {
@@ -61,6 +67,8 @@ SIGNATURES = {
     "b2s_broadcast_state": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _VP]),
     "b2s_copy_states": (C.c_int, [_VP, _I64, _VP, _I64, _I64, _VP]),
     "b2s_rollout": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _VP, _VP]),
+    "b2s_mcts_search": (C.c_int, [_VP, _I64, C.POINTER(MctsConfig), _VP, _VP, _VP, _VP, _VP, _VP]),
+    "b2s_mcts_nodes_used": (C.c_int, [_VP, C.POINTER(_I64)]),
     "b2s_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_size_t]),
     "b2s_host_free": (None, [_VP]),
     "b2s_device_alloc": (C.c_int, [C.c_int, C.POINTER(_VP), C.c_size_t]),

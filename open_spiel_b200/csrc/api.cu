@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "batch_kernels.cuh"
 
@@ -31,6 +32,10 @@ struct Batch {
   // staging for the *_host entry points
   int* act_d = nullptr; u32* mask_d = nullptr; unsigned char* term_d = nullptr; float* rets_d = nullptr;
   cudaStream_t hs = nullptr;
+  // MCTS scratch (b2s_mcts_search): work lanes, log table, node arena
+  void* mcts_work = nullptr; u64* mcts_hist = nullptr; long long mcts_work_cap = 0;
+  double* mcts_log = nullptr; int mcts_log_n = 0;
+  MctsNode* mcts_pool = nullptr; unsigned long long mcts_pool_cap = 0; unsigned long long* mcts_top = nullptr;
   Ctx ctx() const { Ctx c; c.planes = planes; c.cap = cap; c.hist = hist; c.err = err; return c; }
   ~Batch() {
     if (planes) cudaFree(planes);
@@ -41,6 +46,11 @@ struct Batch {
     if (term_d) cudaFree(term_d);
     if (rets_d) cudaFree(rets_d);
     if (hs) cudaStreamDestroy(hs);
+    if (mcts_work) cudaFree(mcts_work);
+    if (mcts_hist) cudaFree(mcts_hist);
+    if (mcts_log) cudaFree(mcts_log);
+    if (mcts_pool) cudaFree(mcts_pool);
+    if (mcts_top) cudaFree(mcts_top);
     delete ops;
   }
 };
@@ -329,6 +339,81 @@ int b2s_rollout(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, floa
   Batch* B = (Batch*)batch;
   B->ops->rollout(B->ctx(), seed, lane_offset, rets_d, plies_d, n, (cudaStream_t)stream);
   return post();
+}
+
+// ---- MCTS ---------------------------------------------------------------------------------------------------
+int b2s_mcts_search(void* roots_batch, int64_t n_trees, const b2s_mcts_config* cfg, int32_t* visit_counts_d,
+                    double* total_reward_d, float* outcome_p0_d, int32_t* best_action_d, int32_t* sims_run_d,
+                    void* stream) {
+  if (int r = check(roots_batch, n_trees)) return r;
+  if (!cfg || !visit_counts_d || !total_reward_d || !best_action_d) return fail("mcts: null argument");
+  if (cfg->max_simulations < 1 || cfg->n_rollouts < 1) return fail("mcts: max_simulations and n_rollouts must be >= 1");
+  if (n_trees == 0) return 0;
+  Batch* B = (Batch*)roots_batch;
+  cudaStream_t st = (cudaStream_t)stream;
+  // scratch lanes: same layout as the roots; only the per-lane history column (go) is ever written
+  if (B->mcts_work_cap < n_trees) {
+    if (B->mcts_work) cudaFree(B->mcts_work);
+    if (B->mcts_hist) cudaFree(B->mcts_hist);
+    B->mcts_work = nullptr; B->mcts_hist = nullptr; B->mcts_work_cap = 0;
+    CU(cudaMalloc(&B->mcts_work, B->ops->chunk_bytes() * (size_t)B->ops->chunks() * (size_t)n_trees));
+    if (B->info.history_bytes) CU(cudaMalloc((void**)&B->mcts_hist, (size_t)B->info.history_bytes * (size_t)n_trees));
+    B->mcts_work_cap = n_trees;
+  }
+  Ctx work;
+  work.planes = B->mcts_work; work.cap = B->mcts_work_cap; work.hist = B->mcts_hist; work.err = B->err;
+  B->ops->copy(work, 0, B->ctx(), 0, n_trees, st);
+  // log table filled by the host's std::log
+  int need = cfg->max_simulations + 2;
+  if (B->mcts_log_n < need) {
+    if (B->mcts_log) cudaFree(B->mcts_log);
+    B->mcts_log = nullptr; B->mcts_log_n = 0;
+    std::vector<double> t(need);
+    for (int k = 0; k < need; ++k) t[k] = std::log((double)k);
+    CU(cudaMalloc((void**)&B->mcts_log, sizeof(double) * need));
+    CU(cudaMemcpy(B->mcts_log, t.data(), sizeof(double) * need, cudaMemcpyHostToDevice));
+    B->mcts_log_n = need;
+  }
+  // node arena: roots + children; sized by the caller or from free memory
+  unsigned long long want = (unsigned long long)cfg->max_nodes_total;
+  if (want == 0) {
+    unsigned long long worst = (unsigned long long)n_trees * (1ull + (unsigned long long)cfg->max_simulations * B->info.num_distinct_actions);
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    unsigned long long fit = (unsigned long long)((free_b + B->mcts_pool_cap * sizeof(MctsNode)) * 0.6 / sizeof(MctsNode));
+    want = worst < fit ? worst : fit;
+  }
+  if (want < (unsigned long long)n_trees * 2) return fail("mcts: node arena too small");
+  if (B->mcts_pool_cap < want) {
+    if (B->mcts_pool) cudaFree(B->mcts_pool);
+    B->mcts_pool = nullptr; B->mcts_pool_cap = 0;
+    CU(cudaMalloc((void**)&B->mcts_pool, sizeof(MctsNode) * want));
+    B->mcts_pool_cap = want;
+  }
+  if (!B->mcts_top) CU(cudaMalloc((void**)&B->mcts_top, sizeof(unsigned long long)));
+  unsigned long long top0 = (unsigned long long)n_trees;
+  CU(cudaMemcpyAsync(B->mcts_top, &top0, sizeof top0, cudaMemcpyHostToDevice, st));
+  MctsArgs a;
+  memset(&a, 0, sizeof a);
+  a.sims = cfg->max_simulations; a.n_rollouts = cfg->n_rollouts; a.solve = cfg->solve; a.uct_c = cfg->uct_c;
+  a.seed = cfg->seed; a.tree_offset = cfg->tree_index_offset; a.log_table = B->mcts_log;
+  a.pool = B->mcts_pool; a.pool_top = B->mcts_top; a.pool_cap = B->mcts_pool_cap;
+  a.visits_out = visit_counts_d; a.reward_out = total_reward_d; a.outcome_out = outcome_p0_d;
+  a.best_out = best_action_d; a.sims_out = sims_run_d; a.err = B->err;
+  const char* e = B->ops->mcts(B->ctx(), work, n_trees, a, st);
+  if (e) return fail(e);
+  if (int r = post()) return r;
+  CU(cudaStreamSynchronize(st));          // top0 lives on this stack frame; the search is a long-running call anyway
+  return 0;
+}
+
+int b2s_mcts_nodes_used(void* roots_batch, int64_t* nodes) {
+  if (int r = check(roots_batch, 0)) return r;
+  Batch* B = (Batch*)roots_batch;
+  unsigned long long v = 0;
+  if (B->mcts_top) CU(cudaMemcpy(&v, B->mcts_top, sizeof v, cudaMemcpyDeviceToHost));
+  if (nodes) *nodes = (int64_t)v;
+  return 0;
 }
 
 int b2s_host_alloc(void** out, size_t bytes) {

@@ -294,6 +294,8 @@ struct GameOps {
   virtual void rollout(const Ctx&, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t) = 0;
   virtual void broadcast(const Ctx& dst, long long dst0, long long count, const Ctx& src, long long srclane, cudaStream_t) = 0;
   virtual void copy(const Ctx& dst, long long dst0, const Ctx& src, long long src0, long long count, cudaStream_t) = 0;
+  // MCTS over n roots (mcts.cuh); returns an error string when the game has no device MCTS
+  virtual const char* mcts(const Ctx& roots, const Ctx& work, long long n, const struct MctsArgs& args, cudaStream_t) = 0;
   b2s_game_info info;
 };
 
@@ -368,11 +370,32 @@ struct GameOpsT : GameOps {
     if (count <= 0) return;
     k_broadcast<R><<<grid_for(count), kBlock, 0, st>>>(dst, dst0, count, src, srclane, cfg); ++g_launches;
   }
+  const char* mcts(const Ctx& roots, const Ctx& work, long long n, const MctsArgs& args, cudaStream_t st) override;
   void copy(const Ctx& dst, long long dst0, const Ctx& src, long long src0, long long count, cudaStream_t st) override {
     if (count <= 0) return;
     k_copy<R><<<grid_for(count), kBlock, 0, st>>>(dst, dst0, src, src0, count, cfg); ++g_launches;
   }
 };
+
+}  // namespace b2s
+#include "mcts.cuh"
+namespace b2s {
+template <class R>
+const char* GameOpsT<R>::mcts(const Ctx& roots, const Ctx& work, long long n, const MctsArgs& args, cudaStream_t st) {
+  if constexpr (R::kMaxPath > 0) {
+    if (info.max_game_length + 2 > R::kMaxPath) return "mcts: max_game_length too large for the device search path stack";
+    if (n <= 0) return nullptr;
+    MctsArgs a = args;
+    a.num_actions = info.num_distinct_actions;
+    a.mask_words = info.mask_words;
+    a.max_plies = info.max_game_length + 4;
+    a.max_utility = info.max_utility;
+    k_mcts<R, R::kMaxPath><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(roots, work, cfg, a, n); ++g_launches;
+    return nullptr;
+  } else {
+    return "mcts: games with chance nodes / imperfect information have no device MCTS";
+  }
+}
 
 // one factory per game, defined in game_<name>.cu
 GameOps* make_ops_tic_tac_toe();

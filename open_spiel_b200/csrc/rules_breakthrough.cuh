@@ -15,6 +15,7 @@ struct BreakthroughRules {
   static constexpr int kMaskWords = 24;   // 64 cells * 12
   static constexpr int kObsWords = 3;
   static constexpr int kPlayers = 2;
+  static constexpr int kMaxPath = 224;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kIlp = 2;      // lanes per thread in the streaming kernels
   static constexpr bool kHasInfoState = false;
 

@@ -15,6 +15,7 @@ struct ConnectFourRules {
   static constexpr int kMaskWords = 1;
   static constexpr int kObsWords = 3;  // 3*rows*cols <= 189 bits
   static constexpr int kPlayers = 2;
+  static constexpr int kMaxPath = 72;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kIlp = 4;      // lanes per thread in the streaming kernels
   static constexpr bool kHasInfoState = false;
 

@@ -26,6 +26,7 @@ struct GoRules {
   static constexpr int kChunks = 2;
   static constexpr int kMaskWords = 3;     // 81 points + pass
   static constexpr int kPlayers = 2;
+  static constexpr int kMaxPath = 176;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kIlp = 1;
   static constexpr bool kHasInfoState = false;
   static constexpr int kStride = 10;

@@ -16,6 +16,7 @@ struct HexRules {
   static constexpr int kChunks = 4;
   static constexpr int kMaskWords = 4;     // up to 121 cells + swap
   static constexpr int kPlayers = 2;
+  static constexpr int kMaxPath = 128;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kIlp = 1;
   static constexpr bool kHasInfoState = false;
 

@@ -14,6 +14,7 @@ struct TicTacToeRules {
   static constexpr int kMaskWords = 1;
   static constexpr int kObsWords = 1;
   static constexpr int kPlayers = 2;
+  static constexpr int kMaxPath = 16;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kIlp = 4;      // lanes per thread in the streaming kernels
   static constexpr bool kHasInfoState = false;
   struct Cfg { int dummy; };

@@ -394,3 +394,62 @@ def _reset_errors(self):
 
 
 BatchedState._reset_errors = _reset_errors
+
+
+def mcts_search(batch, max_simulations, uct_c=2.0, n_rollouts=1, solve=True, seed=0, tree_index_offset=0,
+                n_trees=None, max_nodes_total=0):
+    """Batched MCTSBot.mcts_search (python/pybind11/bots.cc:129-149 -> algorithms/mcts.cc:353-467) over the lanes of
+    `batch`.  Returns dict of device tensors: visits [n, A] int32, total_reward [n, A] float64, outcome_p0 [n, A]
+    float32 (NaN = unproven), best_action [n] int32, sims_run [n] int32."""
+    from ._lib import MctsConfig
+    n = batch.n if n_trees is None else int(n_trees)
+    A = batch.info.num_distinct_actions
+    dev = batch._dev
+    out = {
+        "visits": torch.empty((n, A), dtype=torch.int32, device=dev),
+        "total_reward": torch.empty((n, A), dtype=torch.float64, device=dev),
+        "outcome_p0": torch.empty((n, A), dtype=torch.float32, device=dev),
+        "best_action": torch.empty((n,), dtype=torch.int32, device=dev),
+        "sims_run": torch.empty((n,), dtype=torch.int32, device=dev),
+    }
+    cfg = MctsConfig(int(max_simulations), int(n_rollouts), int(bool(solve)), 0, float(uct_c), int(seed),
+                     int(tree_index_offset), int(max_nodes_total))
+    check(lib().b2s_mcts_search(batch._h, n, C.byref(cfg), out["visits"].data_ptr(), out["total_reward"].data_ptr(),
+                                out["outcome_p0"].data_ptr(), out["best_action"].data_ptr(), out["sims_run"].data_ptr(),
+                                batch._stream()))
+    return out
+
+
+def mcts_nodes_used(batch):
+    v = C.c_int64()
+    check(lib().b2s_mcts_nodes_used(batch._h, C.byref(v)))
+    return v.value
+
+
+class RandomRolloutEvaluator:
+    """Mirror of algorithms::RandomRolloutEvaluator(n_rollouts, seed) (mcts.h:97-111): a parameter holder; the
+    rollouts themselves run inside the device search."""
+
+    def __init__(self, n_rollouts=1, seed=0):
+        self.n_rollouts, self.seed = int(n_rollouts), int(seed)
+
+
+class MCTSBot:
+    """Mirror of pyspiel.MCTSBot(game, evaluator, uct_c, max_simulations, max_memory_mb, solve, seed, verbose)
+    (python/pybind11/bots.cc:129-149, algorithms/mcts.h:161-169) over the device search."""
+
+    def __init__(self, game, evaluator, uct_c, max_simulations, max_memory_mb=1000, solve=True, seed=0, verbose=False):
+        if not isinstance(evaluator, RandomRolloutEvaluator):
+            raise B2SError("the device MCTSBot supports RandomRolloutEvaluator only")
+        self.game, self.evaluator = game, evaluator
+        self.uct_c, self.max_simulations, self.solve, self.seed = float(uct_c), int(max_simulations), bool(solve), int(seed)
+        self.max_nodes = (int(max_memory_mb) << 20) // 32        # arena nodes are 32 B
+
+    def mcts_search(self, state):
+        """Returns the root statistics of one search from `state` (a scalar State adapter)."""
+        return mcts_search(state._b, self.max_simulations, self.uct_c, self.evaluator.n_rollouts, self.solve, self.seed,
+                           n_trees=1, max_nodes_total=self.max_nodes)
+
+    def step(self, state):
+        """Bot::Step (mcts.cc:233-266): the best action at `state`."""
+        return int(self.mcts_search(state)["best_action"].item())

@@ -1,0 +1,185 @@
+// TEST INFRASTRUCTURE ONLY (see oracle/oracle.h).
+// CPU restatement of reference open_spiel/algorithms/mcts.{h,cc}: MCTSBot::MCTSearch with
+// RandomRolloutEvaluator, UCT child selection and the MCTS-Solver back-propagation, for deterministic
+// perfect-information games.  Structure follows the reference (ApplyTreePolicy :273-351, MCTSearch :353-467,
+// UCTValue :90-101, BestChild/CompareFinal :114-143, RandomRolloutEvaluator::Evaluate :43-72).
+// The reference draws from two std::mt19937 streams through std::shuffle and absl::Uniform, whose bit patterns
+// are library specific (RNG-stream parity unpinned); here every random decision is an explicit
+// function of (seed key, tree, simulation / expansion index, position) through Philox (philox.h), and the CUDA
+// kernels consume the identical function, so the search trees can be compared bit for bit:
+//   * expansion #e of a tree: Fisher-Yates over the ascending legal-action list, for i = n-1..1:
+//       j = RngUniform(key, e, i, 1, i + 1); swap(list[i], list[j])          (replaces std::shuffle, mcts.cc:294)
+//   * simulation #t, rollout #r, rollout ply p: index = RngUniform(key, t, p, 2 + r, num_legal)
+//                                                                          (replaces absl::Uniform, mcts.cc:54)
+//   key = seed + tree_index * 0x9E3779B97F4A7C15.
+#include <cmath>
+#include <limits>
+
+#include "../oracle.h"
+#include "philox.h"
+
+namespace oracle {
+namespace {
+
+struct Node {                      // SearchNode, mcts.h:114-146
+  int64_t action = kInvalidAction;
+  int player = 0;                  // the player who chose `action`
+  int explore_count = 0;
+  double total_reward = 0;
+  std::vector<double> outcome;
+  std::vector<Node> children;
+};
+
+double UctValue(const Node& n, int parent_explore_count, double uct_c) {   // mcts.cc:90-101
+  if (!n.outcome.empty()) return n.outcome[n.player];
+  if (n.explore_count == 0) return std::numeric_limits<double>::infinity();
+  return n.total_reward / n.explore_count + uct_c * std::sqrt(std::log(parent_explore_count) / n.explore_count);
+}
+
+bool CompareFinal(const Node& a, const Node& b) {                          // mcts.cc:114-125
+  double out = (a.player >= 0 && a.player < (int)a.outcome.size()) ? a.outcome[a.player] : 0;
+  double out_b = (b.player >= 0 && b.player < (int)b.outcome.size()) ? b.outcome[b.player] : 0;
+  if (out != out_b) return out < out_b;
+  if (a.explore_count != b.explore_count) return a.explore_count < b.explore_count;
+  return a.total_reward < b.total_reward;
+}
+
+struct Search {
+  uint64_t key;
+  double uct_c, max_utility;
+  int n_rollouts;
+  bool solve;
+  uint32_t expansions = 0;
+  long nodes = 1;
+
+  std::vector<double> Evaluate(const State& state, uint32_t sim) {        // mcts.cc:43-72
+    std::vector<double> result;
+    for (int r = 0; r < n_rollouts; ++r) {
+      auto ws = state.Clone();
+      uint32_t ply = 0;
+      while (!ws->IsTerminal()) {
+        auto actions = ws->LegalActions();
+        ws->ApplyAction(actions[RngUniform(key, sim, ply, 2 + r, (uint32_t)actions.size())]);
+        ++ply;
+      }
+      auto returns = ws->Returns();
+      if (result.empty()) result.swap(returns);
+      else for (size_t i = 0; i < result.size(); ++i) result[i] += returns[i];
+    }
+    for (auto& v : result) v /= n_rollouts;
+    return result;
+  }
+
+  std::unique_ptr<State> TreePolicy(Node* root, const State& state, std::vector<Node*>* path) {   // mcts.cc:273-351
+    path->push_back(root);
+    auto ws = state.Clone();
+    Node* cur = root;
+    while (!ws->IsTerminal() && cur->explore_count > 0) {
+      if (cur->children.empty()) {
+        auto legal = ws->LegalActions();             // uniform prior over LegalActions (mcts.cc:74-87)
+        uint32_t e = expansions++;
+        for (int i = (int)legal.size() - 1; i >= 1; --i) std::swap(legal[i], legal[RngUniform(key, e, i, 1, i + 1)]);
+        int player = ws->CurrentPlayer();
+        cur->children.reserve(legal.size());
+        for (auto a : legal) { Node c; c.action = a; c.player = player; cur->children.push_back(c); }
+        nodes += (long)cur->children.capacity();
+      }
+      Node* chosen = nullptr;
+      double max_value = -std::numeric_limits<double>::infinity();
+      for (Node& child : cur->children) {
+        double val = UctValue(child, cur->explore_count, uct_c);
+        if (val > max_value) { max_value = val; chosen = &child; }
+      }
+      cur = chosen;
+      ws->ApplyAction(chosen->action);
+      path->push_back(cur);
+    }
+    return ws;
+  }
+
+  // returns the number of simulations actually run (early exit when the root is solved / has one child)
+  int Run(Node* root, const State& state, int max_simulations) {          // mcts.cc:353-467
+    std::vector<Node*> path;
+    int i = 0;
+    for (; i < max_simulations; ++i) {
+      path.clear();
+      auto ws = TreePolicy(root, state, &path);
+      std::vector<double> returns;
+      bool solved;
+      if (ws->IsTerminal()) {
+        returns = ws->Returns();
+        path.back()->outcome = returns;
+        solved = solve;
+      } else {
+        returns = Evaluate(*ws, (uint32_t)i);
+        solved = false;
+      }
+      while (!path.empty()) {
+        Node* node = path.back();
+        node->total_reward += returns[node->player];
+        node->explore_count += 1;
+        path.pop_back();
+        if (solved && !node->children.empty()) {
+          int player = node->children[0].player;
+          const Node* best = nullptr;
+          bool all_solved = true;
+          for (const Node& child : node->children) {
+            if (child.outcome.empty()) all_solved = false;
+            else if (best == nullptr || child.outcome[player] > best->outcome[player]) best = &child;
+          }
+          if (best != nullptr && (all_solved || best->outcome[player] == max_utility)) node->outcome = best->outcome;
+          else solved = false;
+        }
+      }
+      if (!root->outcome.empty() || root->children.size() == 1) { ++i; break; }
+    }
+    return i;
+  }
+};
+
+}  // namespace
+}  // namespace oracle
+
+extern "C" {
+
+// One MCTSearch from `state` for tree #tree_index.  Root children are reported in child (shuffled) order:
+// child_actions/visits/rewards/outcome_p0 (NaN when unproven).  Returns the number of root children.
+int orc_mcts_search(void* game, void* state, double uct_c, int max_simulations, int n_rollouts, int solve,
+                    uint64_t seed, uint64_t tree_index, int64_t* child_actions, int* child_visits,
+                    double* child_rewards, double* child_outcome_p0, int cap, int64_t* best_action,
+                    int* root_visits, double* root_outcome_p0, long* nodes_out, int* sims_run) {
+  using namespace oracle;
+  Game* g = (Game*)game;
+  State* s = (State*)state;
+  Search srch;
+  srch.key = seed + tree_index * 0x9E3779B97F4A7C15ull;
+  srch.uct_c = uct_c;
+  srch.max_utility = g->info.max_utility;
+  srch.n_rollouts = n_rollouts;
+  srch.solve = solve != 0;
+  Node root;
+  root.player = s->CurrentPlayer();
+  int ran = srch.Run(&root, *s, max_simulations);
+  int n = (int)root.children.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    child_actions[i] = root.children[i].action;
+    child_visits[i] = root.children[i].explore_count;
+    child_rewards[i] = root.children[i].total_reward;
+    child_outcome_p0[i] = root.children[i].outcome.empty() ? std::nan("") : root.children[i].outcome[0];
+  }
+  if (best_action) {
+    *best_action = kInvalidAction;
+    if (n) {
+      const Node* best = &root.children[0];
+      for (int i = 1; i < n; ++i) if (CompareFinal(*best, root.children[i])) best = &root.children[i];   // std::max_element
+      *best_action = best->action;
+    }
+  }
+  if (root_visits) *root_visits = root.explore_count;
+  if (root_outcome_p0) *root_outcome_p0 = root.outcome.empty() ? std::nan("") : root.outcome[0];
+  if (nodes_out) *nodes_out = srch.nodes;
+  if (sims_run) *sims_run = ran;
+  return n;
+}
+
+}  // extern "C"

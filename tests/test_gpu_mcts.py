@@ -1,0 +1,122 @@
+"""GPU parity: the device MCTS (one tree per thread) vs the oracle's restatement of algorithms/mcts.cc, both fed
+the same Philox decisions: root child visit counts, total rewards (exact doubles), proven outcomes, BestChild and
+the number of simulations run must be identical for every tree.  Plus the reference's own outcome-level MCTS tests
+(algorithms/mcts_test.cc:109-155: the solver proves tic_tac_toe positions)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import open_spiel_b200 as b2
+from oracle_lib import OracleGame, oracle_mcts
+
+pytestmark = pytest.mark.gpu
+
+
+def make_roots(game_string, n, max_prefix, seed):
+    """n lanes advanced by random legal plies (same actions on the device batch and on oracle states)."""
+    rng = np.random.RandomState(seed)
+    game, og = b2.load_game(game_string), OracleGame(game_string)
+    batch = game.new_batch(n)
+    states = [og.new_initial_state() for _ in range(n)]
+    ks = rng.randint(0, max_prefix + 1, size=n)
+    for t in range(max_prefix):
+        acts = np.full(n, -1, dtype=np.int32)
+        for i, st in enumerate(states):
+            if t < ks[i] and not st.is_terminal():
+                la = st.legal_actions()
+                a = la[rng.randint(len(la))]
+                nxt = st.clone()
+                nxt.apply_action(a)
+                if nxt.is_terminal():
+                    continue                  # keep roots non-terminal
+                states[i] = nxt
+                acts[i] = a
+        batch.apply_actions(torch.from_numpy(acts).to(batch._dev))
+    batch.check_errors()
+    return game, batch, states
+
+
+CASES = [
+    # game, trees, prefix plies, sims, n_rollouts, solve
+    ("tic_tac_toe", 64, 4, 400, 1, True),
+    ("tic_tac_toe", 32, 3, 150, 3, False),
+    ("connect_four", 48, 12, 300, 1, True),
+    ("connect_four(rows=4,columns=5,x_in_row=3)", 32, 6, 400, 2, True),
+    ("breakthrough(rows=6,columns=6)", 24, 10, 150, 1, True),
+    ("hex(board_size=5)", 32, 8, 200, 1, True),
+    ("hex(board_size=4,swap=True)", 24, 2, 200, 1, True),
+    ("go(board_size=5)", 32, 10, 150, 1, True),
+    ("go(board_size=9)", 16, 30, 40, 1, True),
+    ("go(board_size=3,komi=0.5)", 32, 4, 300, 1, True),
+]
+
+
+@pytest.mark.parametrize("gs,n,prefix,sims,nroll,solve", CASES, ids=["%s-%d" % (c[0], c[3]) for c in CASES])
+def test_device_mcts_equals_oracle_mcts(gs, n, prefix, sims, nroll, solve):
+    game, batch, states = make_roots(gs, n, prefix, seed=hash(gs) % 1000)
+    seed, offset = 0xC0FFEE, 17
+    out = b2.mcts_search(batch, sims, uct_c=2.0, n_rollouts=nroll, solve=solve, seed=seed, tree_index_offset=offset)
+    assert batch.error_count()[0] == 0
+    visits, reward = out["visits"].cpu().numpy(), out["total_reward"].cpu().numpy()
+    outcome, best, ran = out["outcome_p0"].cpu().numpy(), out["best_action"].cpu().numpy(), out["sims_run"].cpu().numpy()
+    for i, st in enumerate(states):
+        o = oracle_mcts(st, 2.0, sims, nroll, solve, seed, tree_index=i + offset)
+        assert ran[i] == o["sims_run"], (gs, i)
+        assert int(visits[i].sum()) == sum(v for _, v, _, _ in o["children"])
+        for a, v, r, oc in o["children"]:
+            assert visits[i, a] == v, (gs, i, a)
+            assert reward[i, a] == r, (gs, i, a, reward[i, a], r)            # exact double equality
+            assert (math.isnan(oc) and math.isnan(outcome[i, a])) or outcome[i, a] == oc, (gs, i, a)
+        illegal = sorted(set(range(game.num_distinct_actions())) - {a for a, _, _, _ in o["children"]})
+        assert not visits[i, illegal].any()
+        assert best[i] == o["best_action"], (gs, i)
+
+
+def _solve(game_string, actions, sims=10000):
+    """GetOutcome-style helper of mcts_test.cc:100-107: search from the position after `actions`."""
+    game = b2.load_game(game_string)
+    st = game.new_initial_state()
+    for a in actions:
+        st.apply_action(a)
+    bot = b2.MCTSBot(game, b2.RandomRolloutEvaluator(20, 42), 2.0, sims, solve=True, seed=42)
+    out = bot.mcts_search(st)
+    legal = st.legal_actions()
+    return st, out, legal
+
+
+def test_solver_proves_tic_tac_toe_positions():
+    # mcts_test.cc:123-134 MCTSTest_SolveDraw: "x(1,1) o(0,0) x(2,2)" -> o to move, proven draw, best move o(2,0) or o(0,2)
+    st, out, legal = _solve("tic_tac_toe", [4, 0, 8])
+    oc = out["outcome_p0"][0].cpu().numpy()
+    assert st.current_player() == 1 and int(out["sims_run"].item()) < 10000       # root proven -> early exit
+    assert not np.isnan(oc[legal]).any() and (oc[legal] >= 0).all()               # no winning move for o
+    assert int(out["best_action"].item()) in (6, 2) and oc[int(out["best_action"].item())] == 0
+    # mcts_test.cc:136-143 SolveLoss: "x(1,1) o(0,0) x(2,2) o(0,1) x(0,2)" -> every o move is a proven loss
+    st, out, legal = _solve("tic_tac_toe", [4, 0, 8, 1, 2])
+    oc = out["outcome_p0"][0].cpu().numpy()
+    assert st.current_player() == 1 and (oc[legal] == 1).all()
+    # mcts_test.cc:145-152 SolveWin: "x(0,1) o(2,2)" -> x wins with x(0,2)
+    st, out, legal = _solve("tic_tac_toe", [1, 8])
+    assert st.current_player() == 0
+    assert int(out["best_action"].item()) == 2 and float(out["outcome_p0"][0, 2].item()) == 1.0
+    assert int(out["sims_run"].item()) < 10000
+
+
+def test_mcts_root_invariants_many_trees():
+    """Deterministic facts of algorithms/mcts.cc that hold for every tree: sum of child visits = sims - 1 when the
+    root is unproven (the first simulation stops at the root), children = LegalActions, runs are reproducible."""
+    game = b2.load_game("connect_four")
+    n, sims = 4096, 64
+    batch = game.new_batch(n)
+    out = b2.mcts_search(batch, sims, solve=False, seed=5)
+    v = out["visits"]
+    assert bool((v.sum(dim=1) == sims - 1).all())
+    assert bool((out["sims_run"] == sims).all())
+    out2 = b2.mcts_search(batch, sims, solve=False, seed=5)
+    assert torch.equal(out["visits"], out2["visits"]) and torch.equal(out["total_reward"], out2["total_reward"])
+    out3 = b2.mcts_search(batch, sims, solve=False, seed=6)
+    assert not torch.equal(out["visits"], out3["visits"])
+    # different trees use different random streams
+    assert len({tuple(r) for r in v[:64].cpu().tolist()}) > 32
