@@ -147,6 +147,9 @@ int b2s_broadcast_state(void* dst_batch, int64_t dst_begin, int64_t count, void*
 /* Lane-range State::Clone (spiel.h:740): dst[dst_begin+i] = src[src_begin+i], i in [0,count). */
 int b2s_copy_states(void* dst_batch, int64_t dst_begin, void* src_batch, int64_t src_begin, int64_t count, void* stream);
 
+/* Gather-clone: dst[i] = src[src_lanes_d[i]], i in [0,count) (State::Child fan-out, spiel.h:740-744). */
+int b2s_gather_states(void* dst_batch, void* src_batch, const int64_t* src_lanes_d, int64_t count, void* stream);
+
 /* Random playouts to terminal from every lane's current state (the inner loop of
  * RandomRolloutEvaluator::Evaluate, algorithms/mcts.cc:43-72, and of examples/benchmark_game.cc:32-115):
  * uniform over legal actions (and over chance outcomes) from a Philox4x32-10 counter stream keyed
@@ -185,6 +188,39 @@ int b2s_mcts_search(void* roots_batch, int64_t n_trees, const b2s_mcts_config* c
                     void* stream);
 /* Arena nodes (32 B each) consumed by the last b2s_mcts_search on this batch. */
 int b2s_mcts_nodes_used(void* roots_batch, int64_t* nodes);
+
+/* ---- CFR ----------------------------------------------------------------------------------- */
+
+/* Replaces algorithms::CFRSolver / CFRPlusSolver (open_spiel/algorithms/cfr.h:312-357) for two-player
+ * games with an information-state tensor (kuhn_poker, leduc_poker): the game tree is expanded once with
+ * the batched kernels, regret / average-policy tables live on the device, and every
+ * EvaluateAndUpdatePolicy (cfr.cc:263-282) runs inside one persistent kernel.  FP64, reference operation
+ * order: tables match the reference bit for bit. */
+enum { B2S_CFR_LINEAR_AVERAGING = 1, B2S_CFR_REGRET_MATCHING_PLUS = 2 };   /* both = CFRPlusSolver */
+typedef struct b2s_cfr_info {
+  int32_t num_nodes, num_levels, num_infosets, num_entries;   /* entries = sum of legal actions over infosets */
+  int32_t key_floats;                                         /* information-state tensor size */
+  int32_t iteration;
+  int32_t chance_nodes, decision_nodes, terminal_nodes;       /* cf. integration_tests/api_test.py:77-88 */
+  int32_t reserved[3];
+} b2s_cfr_info;
+int  b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device, void** out_solver);
+void b2s_cfr_destroy(void* solver);
+/* `iters` x CFRSolverBase::EvaluateAndUpdatePolicy, enqueued on `stream`. */
+int  b2s_cfr_iterate(void* solver, int iters, void* stream);
+int  b2s_cfr_info_get(void* solver, b2s_cfr_info* out);
+/* The CFRInfoStateValuesTable (cfr.h:42-104) as flat host arrays: per-entry cumulative_regrets /
+ * cumulative_policy / current_policy [num_entries], offsets [num_infosets+1], legal actions [num_entries],
+ * acting player [num_infosets], and the information-state tensor of every infoset
+ * [num_infosets][key_floats] as its key (the reference keys by InformationStateString; both identify the
+ * same perfect-recall information state).  Any pointer may be NULL. */
+int  b2s_cfr_export(void* solver, double* regrets_h, double* cum_policy_h, double* cur_policy_h, int32_t* offsets_h,
+                    int32_t* legal_actions_h, int32_t* players_h, float* keys_h, void* stream);
+/* Restore tables (checkpoint / resume; cfr.cc:699-781 DeserializeCFRSolver).  iteration < 0 keeps the counter. */
+int  b2s_cfr_import(void* solver, const double* regrets_h, const double* cum_policy_h, const double* cur_policy_h,
+                    int iteration, void* stream);
+/* Device pointers of the three per-entry tables, e.g. for an NCCL all-reduce between iterations. */
+int  b2s_cfr_tables(void* solver, double** regrets_d, double** cum_policy_d, double** cur_policy_d);
 
 /* ---- pinned host memory helpers (for the *_host entry points) ----------------------------- */
 int  b2s_host_alloc(void** out, size_t bytes);

@@ -42,6 +42,13 @@ class MctsConfig(C.Structure):
                 ("tree_index_offset", C.c_int64), ("max_nodes_total", C.c_int64)]
 
 
+class CfrInfo(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("num_levels", C.c_int32), ("num_infosets", C.c_int32),
+                ("num_entries", C.c_int32), ("key_floats", C.c_int32), ("iteration", C.c_int32),
+                ("chance_nodes", C.c_int32), ("decision_nodes", C.c_int32), ("terminal_nodes", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
+
+
 # name -> (restype, argtypes); the complete export list of include/b2s.h
 _VP, _I64, _I32, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64
 SIGNATURES = {
@@ -69,6 +76,14 @@ SIGNATURES = {
     "b2s_rollout": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _VP, _VP]),
     "b2s_mcts_search": (C.c_int, [_VP, _I64, C.POINTER(MctsConfig), _VP, _VP, _VP, _VP, _VP, _VP]),
     "b2s_mcts_nodes_used": (C.c_int, [_VP, C.POINTER(_I64)]),
+    "b2s_gather_states": (C.c_int, [_VP, _VP, _VP, _I64, _VP]),
+    "b2s_cfr_create": (C.c_int, [C.c_int, C.POINTER(Params), C.c_int, C.c_int, C.POINTER(_VP)]),
+    "b2s_cfr_destroy": (None, [_VP]),
+    "b2s_cfr_iterate": (C.c_int, [_VP, C.c_int, _VP]),
+    "b2s_cfr_info_get": (C.c_int, [_VP, C.POINTER(CfrInfo)]),
+    "b2s_cfr_export": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "b2s_cfr_import": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, _VP]),
+    "b2s_cfr_tables": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     "b2s_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_size_t]),
     "b2s_host_free": (None, [_VP]),
     "b2s_device_alloc": (C.c_int, [C.c_int, C.POINTER(_VP), C.c_size_t]),

@@ -8,14 +8,15 @@
 #include <vector>
 
 #include "batch_kernels.cuh"
+#include "errors.h"
 
 namespace b2s {
 
 long long g_launches = 0;
 static thread_local std::string g_err;
 
-static int fail(const std::string& m) { g_err = m; return 1; }
-static int cuda_fail(cudaError_t e, const char* what) {
+int fail(const std::string& m) { g_err = m; return 1; }
+int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
   return 2;
 }
@@ -338,6 +339,17 @@ int b2s_rollout(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, floa
   if (int r = check(batch, n)) return r;
   Batch* B = (Batch*)batch;
   B->ops->rollout(B->ctx(), seed, lane_offset, rets_d, plies_d, n, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_gather_states(void* dst_batch, void* src_batch, const int64_t* src_lanes_d, int64_t count, void* stream) {
+  if (int r = check(dst_batch, count)) return r;
+  if (!src_batch || !src_lanes_d) return fail("gather: null argument");
+  Batch* D = (Batch*)dst_batch;
+  Batch* S = (Batch*)src_batch;
+  if (D->device != S->device || memcmp(&D->info, &S->info, sizeof(b2s_game_info)) != 0)
+    return fail("gather: batches differ in game/params/device");
+  D->ops->gather(D->ctx(), S->ctx(), (const long long*)src_lanes_d, count, (cudaStream_t)stream);
   return post();
 }
 

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kBlock) k_rollout(Ctx ctx, typename R::Cfg cfg
     for (int w = 0; w < mask_words; ++w) cnt += __popc(m[w]);
     u32 k = philox_uniform(seed, (u64)(i + lane_offset), (u32)ply, (u32)cnt);
     int a = nth_set_bit(m, mask_words, (int)k);
-    R::apply(s, a, cfg, ctx, i);
+    apply_known_legal<R>(s, a, cfg, ctx, i);
     ++ply;
   }
   R::store(s, ctx, i);
@@ -270,6 +270,19 @@ __global__ void __launch_bounds__(kBlock) k_copy(Ctx dst, long long dst0, Ctx sr
   R::copy_history(dst, dst0 + i, srcctx, src0 + i, s, cfg);
 }
 
+// Gather-clone: dst[i] = src[src_lanes[i]] (tree expansion: one child lane per (parent, action) pair).
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_gather(Ctx dst, Ctx srcctx, const long long* __restrict__ src_lanes, long long count, typename R::Cfg cfg) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= count) return;
+  long long sl = src_lanes[i];
+  if (sl < 0 || sl >= srcctx.cap) { flag_error(dst.err, i); return; }
+  typename R::S s;
+  R::load(s, srcctx, sl);
+  R::store(s, dst, i);
+  R::copy_history(dst, i, srcctx, sl, s, cfg);
+}
+
 // ---- host-side per-game dispatch table --------------------------------------------------------------
 
 struct Batch;   // api.cu
@@ -294,6 +307,7 @@ struct GameOps {
   virtual void rollout(const Ctx&, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t) = 0;
   virtual void broadcast(const Ctx& dst, long long dst0, long long count, const Ctx& src, long long srclane, cudaStream_t) = 0;
   virtual void copy(const Ctx& dst, long long dst0, const Ctx& src, long long src0, long long count, cudaStream_t) = 0;
+  virtual void gather(const Ctx& dst, const Ctx& src, const long long* src_lanes, long long count, cudaStream_t) = 0;
   // MCTS over n roots (mcts.cuh); returns an error string when the game has no device MCTS
   virtual const char* mcts(const Ctx& roots, const Ctx& work, long long n, const struct MctsArgs& args, cudaStream_t) = 0;
   b2s_game_info info;
@@ -371,6 +385,10 @@ struct GameOpsT : GameOps {
     k_broadcast<R><<<grid_for(count), kBlock, 0, st>>>(dst, dst0, count, src, srclane, cfg); ++g_launches;
   }
   const char* mcts(const Ctx& roots, const Ctx& work, long long n, const MctsArgs& args, cudaStream_t st) override;
+  void gather(const Ctx& dst, const Ctx& src, const long long* src_lanes, long long count, cudaStream_t st) override {
+    if (count <= 0) return;
+    k_gather<R><<<grid_for(count), kBlock, 0, st>>>(dst, src, src_lanes, count, cfg); ++g_launches;
+  }
   void copy(const Ctx& dst, long long dst0, const Ctx& src, long long src0, long long count, cudaStream_t st) override {
     if (count <= 0) return;
     k_copy<R><<<grid_for(count), kBlock, 0, st>>>(dst, dst0, src, src0, count, cfg); ++g_launches;

@@ -1,0 +1,410 @@
+// Device-resident tabular CFR.  Semantics: reference open_spiel/algorithms/cfr.cc — CFRSolverBase::
+// EvaluateAndUpdatePolicy :263-282 (alternating updates: one full traversal + regret matching per player),
+// ComputeCounterFactualRegret :331-408 and ...ForActionProbs :443-469 (state values, counterfactual regrets,
+// average-policy accumulation), CounterFactualReachProb :309-318, CFRInfoStateValues::ApplyRegretMatching
+// :596-615, ApplyRegretMatchingPlusReset :683-691.
+//
+// The reference walks the game tree recursively, cloning a State per edge and looking every information
+// state up by string.  Here the tree is expanded ONCE, level by level, with the batched device kernels
+// (b2s_status / b2s_legal_mask / b2s_information_state / b2s_gather_states / b2s_apply_actions — the C ABI,
+// no CPU rule code), flattened into level-ordered SoA arrays, and every iteration runs inside one persistent
+// kernel: a top-down pass for reach probabilities, a bottom-up pass for state values, one thread per
+// information state for the regret / average-policy update, then regret matching, with block barriers
+// between tree levels.  The current policy is frozen during a traversal in the reference too, so the
+// traversal is a pure tree reduction.
+//
+// Floating point: FP64 throughout, every product and sum written as an explicitly rounded operation (no FMA
+// contraction), children combined in action order from 0.0, an information state's histories accumulated in
+// the reference's DFS order, the chance player's reach kept as the last factor — the same operations in the
+// same order as the reference, so tables are reproduced bit for bit (north-star tolerance: 1e-6).
+// The reference prunes decision nodes where every player's reach is 0 and returns zeros (cfr.cc:350-355);
+// we reproduce the returned zeros; the skipped updates below such a node add +-0 and change nothing.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/b2s.h"
+#include "errors.h"
+
+namespace b2s {
+extern long long g_launches;
+
+struct CfrDev {
+  int n_nodes, n_levels, n_infosets, n_entries;
+  const int* level_off;        // [n_levels + 1]
+  const int* parent;           // [n]
+  const signed char* kind;     // 0 terminal, 1 chance, 2 decision
+  const signed char* actor;    // 0/1 = player to move, 2 = chance
+  const int* first_child;      // [n]
+  const signed char* nchild;   // [n]
+  const signed char* aidx;     // index of this node among its parent's children
+  const double* chance_prob;   // [n] probability of the edge into n when the parent is a chance node
+  const double* ret;           // [n][2] terminal returns
+  const int* infoset;          // [n] (decision nodes)
+  const int* is_player;        // [I]
+  const int* is_off;           // [I + 1] offsets into the per-action tables
+  const int* hist_off;         // [I + 1] offsets into hist
+  const int* hist;             // decision nodes of each information state in DFS order
+  double* reach;               // [n][3]  (player 0, player 1, chance)
+  double* edge_prob;           // [n]
+  double* value;               // [n][2]
+  double* regrets;             // [E]
+  double* cum_policy;          // [E]
+  double* cur_policy;          // [E]
+};
+
+__global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration0, int linear_averaging, int rm_plus) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int it = 0; it < iters; ++it) {
+    const double iteration = (double)(iteration0 + it + 1);          // ++iteration_ (cfr.cc:264)
+    for (int p = 0; p < 2; ++p) {
+      // ---- reach probabilities, top-down (new_reach_probabilities[current_player] *= prob, cfr.cc:457) ----
+      if (tid == 0) { d.reach[0] = 1.0; d.reach[1] = 1.0; d.reach[2] = 1.0; }
+      __syncthreads();
+      for (int l = 1; l < d.n_levels; ++l) {
+        for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
+          int par = d.parent[n];
+          double r0 = d.reach[3 * par], r1 = d.reach[3 * par + 1], r2 = d.reach[3 * par + 2];
+          double prob = d.kind[par] == 1 ? d.chance_prob[n] : d.cur_policy[d.is_off[d.infoset[par]] + d.aidx[n]];
+          int a = d.actor[par];
+          if (a == 0) r0 = __dmul_rn(r0, prob); else if (a == 1) r1 = __dmul_rn(r1, prob); else r2 = __dmul_rn(r2, prob);
+          d.reach[3 * n] = r0; d.reach[3 * n + 1] = r1; d.reach[3 * n + 2] = r2;
+          d.edge_prob[n] = prob;
+        }
+        __syncthreads();
+      }
+      // ---- state values, bottom-up (state_value[i] += prob * child_value[i], cfr.cc:461-463) ----
+      for (int l = d.n_levels - 1; l >= 0; --l) {
+        for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
+          double v0, v1;
+          if (d.kind[n] == 0) { v0 = d.ret[2 * n]; v1 = d.ret[2 * n + 1]; }
+          else if (d.kind[n] == 2 && d.reach[3 * n] == 0.0 && d.reach[3 * n + 1] == 0.0) { v0 = 0.0; v1 = 0.0; }
+          else {
+            v0 = 0.0; v1 = 0.0;
+            int fc = d.first_child[n];
+            for (int c = 0; c < d.nchild[n]; ++c) {
+              double pr = d.edge_prob[fc + c];
+              v0 = __dadd_rn(v0, __dmul_rn(pr, d.value[2 * (fc + c)]));
+              v1 = __dadd_rn(v1, __dmul_rn(pr, d.value[2 * (fc + c) + 1]));
+            }
+          }
+          d.value[2 * n] = v0; d.value[2 * n + 1] = v1;
+        }
+        __syncthreads();
+      }
+      // ---- regret and average-policy update for player p's information states (cfr.cc:379-405) ----
+      for (int I = tid; I < d.n_infosets; I += nt) {
+        if (d.is_player[I] != p) continue;
+        int off = d.is_off[I], na = d.is_off[I + 1] - off;
+        for (int hh = d.hist_off[I]; hh < d.hist_off[I + 1]; ++hh) {
+          int h = d.hist[hh];
+          double self_reach = d.reach[3 * h + p];
+          double cfr_reach = 1.0;                                       // CounterFactualReachProb, index order
+          for (int i = 0; i < 3; ++i) if (i != p) cfr_reach = __dmul_rn(cfr_reach, d.reach[3 * h + i]);
+          double vh = d.value[2 * h + p];
+          int fc = d.first_child[h];
+          for (int a = 0; a < na; ++a) {
+            double regret = __dmul_rn(cfr_reach, __dsub_rn(d.value[2 * (fc + a) + p], vh));
+            d.regrets[off + a] = __dadd_rn(d.regrets[off + a], regret);
+            double pol = d.cur_policy[off + a];
+            double inc = linear_averaging ? __dmul_rn(__dmul_rn(iteration, self_reach), pol) : __dmul_rn(self_reach, pol);
+            d.cum_policy[off + a] = __dadd_rn(d.cum_policy[off + a], inc);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- regret matching over the whole table (cfr.cc:596-615, 683-697) ----
+      for (int I = tid; I < d.n_infosets; I += nt) {
+        int off = d.is_off[I], na = d.is_off[I + 1] - off;
+        double sum = 0.0;
+        for (int a = 0; a < na; ++a) {
+          double r = d.regrets[off + a];
+          if (rm_plus && r < 0) { r = 0; d.regrets[off + a] = 0; }
+          if (r > 0) sum = __dadd_rn(sum, r);
+        }
+        for (int a = 0; a < na; ++a) {
+          double r = d.regrets[off + a];
+          d.cur_policy[off + a] = sum > 0 ? (r > 0 ? __ddiv_rn(r, sum) : 0.0) : __ddiv_rn(1.0, (double)na);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct CfrSolver {
+  int device = 0;
+  int game_id = 0;
+  int iteration = 0;
+  int linear_averaging = 0, rm_plus = 0;
+  int tensor_size = 0;
+  CfrDev d;
+  std::vector<void*> allocs;
+  // host copies of the structure (export)
+  std::vector<int> is_player, is_off, legal_actions, node_counts;    // node_counts = {chance, decision, terminal}
+  std::vector<float> keys;                                           // [I][tensor_size] information-state tensors
+  ~CfrSolver() { for (void* p : allocs) cudaFree(p); }
+};
+
+template <typename T>
+static int upload(CfrSolver* s, const std::vector<T>& v, const T** out) {
+  void* p = nullptr;
+  B2S_CU(cudaMalloc(&p, sizeof(T) * (v.empty() ? 1 : v.size())));
+  s->allocs.push_back(p);
+  if (!v.empty()) B2S_CU(cudaMemcpy(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  *out = (const T*)p;
+  return 0;
+}
+static int alloc_d(CfrSolver* s, size_t n, double** out) {
+  void* p = nullptr;
+  B2S_CU(cudaMalloc(&p, sizeof(double) * (n ? n : 1)));
+  B2S_CU(cudaMemset(p, 0, sizeof(double) * (n ? n : 1)));
+  s->allocs.push_back(p);
+  *out = (double*)p;
+  return 0;
+}
+
+}  // namespace b2s
+
+using namespace b2s;
+
+#define CK(x) do { int _r = (x); if (_r) { if (level) b2s_batch_destroy(level); if (next) b2s_batch_destroy(next); delete S; return _r; } } while (0)
+
+extern "C" {
+
+int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device, void** out_solver) {
+  if (!out_solver) return fail("cfr: null out_solver");
+  *out_solver = nullptr;
+  if (b2s_device_count() <= 0) return fail("no CUDA device: the b2s device path has no CPU fallback");
+  b2s_game_info gi;
+  if (int r = b2s_game_info_get(game_id, params, &gi)) return r;
+  if (gi.num_players != 2) return fail("cfr: two-player games only");
+  if (gi.information_state_tensor_size <= 0)
+    return fail("cfr: the game provides no information-state tensor (device CFR keys information states by it)");
+  CfrSolver* S = new CfrSolver;
+  S->device = device; S->game_id = game_id; S->tensor_size = gi.information_state_tensor_size;
+  S->linear_averaging = (flags & B2S_CFR_LINEAR_AVERAGING) ? 1 : 0;
+  S->rm_plus = (flags & B2S_CFR_REGRET_MATCHING_PLUS) ? 1 : 0;
+  void* level = nullptr;
+  void* next = nullptr;
+  const int T = gi.information_state_tensor_size, MW = gi.mask_words;
+  std::vector<int> parent, first_child, infoset, level_off;
+  std::vector<signed char> kind, actor, nchild, aidx;
+  std::vector<double> chance_prob, ret;
+  std::unordered_map<std::string, int> key_to_is;
+  std::vector<int> is_nact;
+  int counts[3] = {0, 0, 0};
+  // level 0 = the initial state
+  CK(b2s_batch_create(game_id, params, 1, device, &level));
+  long long n = 1;
+  parent.push_back(-1); aidx.push_back(0); chance_prob.push_back(1.0);
+  level_off.push_back(0);
+  long long base = 0;                       // node id of lane 0 of the current level
+  for (int depth = 0; n > 0; ++depth) {
+    if (depth > 4096 || base + n > 50000000LL) CK(fail("cfr: game tree too large for the device solver"));
+    // per-lane facts of this level, computed by the batched kernels
+    signed char* cur_d; unsigned char* term_d; float* rets_d; uint32_t* mask_d; float* tens_d;
+    CK(b2s_device_alloc(device, (void**)&cur_d, n));
+    CK(b2s_device_alloc(device, (void**)&term_d, n));
+    CK(b2s_device_alloc(device, (void**)&rets_d, sizeof(float) * 2 * n));
+    CK(b2s_device_alloc(device, (void**)&mask_d, sizeof(uint32_t) * MW * n));
+    CK(b2s_device_alloc(device, (void**)&tens_d, sizeof(float) * (size_t)T * n));
+    CK(b2s_status(level, (int8_t*)cur_d, term_d, rets_d, n, nullptr));
+    CK(b2s_legal_mask(level, mask_d, n, nullptr));
+    CK(b2s_information_state(level, -1, tens_d, n, nullptr));
+    std::vector<signed char> cur(n); std::vector<unsigned char> term(n); std::vector<float> rets(2 * n), tens((size_t)T * n);
+    std::vector<uint32_t> mask((size_t)MW * n);
+    CK(b2s_memcpy_d2h(device, cur.data(), cur_d, n, nullptr));
+    CK(b2s_memcpy_d2h(device, term.data(), term_d, n, nullptr));
+    CK(b2s_memcpy_d2h(device, rets.data(), rets_d, sizeof(float) * 2 * n, nullptr));
+    CK(b2s_memcpy_d2h(device, mask.data(), mask_d, sizeof(uint32_t) * MW * n, nullptr));
+    CK(b2s_memcpy_d2h(device, tens.data(), tens_d, sizeof(float) * (size_t)T * n, nullptr));
+    CK(b2s_stream_synchronize(device, nullptr));
+    b2s_device_free(device, cur_d); b2s_device_free(device, term_d); b2s_device_free(device, rets_d);
+    b2s_device_free(device, mask_d); b2s_device_free(device, tens_d);
+    // node records + the child list of the next level
+    std::vector<long long> src_lanes;
+    std::vector<int32_t> actions;
+    kind.resize(base + n); actor.resize(base + n); nchild.resize(base + n); first_child.resize(base + n);
+    infoset.resize(base + n, -1); ret.resize(2 * (base + n), 0.0);
+    long long next_base = base + n;
+    for (long long i = 0; i < n; ++i) {
+      long long id = base + i;
+      first_child[id] = (int)(next_base + (long long)src_lanes.size());
+      if (term[i]) {
+        kind[id] = 0; actor[id] = 0; nchild[id] = 0;
+        ret[2 * id] = (double)rets[2 * i]; ret[2 * id + 1] = (double)rets[2 * i + 1];
+        counts[2]++;
+        continue;
+      }
+      std::vector<int> acts;
+      for (int w = 0; w < MW; ++w)
+        for (int b = 0; b < 32; ++b) if ((mask[(size_t)i * MW + w] >> b) & 1u) acts.push_back(w * 32 + b);
+      if (acts.empty() || acts.size() > 120) CK(fail("cfr: unexpected legal-action count"));
+      nchild[id] = (signed char)acts.size();
+      if (cur[i] == -1) {                                    // chance: uniform over the available outcomes
+        kind[id] = 1; actor[id] = 2; counts[0]++;            // (kuhn_poker.cc:329-337, leduc_poker.cc:546-571)
+      } else {
+        kind[id] = 2; actor[id] = cur[i]; counts[1]++;
+        std::string key((const char*)&tens[(size_t)i * T], sizeof(float) * T);
+        auto itk = key_to_is.find(key);
+        int is;
+        if (itk == key_to_is.end()) {
+          is = (int)key_to_is.size();
+          key_to_is.emplace(key, is);
+          S->is_player.push_back(cur[i]);
+          is_nact.push_back((int)acts.size());
+          S->keys.insert(S->keys.end(), tens.begin() + (size_t)i * T, tens.begin() + (size_t)(i + 1) * T);
+          S->is_off.push_back((int)S->legal_actions.size());
+          for (int a : acts) S->legal_actions.push_back(a);
+        } else {
+          is = itk->second;
+          if (is_nact[is] != (int)acts.size()) CK(fail("cfr: information state with inconsistent legal actions"));
+        }
+        infoset[id] = is;
+      }
+      for (size_t k = 0; k < acts.size(); ++k) {
+        src_lanes.push_back(i);
+        actions.push_back(acts[k]);
+        parent.push_back((int)id);
+        aidx.push_back((signed char)k);
+        chance_prob.push_back(cur[i] == -1 ? 1.0 / (double)acts.size() : 0.0);
+      }
+    }
+    level_off.push_back((int)(base + n));
+    long long m = (long long)src_lanes.size();
+    if (m == 0) break;
+    // next level = clone of each parent lane, then the child action applied
+    CK(b2s_batch_create(game_id, params, m, device, &next));
+    long long* lanes_d; int32_t* act_d;
+    CK(b2s_device_alloc(device, (void**)&lanes_d, sizeof(long long) * m));
+    CK(b2s_device_alloc(device, (void**)&act_d, sizeof(int32_t) * m));
+    CK(b2s_memcpy_h2d(device, lanes_d, src_lanes.data(), sizeof(long long) * m, nullptr));
+    CK(b2s_memcpy_h2d(device, act_d, actions.data(), sizeof(int32_t) * m, nullptr));
+    CK(b2s_gather_states(next, level, (const int64_t*)lanes_d, m, nullptr));
+    CK(b2s_apply_actions(next, act_d, m, nullptr));
+    int64_t bad = 0;
+    CK(b2s_error_count(next, &bad, nullptr, nullptr));
+    b2s_device_free(device, lanes_d); b2s_device_free(device, act_d);
+    if (bad) CK(fail("cfr: tree expansion applied an illegal action"));
+    b2s_batch_destroy(level);
+    level = next; next = nullptr;
+    base += n; n = m;
+  }
+  if (level) { b2s_batch_destroy(level); level = nullptr; }
+  const int N = (int)kind.size(), I = (int)S->is_player.size();
+  S->is_off.push_back((int)S->legal_actions.size());
+  const int E = (int)S->legal_actions.size();
+  // histories of each information state in the reference's DFS order (children in action order)
+  std::vector<std::vector<int>> by_is(I);
+  {
+    std::vector<int> stack = {0};
+    while (!stack.empty()) {
+      int v = stack.back(); stack.pop_back();
+      if (kind[v] == 2) by_is[infoset[v]].push_back(v);
+      for (int c = nchild[v] - 1; c >= 0; --c) stack.push_back(first_child[v] + c);
+    }
+  }
+  std::vector<int> hist_off(1, 0), hist;
+  for (int i = 0; i < I; ++i) { hist.insert(hist.end(), by_is[i].begin(), by_is[i].end()); hist_off.push_back((int)hist.size()); }
+  S->node_counts = {counts[0], counts[1], counts[2]};
+  // upload
+  B2S_CU(cudaSetDevice(device));
+  CfrDev& d = S->d;
+  memset(&d, 0, sizeof d);
+  d.n_nodes = N; d.n_levels = (int)level_off.size() - 1; d.n_infosets = I; d.n_entries = E;
+  CK(upload(S, level_off, &d.level_off)); CK(upload(S, parent, &d.parent)); CK(upload(S, kind, &d.kind));
+  CK(upload(S, actor, &d.actor)); CK(upload(S, first_child, &d.first_child)); CK(upload(S, nchild, &d.nchild));
+  CK(upload(S, aidx, &d.aidx)); CK(upload(S, chance_prob, &d.chance_prob)); CK(upload(S, ret, &d.ret));
+  CK(upload(S, infoset, &d.infoset)); CK(upload(S, S->is_player, &d.is_player)); CK(upload(S, S->is_off, &d.is_off));
+  CK(upload(S, hist_off, &d.hist_off)); CK(upload(S, hist, &d.hist));
+  CK(alloc_d(S, 3 * (size_t)N, &d.reach)); CK(alloc_d(S, N, &d.edge_prob)); CK(alloc_d(S, 2 * (size_t)N, &d.value));
+  CK(alloc_d(S, E, &d.regrets)); CK(alloc_d(S, E, &d.cum_policy)); CK(alloc_d(S, E, &d.cur_policy));
+  // CFRInfoStateValues(legal_actions): regrets 0, cumulative policy 0, current policy uniform (cfr.h:42-98)
+  std::vector<double> uni(E);
+  for (int i = 0; i < I; ++i)
+    for (int k = S->is_off[i]; k < S->is_off[i + 1]; ++k) uni[k] = 1.0 / (double)(S->is_off[i + 1] - S->is_off[i]);
+  B2S_CU(cudaMemcpy(d.cur_policy, uni.data(), sizeof(double) * E, cudaMemcpyHostToDevice));
+  *out_solver = S;
+  return 0;
+}
+
+void b2s_cfr_destroy(void* solver) {
+  if (!solver) return;
+  CfrSolver* S = (CfrSolver*)solver;
+  cudaSetDevice(S->device);
+  delete S;
+}
+
+int b2s_cfr_iterate(void* solver, int iters, void* stream) {
+  if (!solver) return fail("cfr: null solver");
+  if (iters < 0) return fail("cfr: negative iteration count");
+  CfrSolver* S = (CfrSolver*)solver;
+  B2S_CU(cudaSetDevice(S->device));
+  if (iters == 0) return 0;
+  k_cfr<<<1, 1024, 0, (cudaStream_t)stream>>>(S->d, iters, S->iteration, S->linear_averaging, S->rm_plus);
+  ++g_launches;
+  S->iteration += iters;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_cfr launch");
+  return 0;
+}
+
+int b2s_cfr_info_get(void* solver, b2s_cfr_info* out) {
+  if (!solver || !out) return fail("cfr: null argument");
+  CfrSolver* S = (CfrSolver*)solver;
+  out->num_nodes = S->d.n_nodes; out->num_levels = S->d.n_levels; out->num_infosets = S->d.n_infosets;
+  out->num_entries = S->d.n_entries; out->key_floats = S->tensor_size; out->iteration = S->iteration;
+  out->chance_nodes = S->node_counts[0]; out->decision_nodes = S->node_counts[1]; out->terminal_nodes = S->node_counts[2];
+  return 0;
+}
+
+int b2s_cfr_export(void* solver, double* regrets_h, double* cum_policy_h, double* cur_policy_h, int32_t* offsets_h,
+                   int32_t* legal_actions_h, int32_t* players_h, float* keys_h, void* stream) {
+  if (!solver) return fail("cfr: null solver");
+  CfrSolver* S = (CfrSolver*)solver;
+  B2S_CU(cudaSetDevice(S->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t eb = sizeof(double) * S->d.n_entries;
+  if (regrets_h) B2S_CU(cudaMemcpyAsync(regrets_h, S->d.regrets, eb, cudaMemcpyDeviceToHost, st));
+  if (cum_policy_h) B2S_CU(cudaMemcpyAsync(cum_policy_h, S->d.cum_policy, eb, cudaMemcpyDeviceToHost, st));
+  if (cur_policy_h) B2S_CU(cudaMemcpyAsync(cur_policy_h, S->d.cur_policy, eb, cudaMemcpyDeviceToHost, st));
+  B2S_CU(cudaStreamSynchronize(st));
+  if (offsets_h) memcpy(offsets_h, S->is_off.data(), sizeof(int) * S->is_off.size());
+  if (legal_actions_h) memcpy(legal_actions_h, S->legal_actions.data(), sizeof(int) * S->legal_actions.size());
+  if (players_h) memcpy(players_h, S->is_player.data(), sizeof(int) * S->is_player.size());
+  if (keys_h) memcpy(keys_h, S->keys.data(), sizeof(float) * S->keys.size());
+  return 0;
+}
+
+int b2s_cfr_import(void* solver, const double* regrets_h, const double* cum_policy_h, const double* cur_policy_h,
+                   int iteration, void* stream) {
+  if (!solver) return fail("cfr: null solver");
+  CfrSolver* S = (CfrSolver*)solver;
+  B2S_CU(cudaSetDevice(S->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t eb = sizeof(double) * S->d.n_entries;
+  if (regrets_h) B2S_CU(cudaMemcpyAsync(S->d.regrets, regrets_h, eb, cudaMemcpyHostToDevice, st));
+  if (cum_policy_h) B2S_CU(cudaMemcpyAsync(S->d.cum_policy, cum_policy_h, eb, cudaMemcpyHostToDevice, st));
+  if (cur_policy_h) B2S_CU(cudaMemcpyAsync(S->d.cur_policy, cur_policy_h, eb, cudaMemcpyHostToDevice, st));
+  B2S_CU(cudaStreamSynchronize(st));
+  if (iteration >= 0) S->iteration = iteration;
+  return 0;
+}
+
+// Device pointers of the per-action tables (regrets, cumulative policy, current policy; num_entries doubles
+// each) so a caller can all-reduce them in place (NCCL) between b2s_cfr_iterate calls.
+int b2s_cfr_tables(void* solver, double** regrets_d, double** cum_policy_d, double** cur_policy_d) {
+  if (!solver) return fail("cfr: null solver");
+  CfrSolver* S = (CfrSolver*)solver;
+  if (regrets_d) *regrets_d = S->d.regrets;
+  if (cum_policy_d) *cum_policy_d = S->d.cum_policy;
+  if (cur_policy_d) *cur_policy_d = S->d.cur_policy;
+  return 0;
+}
+
+}  // extern "C"

@@ -81,6 +81,19 @@ __device__ __forceinline__ int nth_set_bit(const u32* words, int nwords, int k) 
   return -1;
 }
 
+// R::apply_legal(...) when the rule core offers a cheaper "already known legal" path, else R::apply(...)
+template <class R, class S, class Cfg>
+__device__ __forceinline__ auto apply_known_legal_impl(S& s, int a, const Cfg& c, const Ctx& ctx, long long lane, int)
+    -> decltype(R::apply_legal(s, a, c, ctx, lane)) { return R::apply_legal(s, a, c, ctx, lane); }
+template <class R, class S, class Cfg>
+__device__ __forceinline__ bool apply_known_legal_impl(S& s, int a, const Cfg& c, const Ctx& ctx, long long lane, long) {
+  return R::apply(s, a, c, ctx, lane);
+}
+template <class R, class S, class Cfg>
+__device__ __forceinline__ bool apply_known_legal(S& s, int a, const Cfg& c, const Ctx& ctx, long long lane) {
+  return apply_known_legal_impl<R>(s, a, c, ctx, lane, 0);
+}
+
 // ---- 128-bit bitboards (hex: up to 121 cells; go: 9 rows x 10-bit stride) ------------------------------------
 struct B128 {
   u64 lo, hi;

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128) k_mcts(Ctx rootctx, Ctx workctx, typename
         if (v > best) { best = v; chosen = first + i; }
       }
       cur = chosen;
-      R::apply(s, (int)pool[cur].action, cfg, workctx, tree);
+      apply_known_legal<R>(s, (int)pool[cur].action, cfg, workctx, tree);
       path[depth++] = cur;
       term = R::terminal(s, cfg);
     }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) k_mcts(Ctx rootctx, Ctx workctx, typename
           int cnt = 0;
           for (int q = 0; q < P.mask_words; ++q) cnt += __popc(m[q]);
           u32 k = rng_uniform(key, (u32)sim, ply, 2u + (u32)ro, (u32)cnt);
-          R::apply(w, nth_set_bit(m, P.mask_words, (int)k), cfg, workctx, tree);
+          apply_known_legal<R>(w, nth_set_bit(m, P.mask_words, (int)k), cfg, workctx, tree);
           ++ply;
         }
         float r[2];

@@ -7,7 +7,9 @@
 // chains / liberties are recomputed on demand by bitboard flood fill.  "In atari" (go_board.h:243-248: all
 // pseudo-liberties are one point) is exactly "the chain has one liberty", which is what we count.
 // Packed state, 32 B as two 16-byte SoA planes: {black.lo, black.hi | meta << 32}, {white.lo, white.hi};
-// meta = ko+1 (7 bits) | to_play (1) | pass_run (2) | superko (1) | ply (10).
+// meta = ko+1 (7 bits) | to_play (1) | pass_run (2) | superko (1) | ply (10) | cap_ply (10), where cap_ply is the
+// index of the position produced by the most recent capturing move: a position can only recur if stones were
+// removed in between, so the superko scan needs the history before cap_ply only.
 // Positional superko (go.cc:280-285) needs every earlier position: an extra per-lane column of Zobrist hashes
 // hist[k][lane], k = 0..max_game_length, holds the same hash values the reference computes
 // (chess_common.h:129-170 table, seed 2765481), so repetition is detected on identical 64-bit keys.
@@ -44,6 +46,7 @@ struct GoRules {
     int pass_run;         // consecutive passes ending at the last move (capped at 2)
     int superko;
     int ply;              // history_.size()
+    int cap_ply;          // index of the position created by the latest capture (0 = no capture yet)
   };
 
   static __host__ const char* make_cfg(const b2s_params& p, Cfg& c, b2s_game_info& gi) {
@@ -96,16 +99,18 @@ struct GoRules {
     s.pass_run = (meta >> 8) & 3;
     s.superko = (meta >> 10) & 1;
     s.ply = (meta >> 11) & 1023;
+    s.cap_ply = (meta >> 21) & 1023;
   }
   __device__ static __forceinline__ void store(const S& s, const Ctx& ctx, long long i) {
     ulonglong2* pl = reinterpret_cast<ulonglong2*>(ctx.planes);
-    u32 meta = (u32)(s.ko + 1) | (u32)s.to_play << 7 | (u32)s.pass_run << 8 | (u32)s.superko << 10 | (u32)s.ply << 11;
+    u32 meta = (u32)(s.ko + 1) | (u32)s.to_play << 7 | (u32)s.pass_run << 8 | (u32)s.superko << 10 | (u32)s.ply << 11 |
+               (u32)s.cap_ply << 21;
     pl[i] = make_ulonglong2(s.black.lo, s.black.hi | ((u64)meta << 32));
     pl[ctx.cap + i] = make_ulonglong2(s.white.lo, s.white.hi);
   }
   __device__ static __forceinline__ void init(S& s, const Cfg&, const Ctx& ctx, long long i) {
     s.black = {0, 0}; s.white = {0, 0};
-    s.ko = -1; s.to_play = 0; s.pass_run = 0; s.superko = 0; s.ply = 0;
+    s.ko = -1; s.to_play = 0; s.pass_run = 0; s.superko = 0; s.ply = 0; s.cap_ply = 0;
     ctx.hist[i] = 0;                      // repetitions_ starts with the empty-board hash (go.cc:298-299)
   }
   __device__ static __forceinline__ void copy_history(const Ctx& dst, long long di, const Ctx& src, long long si, const S& s, const Cfg&) {
@@ -251,8 +256,10 @@ struct GoRules {
       while (b_any(captured)) { int q = b_ffs(captured); captured = b_andn(captured, b_bit(q)); h ^= g_go_zobrist[1 - s.to_play][q]; }
       if (s.to_play == 0) { s.black = own; s.white = opp; } else { s.white = own; s.black = opp; }
       s.pass_run = 0;
-      // positional superko: has this position occurred before (including the initial one)?
-      for (int k = 0; k <= s.ply; ++k)
+      // positional superko: has this position occurred before (including the initial one)?  Stones only leave the
+      // board by capture, so an earlier equal position must precede the latest capture.
+      if (ncap > 0) s.cap_ply = s.ply + 1;
+      for (int k = 0; k < s.cap_ply; ++k)
         if (ctx.hist[(long long)k * ctx.cap + lane] == h) { s.superko = 1; break; }
     }
     s.to_play ^= 1;
@@ -262,6 +269,10 @@ struct GoRules {
   }
   __device__ static __forceinline__ bool apply(S& s, int a, const Cfg& c, const Ctx& ctx, long long lane) {
     return apply_impl(s, a, c, ctx, lane, false);
+  }
+  // the caller guarantees `a` came from this state's legal set (rollouts, tree descent)
+  __device__ static __forceinline__ bool apply_legal(S& s, int a, const Cfg& c, const Ctx& ctx, long long lane) {
+    return apply_impl(s, a, c, ctx, lane, true);
   }
 
   // planes black, white, empty in board-point order, plane 3 = "white to play" (go.cc:138-158)

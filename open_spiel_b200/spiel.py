@@ -453,3 +453,76 @@ class MCTSBot:
     def step(self, state):
         """Bot::Step (mcts.cc:233-266): the best action at `state`."""
         return int(self.mcts_search(state)["best_action"].item())
+
+
+class CFRSolver:
+    """Mirror of pyspiel.CFRSolver(game) (python/pybind11/policy.cc:224-245; algorithms/cfr.h:312-328) with
+    device-resident tables.  CFRPlusSolver = CFRSolver(game, linear_averaging=True, regret_matching_plus=True)."""
+
+    def __init__(self, game, linear_averaging=False, regret_matching_plus=False):
+        from ._lib import CfrInfo
+        if not torch.cuda.is_available():
+            raise B2SError("no CUDA device: open_spiel_b200 has no CPU fallback")
+        self.game = game
+        self._h = C.c_void_p()
+        flags = (1 if linear_averaging else 0) | (2 if regret_matching_plus else 0)
+        check(lib().b2s_cfr_create(game._gid, C.byref(game._cparams), flags, game.device, C.byref(self._h)))
+        self._info = CfrInfo()
+        check(lib().b2s_cfr_info_get(self._h, C.byref(self._info)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().b2s_cfr_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def info(self):
+        from ._lib import CfrInfo
+        i = CfrInfo()
+        check(lib().b2s_cfr_info_get(self._h, C.byref(i)))
+        return i
+
+    def evaluate_and_update_policy(self, iterations=1):
+        """CFRSolverBase::EvaluateAndUpdatePolicy (cfr.cc:263-282), `iterations` times in one kernel launch."""
+        st = C.c_void_p(torch.cuda.current_stream(torch.device("cuda", self.game.device)).cuda_stream)
+        check(lib().b2s_cfr_iterate(self._h, int(iterations), st))
+
+    def table(self):
+        """The info-state table as numpy arrays: dict(regrets, cum_policy, cur_policy, offsets, legal_actions,
+        players, keys) — see b2s_cfr_export."""
+        i = self._info
+        E, I, T = i.num_entries, i.num_infosets, i.key_floats
+        out = {"regrets": np.empty(E), "cum_policy": np.empty(E), "cur_policy": np.empty(E),
+               "offsets": np.empty(I + 1, dtype=np.int32), "legal_actions": np.empty(E, dtype=np.int32),
+               "players": np.empty(I, dtype=np.int32), "keys": np.empty((I, T), dtype=np.float32)}
+        p = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+        check(lib().b2s_cfr_export(self._h, p(out["regrets"]), p(out["cum_policy"]), p(out["cur_policy"]),
+                                   p(out["offsets"]), p(out["legal_actions"]), p(out["players"]), p(out["keys"]), None))
+        return out
+
+    def load_table(self, regrets=None, cum_policy=None, cur_policy=None, iteration=-1):
+        p = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.c_void_p)   # noqa: E731
+        keep = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (regrets, cum_policy, cur_policy)]
+        check(lib().b2s_cfr_import(self._h, *[None if a is None else a.ctypes.data_as(C.c_void_p) for a in keep],
+                                   int(iteration), None))
+
+    def table_pointers(self):
+        r, c, u = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib().b2s_cfr_tables(self._h, C.byref(r), C.byref(c), C.byref(u)))
+        return r.value, c.value, u.value
+
+    def average_policy(self):
+        """CFRAveragePolicy (cfr.cc:104-125): {key bytes: [(action, prob)]}, uniform where nothing accumulated."""
+        t = self.table()
+        pol = {}
+        for k in range(len(t["players"])):
+            lo, hi = t["offsets"][k], t["offsets"][k + 1]
+            cp = t["cum_policy"][lo:hi]
+            s = 0.0
+            for v in cp:
+                s += v
+            probs = [1.0 / (hi - lo)] * (hi - lo) if s == 0.0 else [v / s for v in cp]
+            pol[t["keys"][k].tobytes()] = list(zip(t["legal_actions"][lo:hi].tolist(), probs))
+        return pol

@@ -195,3 +195,63 @@ def oracle_mcts(state, uct_c, max_simulations, n_rollouts=1, solve=True, seed=0,
                           acts, vis, rew, outc, cap, C.byref(best), C.byref(rv), C.byref(ro), C.byref(nodes), C.byref(ran))
     return {"children": [(acts[i], vis[i], rew[i], outc[i]) for i in range(n)], "best_action": best.value,
             "root_visits": rv.value, "root_outcome_p0": ro.value, "nodes": nodes.value, "sims_run": ran.value}
+
+
+class OracleCFR:
+    """oracle/algorithms/cfr.cc: restatement of algorithms::CFRSolver / CFRPlusSolver."""
+
+    def __init__(self, game, linear_averaging=False, regret_matching_plus=False):
+        L = lib()
+        L.orc_cfr_new.restype = C.c_void_p
+        L.orc_cfr_new.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_cfr_free.argtypes = [C.c_void_p]
+        L.orc_cfr_iterate.argtypes = [C.c_void_p, C.c_int]
+        L.orc_cfr_num_infosets.argtypes = [C.c_void_p]
+        L.orc_cfr_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+        self.game = game
+        self._c = L.orc_cfr_new(game._g, int(linear_averaging), int(regret_matching_plus))
+
+    def __del__(self):
+        try:
+            lib().orc_cfr_free(self._c)
+        except Exception:
+            pass
+
+    def iterate(self, iters=1):
+        lib().orc_cfr_iterate(self._c, iters)
+
+    def table(self):
+        """{info_state_string: dict(legal, regrets, cum_policy, cur_policy, player)}"""
+        L = lib()
+        out = {}
+        for k in range(L.orc_cfr_num_infosets(self._c)):
+            key = C.create_string_buffer(512)
+            legal = (C.c_int64 * 16)()
+            r, cu, cp = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_double * 16)()
+            pl = C.c_int()
+            n = L.orc_cfr_get(self._c, k, key, 512, legal, r, cu, cp, 16, C.byref(pl))
+            out[key.value.decode()] = {"legal": list(legal[:n]), "regrets": list(r[:n]), "cum_policy": list(cu[:n]),
+                                       "cur_policy": list(cp[:n]), "player": pl.value}
+        return out
+
+
+def infostate_tensors(game):
+    """{info_state_string: information-state tensor bytes} for every decision node of the oracle's game tree."""
+    out = {}
+
+    def walk(st):
+        if st.is_terminal():
+            return
+        if not st.is_chance_node():
+            p = st.current_player()
+            key = st.information_state_string(p)
+            if key not in out:
+                out[key] = st.information_state_tensor(p).tobytes()
+        for a in st.legal_actions():
+            c = st.clone()
+            c.apply_action(a)
+            walk(c)
+
+    walk(game.new_initial_state())
+    return out

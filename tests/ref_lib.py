@@ -153,3 +153,43 @@ class RefState:
         buf = (C.c_int64 * 2048)()
         n = lib().ref_history(self._s, buf, 2048)
         return list(buf[:n])
+
+
+class RefCFR:
+    """The unmodified reference's algorithms::CFRSolver (through oracle/ref_glue/ref_c_api.cc)."""
+
+    def __init__(self, game):
+        self.game = game
+        self._c = lib().ref_cfr_new(game._g)
+
+    def __del__(self):
+        try:
+            lib().ref_cfr_free(self._c)
+        except Exception:
+            pass
+
+    def iterate(self, iters=1):
+        assert lib().ref_cfr_iterate(self._c, iters) == 0
+
+    def table(self):
+        L = lib()
+        buf = C.create_string_buffer(1 << 20)
+        L.ref_cfr_keys(self._c, buf, 1 << 20)
+        out = {}
+        for key in buf.value.decode().split("\n"):
+            if key == "" and not out:
+                pass
+            legal = (C.c_int64 * 16)()
+            r, cu, cp = (C.c_double * 16)(), (C.c_double * 16)(), (C.c_double * 16)()
+            n = L.ref_cfr_get(self._c, key.encode(), legal, r, cu, cp, 16)
+            if n < 0:
+                continue
+            out[key] = {"legal": list(legal[:n]), "regrets": list(r[:n]), "cum_policy": list(cu[:n]),
+                        "cur_policy": list(cp[:n])}
+        return out
+
+    def exploitability(self):
+        return lib().ref_cfr_exploitability(self.game._g, self._c)
+
+    def nash_conv(self):
+        return lib().ref_cfr_nash_conv(self.game._g, self._c)

@@ -1,0 +1,74 @@
+"""GPU parity: device-resident CFR vs the oracle's restatement of algorithms/cfr.cc (and vs the unmodified
+reference when oracle/_ref is present): cumulative regrets, cumulative policy and current policy of every
+information state, BIT FOR BIT (north-star tolerance is 1e-6), after several iteration counts; tree sizes and
+information-state counts of integration_tests/api_test.py:77-104."""
+import numpy as np
+import pytest
+
+import open_spiel_b200 as b2
+import ref_lib
+from oracle_lib import OracleCFR, OracleGame, infostate_tensors
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6      # north-star tolerance; the assertions below demand exact equality and report the max |delta|
+
+
+def compare(dev_table, cpu_table, tensors):
+    by_key = {dev_table["keys"][k].tobytes(): k for k in range(len(dev_table["players"]))}
+    assert len(by_key) == len(cpu_table)
+    worst = 0.0
+    for key, v in cpu_table.items():
+        k = by_key[tensors[key]]
+        lo, hi = dev_table["offsets"][k], dev_table["offsets"][k + 1]
+        assert dev_table["legal_actions"][lo:hi].tolist() == v["legal"]
+        for f in ("regrets", "cum_policy", "cur_policy"):
+            d = dev_table[f][lo:hi]
+            c = np.array(v[f])
+            worst = max(worst, float(np.abs(d - c).max()))
+            assert np.array_equal(d, c), (key, f, d, c)
+    assert worst <= TOL
+    return worst
+
+
+@pytest.mark.parametrize("gs,steps,plus", [("kuhn_poker", [1, 1, 3, 45, 250], False), ("leduc_poker", [1, 1, 2, 6], False),
+                                           ("kuhn_poker", [1, 2, 47], True), ("leduc_poker", [1, 3], True)])
+def test_device_cfr_equals_oracle_bitwise(gs, steps, plus):
+    game, og = b2.load_game(gs), OracleGame(gs)
+    dev = b2.CFRSolver(game, linear_averaging=plus, regret_matching_plus=plus)
+    cpu = OracleCFR(og, linear_averaging=plus, regret_matching_plus=plus)
+    tensors = infostate_tensors(og)
+    info = dev.info()
+    expect = {"kuhn_poker": (4, 24, 30, 12), "leduc_poker": (157, 3780, 5520, 936)}[gs]   # api_test.py:77-104
+    assert (info.chance_nodes, info.decision_nodes, info.terminal_nodes, info.num_infosets) == expect
+    for k in steps:
+        dev.evaluate_and_update_policy(k)
+        cpu.iterate(k)
+        compare(dev.table(), cpu.table(), tensors)
+
+
+@pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("gs,iters", [("kuhn_poker", 300), ("leduc_poker", 25)])
+def test_device_cfr_equals_unmodified_reference(gs, iters):
+    game = b2.load_game(gs)
+    dev = b2.CFRSolver(game)
+    ref = ref_lib.RefCFR(ref_lib.RefGame(gs))
+    dev.evaluate_and_update_policy(iters)
+    ref.iterate(iters)
+    tensors = infostate_tensors(OracleGame(gs))
+    compare(dev.table(), ref.table(), tensors)
+    if gs == "kuhn_poker":
+        assert ref.exploitability() <= 0.05          # cfr_test.cc:36-62, now also true of the device tables
+
+
+def test_checkpoint_resume_is_exact():
+    game = b2.load_game("kuhn_poker")
+    a, b = b2.CFRSolver(game), b2.CFRSolver(game)
+    a.evaluate_and_update_policy(20)
+    t = a.table()
+    b.load_table(t["regrets"], t["cum_policy"], t["cur_policy"], iteration=20)
+    a.evaluate_and_update_policy(15)
+    b.evaluate_and_update_policy(15)
+    ta, tb = a.table(), b.table()
+    for f in ("regrets", "cum_policy", "cur_policy"):
+        assert np.array_equal(ta[f], tb[f])
