@@ -219,8 +219,19 @@ int  b2s_cfr_export(void* solver, double* regrets_h, double* cum_policy_h, doubl
 /* Restore tables (checkpoint / resume; cfr.cc:699-781 DeserializeCFRSolver).  iteration < 0 keeps the counter. */
 int  b2s_cfr_import(void* solver, const double* regrets_h, const double* cum_policy_h, const double* cur_policy_h,
                     int iteration, void* stream);
-/* Device pointers of the three per-entry tables, e.g. for an NCCL all-reduce between iterations. */
+/* Device pointers of the three per-entry tables. */
 int  b2s_cfr_tables(void* solver, double** regrets_d, double** cum_policy_d, double** cur_policy_d);
+/* Multi-GPU CFR (the path's one real exchange step).  One player-traversal of iteration `iteration`
+ * (1-based, CFRSolverBase::iteration_) is split in two launches around an all-reduce the CALLER performs
+ * (NCCL over NVLink) on the delta buffer (2*num_entries doubles: regret deltas, then average-policy deltas):
+ *   b2s_cfr_traverse_shard(s, player, iteration, rank, world)  ->  all-reduce(delta, sum)  ->  b2s_cfr_apply_deltas(s)
+ * Every rank evaluates reach/value for the whole tree; history k of an information state contributes on rank
+ * k mod world.  Summation order differs from the single-GPU kernel, so results agree to rounding (1e-6 asked),
+ * not bit for bit. */
+int  b2s_cfr_traverse_shard(void* solver, int player, int iteration, int shard, int num_shards, void* stream);
+int  b2s_cfr_apply_deltas(void* solver, void* stream);
+int  b2s_cfr_delta_buffer(void* solver, double** delta_d);
+int  b2s_cfr_set_iteration(void* solver, int iteration);
 
 /* ---- pinned host memory helpers (for the *_host entry points) ----------------------------- */
 int  b2s_host_alloc(void** out, size_t bytes);

@@ -55,6 +55,7 @@ struct CfrDev {
   double* regrets;             // [E]
   double* cum_policy;          // [E]
   double* cur_policy;          // [E]
+  double* delta;               // [2E]: regret deltas then average-policy deltas of one sharded traversal
 };
 
 __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration0, int linear_averaging, int rm_plus) {
@@ -132,6 +133,89 @@ __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration
         }
       }
       __syncthreads();
+    }
+  }
+}
+
+// ---- multi-GPU variant: one traversal split into "compute my shard's deltas" / all-reduce / "apply" -----------
+// Every rank evaluates reach and value for the whole (tiny) tree; the regret / average-policy contributions of
+// history k of an information state are accumulated only by rank (k mod num_shards) into `delta`, the ranks
+// all-reduce `delta` (NCCL, 2E doubles), then every rank applies the summed deltas and runs regret matching.
+// Summation order differs from the reference's running total, so this path is within rounding (asked: 1e-6),
+// not bit-exact; the single-GPU kernel above stays exact.
+__global__ void __launch_bounds__(1024) k_cfr_traverse(CfrDev d, int p, int iteration, int linear_averaging, int shard, int num_shards) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) { d.reach[0] = 1.0; d.reach[1] = 1.0; d.reach[2] = 1.0; }
+  for (int k = tid; k < 2 * d.n_entries; k += nt) d.delta[k] = 0.0;
+  __syncthreads();
+  for (int l = 1; l < d.n_levels; ++l) {
+    for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
+      int par = d.parent[n];
+      double r0 = d.reach[3 * par], r1 = d.reach[3 * par + 1], r2 = d.reach[3 * par + 2];
+      double prob = d.kind[par] == 1 ? d.chance_prob[n] : d.cur_policy[d.is_off[d.infoset[par]] + d.aidx[n]];
+      int a = d.actor[par];
+      if (a == 0) r0 = __dmul_rn(r0, prob); else if (a == 1) r1 = __dmul_rn(r1, prob); else r2 = __dmul_rn(r2, prob);
+      d.reach[3 * n] = r0; d.reach[3 * n + 1] = r1; d.reach[3 * n + 2] = r2;
+      d.edge_prob[n] = prob;
+    }
+    __syncthreads();
+  }
+  for (int l = d.n_levels - 1; l >= 0; --l) {
+    for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
+      double v0, v1;
+      if (d.kind[n] == 0) { v0 = d.ret[2 * n]; v1 = d.ret[2 * n + 1]; }
+      else if (d.kind[n] == 2 && d.reach[3 * n] == 0.0 && d.reach[3 * n + 1] == 0.0) { v0 = 0.0; v1 = 0.0; }
+      else {
+        v0 = 0.0; v1 = 0.0;
+        int fc = d.first_child[n];
+        for (int c = 0; c < d.nchild[n]; ++c) {
+          double pr = d.edge_prob[fc + c];
+          v0 = __dadd_rn(v0, __dmul_rn(pr, d.value[2 * (fc + c)]));
+          v1 = __dadd_rn(v1, __dmul_rn(pr, d.value[2 * (fc + c) + 1]));
+        }
+      }
+      d.value[2 * n] = v0; d.value[2 * n + 1] = v1;
+    }
+    __syncthreads();
+  }
+  const double iter = (double)iteration;
+  for (int I = tid; I < d.n_infosets; I += nt) {
+    if (d.is_player[I] != p) continue;
+    int off = d.is_off[I], na = d.is_off[I + 1] - off;
+    for (int hh = d.hist_off[I]; hh < d.hist_off[I + 1]; ++hh) {
+      if ((hh - d.hist_off[I]) % num_shards != shard) continue;
+      int h = d.hist[hh];
+      double self_reach = d.reach[3 * h + p];
+      double cfr_reach = 1.0;
+      for (int i = 0; i < 3; ++i) if (i != p) cfr_reach = __dmul_rn(cfr_reach, d.reach[3 * h + i]);
+      double vh = d.value[2 * h + p];
+      int fc = d.first_child[h];
+      for (int a = 0; a < na; ++a) {
+        double regret = __dmul_rn(cfr_reach, __dsub_rn(d.value[2 * (fc + a) + p], vh));
+        d.delta[off + a] = __dadd_rn(d.delta[off + a], regret);
+        double pol = d.cur_policy[off + a];
+        double inc = linear_averaging ? __dmul_rn(__dmul_rn(iter, self_reach), pol) : __dmul_rn(self_reach, pol);
+        d.delta[d.n_entries + off + a] = __dadd_rn(d.delta[d.n_entries + off + a], inc);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_cfr_apply(CfrDev d, int rm_plus) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int I = tid; I < d.n_infosets; I += nt) {
+    int off = d.is_off[I], na = d.is_off[I + 1] - off;
+    double sum = 0.0;
+    for (int a = 0; a < na; ++a) {
+      double r = __dadd_rn(d.regrets[off + a], d.delta[off + a]);
+      if (rm_plus && r < 0) r = 0;
+      d.regrets[off + a] = r;
+      d.cum_policy[off + a] = __dadd_rn(d.cum_policy[off + a], d.delta[d.n_entries + off + a]);
+      if (r > 0) sum = __dadd_rn(sum, r);
+    }
+    for (int a = 0; a < na; ++a) {
+      double r = d.regrets[off + a];
+      d.cur_policy[off + a] = sum > 0 ? (r > 0 ? __ddiv_rn(r, sum) : 0.0) : __ddiv_rn(1.0, (double)na);
     }
   }
 }
@@ -324,6 +408,7 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
   CK(upload(S, hist_off, &d.hist_off)); CK(upload(S, hist, &d.hist));
   CK(alloc_d(S, 3 * (size_t)N, &d.reach)); CK(alloc_d(S, N, &d.edge_prob)); CK(alloc_d(S, 2 * (size_t)N, &d.value));
   CK(alloc_d(S, E, &d.regrets)); CK(alloc_d(S, E, &d.cum_policy)); CK(alloc_d(S, E, &d.cur_policy));
+  CK(alloc_d(S, 2 * (size_t)E, &d.delta));
   // CFRInfoStateValues(legal_actions): regrets 0, cumulative policy 0, current policy uniform (cfr.h:42-98)
   std::vector<double> uni(E);
   for (int i = 0; i < I; ++i)
@@ -393,6 +478,42 @@ int b2s_cfr_import(void* solver, const double* regrets_h, const double* cum_poli
   if (cur_policy_h) B2S_CU(cudaMemcpyAsync(S->d.cur_policy, cur_policy_h, eb, cudaMemcpyHostToDevice, st));
   B2S_CU(cudaStreamSynchronize(st));
   if (iteration >= 0) S->iteration = iteration;
+  return 0;
+}
+
+// Multi-GPU step 1 of 2 for one player's traversal of iteration `iteration` (1-based, as CFRSolverBase::iteration_):
+// reach + value passes, then this shard's regret / average-policy deltas into the delta buffer.
+int b2s_cfr_traverse_shard(void* solver, int player, int iteration, int shard, int num_shards, void* stream) {
+  if (!solver) return fail("cfr: null solver");
+  if (player < 0 || player > 1 || num_shards < 1 || shard < 0 || shard >= num_shards) return fail("cfr: bad shard arguments");
+  CfrSolver* S = (CfrSolver*)solver;
+  B2S_CU(cudaSetDevice(S->device));
+  k_cfr_traverse<<<1, 1024, 0, (cudaStream_t)stream>>>(S->d, player, iteration, S->linear_averaging, shard, num_shards);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_cfr_traverse launch");
+  return 0;
+}
+// Step 2 of 2 (after the caller all-reduced the delta buffer): tables += deltas, RM+ reset, regret matching.
+int b2s_cfr_apply_deltas(void* solver, void* stream) {
+  if (!solver) return fail("cfr: null solver");
+  CfrSolver* S = (CfrSolver*)solver;
+  B2S_CU(cudaSetDevice(S->device));
+  k_cfr_apply<<<1, 1024, 0, (cudaStream_t)stream>>>(S->d, S->rm_plus);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_cfr_apply launch");
+  return 0;
+}
+// The delta buffer: 2 * num_entries doubles (regret deltas, then average-policy deltas), device pointer.
+int b2s_cfr_delta_buffer(void* solver, double** delta_d) {
+  if (!solver || !delta_d) return fail("cfr: null argument");
+  *delta_d = ((CfrSolver*)solver)->d.delta;
+  return 0;
+}
+int b2s_cfr_set_iteration(void* solver, int iteration) {
+  if (!solver) return fail("cfr: null solver");
+  ((CfrSolver*)solver)->iteration = iteration;
   return 0;
 }
 

@@ -1,0 +1,82 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed for the collectives.
+
+The hot path shards by independent lanes / search roots, so stepping, rollouts and MCTS need no data-path
+collective — each rank owns a contiguous slice of the global lane range and a disjoint slice of the random
+stream space (lane_offset / tree_index_offset).  Only two things are ever exchanged:
+  * a handful of int64 statistics per batch (wins / draws / plies, visit totals): `allreduce_stats`;
+  * CFR's regret / average-policy deltas, once per player traversal: `DistributedCFRSolver`.
+Works with backend "nccl" (CUDA tensors) and "gloo" (CPU tensors; used by the CPU tests of this logic).
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib
+
+
+def world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(total, rank=None, world_size=None):
+    """Contiguous, balanced slice [lo, hi) of `total` global lanes owned by `rank` (sizes differ by at most 1)."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    base, rem = divmod(int(total), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_stats(t):
+    """Sum a small statistics tensor over all ranks in place (no-op for a single process)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def rollout_stats(returns, plies):
+    """[p0 wins, p1 wins, draws, total plies, games] of a batch of finished playouts, summed over ranks."""
+    r0 = returns[:, 0]
+    s = torch.stack([(r0 > 0).sum(), (r0 < 0).sum(), (r0 == 0).sum(), plies.sum(), torch.tensor(plies.numel(), device=plies.device)])
+    return allreduce_stats(s.to(torch.int64))
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of library-owned device memory, so torch / NCCL can operate on it in place."""
+
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class DistributedCFRSolver:
+    """CFRSolver whose traversal work is split over the ranks: per player traversal every rank computes its share of
+    the regret / average-policy deltas, the delta buffer is all-reduced (NCCL), every rank applies the sum and runs
+    regret matching — tables stay replicated.  Agrees with the single-GPU solver to rounding (north star: 1e-6)."""
+
+    def __init__(self, game, linear_averaging=False, regret_matching_plus=False):
+        from .spiel import CFRSolver
+        self.solver = CFRSolver(game, linear_averaging, regret_matching_plus)
+        self.rank, self.world = world()
+        self.iteration = 0
+        ptr = C.c_void_p()
+        check(lib().b2s_cfr_delta_buffer(self.solver._h, C.byref(ptr)))
+        n = 2 * self.solver._info.num_entries
+        self.delta = torch.as_tensor(_DevArray(ptr.value, n), device=torch.device("cuda", game.device))
+
+    def evaluate_and_update_policy(self, iterations=1):
+        L, h = lib(), self.solver._h
+        st = C.c_void_p(torch.cuda.current_stream(self.delta.device).cuda_stream)
+        for _ in range(int(iterations)):
+            self.iteration += 1
+            for player in (0, 1):
+                check(L.b2s_cfr_traverse_shard(h, player, self.iteration, self.rank, self.world, st))
+                allreduce_stats(self.delta)
+                check(L.b2s_cfr_apply_deltas(h, st))
+        check(L.b2s_cfr_set_iteration(h, self.iteration))
+
+    def table(self):
+        return self.solver.table()
