@@ -75,6 +75,24 @@ def cpu_arm(n_sample, threads, reps, seed=0x5EED):
     return v, "port", list(per)
 
 
+def cpu_loops():
+    """The unmodified reference's MCTSBot / CFRSolver / random playouts on the host (bounded samples), when
+    oracle/_ref/ref_bench was shipped; reported beside the device numbers in extras."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+    if not os.path.exists(ref):
+        return None
+    out = {}
+    for key, argv in (("mcts_go9x9_1thread", ["mcts", "go(board_size=9)", "2000", "1", "1"]),
+                      ("mcts_go9x9_16threads", ["mcts", "go(board_size=9)", "2000", "1", "16"]),
+                      ("cfr_leduc", ["cfr", "leduc_poker", "20"])):
+        try:
+            r = subprocess.run([ref] + argv, capture_output=True, text=True, timeout=300)
+            out[key] = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:          # noqa: BLE001
+            out[key] = {"error": str(e)}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -308,6 +326,69 @@ def run_gpu(args):
     for w_ in works:
         w_.check_errors()
     total_launches = L.b2s_launch_count() - launches0
+    del works, acts
+    torch.cuda.empty_cache()
+
+    # ---- the loops that drive the step kernels (BASELINE configs[2..4]); reported under "extras" -------------
+    def maxtime(seconds):
+        if dist is None:
+            return seconds
+        t = torch.tensor([seconds], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    loops = {}
+    from open_spiel_b200 import parallel
+    # MCTS: go 9x9, RandomRolloutEvaluator(1), uct_c=2, solve; independent roots sharded over GPUs
+    go = b2.Game("go", {"board_size": 9}, device=local)
+    trees, sims = 16384, 128
+    roots = go.new_batch(trees)
+    b2.mcts_search(roots, 8, seed=1, tree_index_offset=rank * trees)          # warm-up: allocations, table upload
+    barrier()
+    t0 = time.perf_counter()
+    out = b2.mcts_search(roots, sims, uct_c=2.0, n_rollouts=1, solve=True, seed=1, tree_index_offset=rank * trees)
+    torch.cuda.synchronize()
+    dt = maxtime(time.perf_counter() - t0)
+    nsims = parallel.allreduce_stats(out["sims_run"].sum().to(torch.int64).reshape(1))
+    loops["mcts_go9x9"] = {"sims_per_s": float(nsims.item()) / dt, "trees_per_gpu": trees, "sims_per_tree": sims,
+                           "seconds": dt, "errors": roots.error_count()[0]}
+    del roots, out
+    # self-play rollouts: breakthrough 8x8, 2^20 games per GPU, statistics all-reduced
+    bt = b2.Game("breakthrough", device=local)
+    games = 1 << 20
+    bb = bt.new_batch(games)
+    bb.rollout(seed=9, lane_offset=rank * games, n=1024)
+    bb.reset()
+    barrier()
+    t0 = time.perf_counter()
+    rets_r, plies_r = bb.rollout(seed=9, lane_offset=rank * games)
+    torch.cuda.synchronize()
+    dt = maxtime(time.perf_counter() - t0)
+    st = parallel.rollout_stats(rets_r, plies_r).tolist()
+    loops["rollouts_breakthrough"] = {"games_per_s": st[4] / dt, "plies_per_s": st[3] / dt, "p0_wins": st[0], "p1_wins": st[1],
+                                      "games": st[4], "seconds": dt}
+    del bb, rets_r, plies_r
+    # CFR: leduc_poker; single-GPU bit-exact solver (replicated per rank) and, for N > 1, the NCCL-sharded solver
+    leduc = b2.Game("leduc_poker", device=local)
+    solver = b2.CFRSolver(leduc)
+    solver.evaluate_and_update_policy(10)
+    torch.cuda.synchronize()
+    iters = 2000
+    t0 = time.perf_counter()
+    solver.evaluate_and_update_policy(iters)
+    torch.cuda.synchronize()
+    dt = maxtime(time.perf_counter() - t0)
+    loops["cfr_leduc"] = {"iters_per_s": iters / dt, "node_visits_per_s": iters * 2 * 9457 / dt, "iters": iters, "seconds": dt}
+    if world > 1:
+        dsolver = parallel.DistributedCFRSolver(leduc)
+        dsolver.evaluate_and_update_policy(5)
+        barrier()
+        t0 = time.perf_counter()
+        dsolver.evaluate_and_update_policy(200)
+        torch.cuda.synchronize()
+        dt = maxtime(time.perf_counter() - t0)
+        loops["cfr_leduc_nccl_sharded"] = {"iters_per_s": 200 / dt, "world": world, "seconds": dt}
+    barrier()
 
     if rank != 0:
         if dist is not None:
@@ -350,7 +431,7 @@ def run_gpu(args):
         "extras": {"fused_step_steps_per_s": world * n / (ms_fused / 1e3), "fused_ms": ms_fused,
                    "fused_gbs": BYTES_FUSED * n / (ms_fused / 1e3) / 1e9,
                    "legal_mask_per_s": world * n / (ms_mask / 1e3), "legal_mask_ms": ms_mask,
-                   "launches_total_incl_setup": total_launches},
+                   "launches_total_incl_setup": total_launches, "loops": loops, "cpu_reference_loops": cpu_loops()},
         "clocks": sampler.summary() if sampler else None,
     }
     print(json.dumps(line))
