@@ -230,12 +230,8 @@ __global__ void __launch_bounds__(kBlock) k_rollout(Ctx ctx, typename R::Cfg cfg
   R::load(s, ctx, i);
   int ply = 0;
   while (!R::terminal(s, cfg) && ply < max_plies) {
-    u32 m[R::kMaskWords];
-    R::legal_nonterminal(s, cfg, m);
-    int cnt = 0;
-    for (int w = 0; w < mask_words; ++w) cnt += __popc(m[w]);
-    u32 k = philox_uniform(seed, (u64)(i + lane_offset), (u32)ply, (u32)cnt);
-    int a = nth_set_bit(m, mask_words, (int)k);
+    auto draw = [&](u32 b, u32 n) { return philox_uniform(seed, (u64)(i + lane_offset), b, n); };
+    int a = sample_action<R>(s, cfg, mask_words, draw, (u32)ply);
     apply_known_legal<R>(s, a, cfg, ctx, i);
     ++ply;
   }

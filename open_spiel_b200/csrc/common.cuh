@@ -94,6 +94,32 @@ __device__ __forceinline__ bool apply_known_legal(S& s, int a, const Cfg& c, con
   return apply_known_legal_impl<R>(s, a, c, ctx, lane, 0);
 }
 
+// Uniform random legal action for playouts.  Rule cores may expose a cheap candidate superset
+// (R::num_candidates / R::candidate / R::is_legal_action, e.g. go: empty points + pass); a uniformly drawn candidate
+// is kept iff legal (rejection sampling = uniform over the legal actions), retry q draws at ply + 4096 q.
+// Otherwise the action is the k-th set bit of the legal mask.  `draw(b, n)` returns a uniform integer in [0, n).
+template <class R, class S, class Cfg, class Draw>
+__device__ __forceinline__ auto sample_action_impl(const S& s, const Cfg& c, int /*mask_words*/, Draw& draw, u32 ply, int)
+    -> decltype(R::num_candidates(s, c)) {
+  int n = R::num_candidates(s, c);
+  for (u32 retry = 0;; ++retry) {
+    int a = R::candidate(s, c, (int)draw(ply + 4096u * retry, (u32)n));
+    if (R::is_legal_action(s, c, a)) return a;
+  }
+}
+template <class R, class S, class Cfg, class Draw>
+__device__ __forceinline__ int sample_action_impl(const S& s, const Cfg& c, int mask_words, Draw& draw, u32 ply, long) {
+  u32 m[R::kMaskWords];
+  R::legal_nonterminal(s, c, m);
+  int cnt = 0;
+  for (int w = 0; w < mask_words; ++w) cnt += __popc(m[w]);
+  return nth_set_bit(m, mask_words, (int)draw(ply, (u32)cnt));
+}
+template <class R, class S, class Cfg, class Draw>
+__device__ __forceinline__ int sample_action(const S& s, const Cfg& c, int mask_words, Draw& draw, u32 ply) {
+  return sample_action_impl<R>(s, c, mask_words, draw, ply, 0);
+}
+
 // ---- 128-bit bitboards (hex: up to 121 cells; go: 9 rows x 10-bit stride) ------------------------------------
 struct B128 {
   u64 lo, hi;
@@ -111,6 +137,17 @@ __host__ __device__ __forceinline__ B128 b_shr(B128 a, int s) {
 __host__ __device__ __forceinline__ B128 b_bit(int i) { return i < 64 ? B128{1ull << i, 0} : B128{0, 1ull << (i - 64)}; }
 __host__ __device__ __forceinline__ bool b_test(B128 a, int i) { return i < 64 ? (a.lo >> i) & 1ull : (a.hi >> (i - 64)) & 1ull; }
 __device__ __forceinline__ int b_popc(B128 a) { return __popcll(a.lo) + __popcll(a.hi); }
+// position of the k-th (0-based) set bit; k < popcount
+__device__ __forceinline__ int b_select(B128 a, int k) {
+  int c0 = __popc((u32)a.lo), c1 = __popc((u32)(a.lo >> 32)), c2 = __popc((u32)a.hi);
+  if (k < c0) return (int)__fns((u32)a.lo, 0, k + 1);
+  k -= c0;
+  if (k < c1) return 32 + (int)__fns((u32)(a.lo >> 32), 0, k + 1);
+  k -= c1;
+  if (k < c2) return 64 + (int)__fns((u32)a.hi, 0, k + 1);
+  k -= c2;
+  return 96 + (int)__fns((u32)(a.hi >> 32), 0, k + 1);
+}
 __device__ __forceinline__ int b_ffs(B128 a) { return a.lo ? __ffsll((long long)a.lo) - 1 : 64 + __ffsll((long long)a.hi) - 1; }
 
 }  // namespace b2s

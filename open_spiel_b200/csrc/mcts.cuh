@@ -8,7 +8,8 @@
 // independent roots per GPU.  Random decisions are an explicit function of (seed, tree, simulation, position)
 // through Philox (common.cuh), the same function oracle/algorithms/mcts.cc uses, so trees match bit for bit:
 //   expansion #e:  Fisher-Yates over the ascending legal list, j = rng(key, e, i, 1, i+1) for i = n-1..1
-//   simulation #t, rollout #r, ply p:  index = rng(key, t, p, 2+r, num_legal)
+//   simulation #t, rollout #r, ply p:  k = rng(key, t, p + 4096 q, 2+r, C) over the C playout candidates
+//     (the legal actions; for go: empty non-ko points + pass), q = 0,1,.. until the candidate is legal
 // UCT arithmetic is done with explicitly rounded double operations (no FMA contraction) and log(N_parent)
 // comes from a table the HOST fills with std::log, so values equal the CPU's to the last bit.
 // Not implemented: chance nodes in the tree, PUCT / Dirichlet noise, the reference's node-budget garbage
@@ -153,12 +154,9 @@ __global__ void __launch_bounds__(128) k_mcts(Ctx rootctx, Ctx workctx, typename
         typename R::S w = s;
         u32 ply = 0;
         while (!R::terminal(w, cfg) && (int)ply < P.max_plies) {
-          u32 m[R::kMaskWords];
-          R::legal_nonterminal(w, cfg, m);
-          int cnt = 0;
-          for (int q = 0; q < P.mask_words; ++q) cnt += __popc(m[q]);
-          u32 k = rng_uniform(key, (u32)sim, ply, 2u + (u32)ro, (u32)cnt);
-          apply_known_legal<R>(w, nth_set_bit(m, P.mask_words, (int)k), cfg, workctx, tree);
+          auto draw = [&](u32 b, u32 n) { return rng_uniform(key, (u32)sim, b, 2u + (u32)ro, n); };
+          int act = sample_action<R>(w, cfg, P.mask_words, draw, ply);
+          apply_known_legal<R>(w, act, cfg, workctx, tree);
           ++ply;
         }
         float r[2];

@@ -166,9 +166,19 @@ struct GoRules {
   }
 
   // Stones (either colour) adjacent to `pts` that belong to chains with exactly one liberty.
+  // `pts` are empty points without empty neighbours.  A chain that touches an "open" empty point (one that has an
+  // empty neighbour) keeps that liberty whichever point of `pts` is played, so when many chains border `pts`
+  // those chains are found with one whole-board flood per colour and only the remaining chains — whose liberties
+  // are all surrounded points — are examined one by one.
   __device__ static __forceinline__ B128 atari_chains_near(const S& s, const Cfg& c, B128 pts, B128 empty) {
     B128 atari = {0, 0};
     B128 todo = b_and(nb4(pts, c), b_or(s.black, s.white));
+    if (b_popc(todo) > 4) {
+      B128 open = b_and(empty, nb4(empty, c));
+      B128 near_open = nb4(open, c);
+      B128 safe = b_or(flood(b_and(s.black, near_open), s.black, c), flood(b_and(s.white, near_open), s.white, c));
+      todo = b_andn(todo, safe);
+    }
     while (b_any(todo)) {
       int p = b_ffs(todo);
       B128 pb = b_bit(p);
@@ -195,14 +205,53 @@ struct GoRules {
     if (s.ko >= 0) legal = b_andn(legal, b_bit(s.ko));
     return legal;
   }
+  // Does the chain containing stone set `seed` (all of one colour `col`) have a liberty in `libs_allowed`?
+  // Quick accept when a seed stone itself touches an allowed empty point; otherwise flood the chain.
+  __device__ static __forceinline__ bool chain_has_liberty(B128 seed, B128 col, B128 libs_allowed, const Cfg& c) {
+    if (b_any(b_and(nb4(seed, c), libs_allowed))) return true;
+    B128 chain = flood(seed, col, c);
+    return b_any(b_and(nb4(chain, c), libs_allowed));
+  }
   __device__ static __forceinline__ bool legal_point(const S& s, const Cfg& c, int p) {
     B128 pb = b_bit(p);
     B128 empty = b_andn(c.board, b_or(s.black, s.white));
     if (!b_any(b_and(pb, empty)) || p == s.ko) return false;
-    if (b_any(b_and(nb4(pb, c), empty))) return true;
+    B128 nbp = nb4(pb, c);
+    if (b_any(b_and(nbp, empty))) return true;
     B128 own = s.to_play == 0 ? s.black : s.white, opp = s.to_play == 0 ? s.white : s.black;
-    B128 atari = atari_chains_near(s, c, pb, empty);
-    return b_any(b_and(nb4(pb, c), b_andn(own, atari))) || b_any(b_and(nb4(pb, c), b_and(opp, atari)));
+    B128 other = b_andn(empty, pb);                    // liberties other than p itself
+    // joins a friendly chain that keeps a liberty (one flood covers every friendly neighbour chain)
+    B128 mine = b_and(nbp, own);
+    if (b_any(mine) && chain_has_liberty(mine, own, other, c)) return true;
+    // captures an enemy chain whose only liberty is p
+    B128 todo = b_and(nbp, opp);
+    while (b_any(todo)) {
+      B128 q = b_bit(b_ffs(todo));
+      if (b_any(b_and(nb4(q, c), other))) { todo = b_andn(todo, q); continue; }
+      B128 chain = flood(q, opp, c);
+      if (!b_any(b_and(nb4(chain, c), other))) return true;
+      todo = b_andn(todo, chain);
+    }
+    return false;
+  }
+  // playout candidates: empty points other than the ko point (ascending), then pass
+  __device__ static __forceinline__ int num_candidates(const S& s, const Cfg& c) {
+    B128 e = b_andn(c.board, b_or(s.black, s.white));
+    if (s.ko >= 0) e = b_andn(e, b_bit(s.ko));
+    return b_popc(e) + 1;
+  }
+  __device__ static __forceinline__ int candidate(const S& s, const Cfg& c, int k) {
+    B128 e = b_andn(c.board, b_or(s.black, s.white));
+    if (s.ko >= 0) e = b_andn(e, b_bit(s.ko));
+    if (k >= b_popc(e)) return c.cells;
+    int p = b_select(e, k);
+    int r = p / kStride;
+    return r * c.n + (p - r * kStride);
+  }
+  __device__ static __forceinline__ bool is_legal_action(const S& s, const Cfg& c, int a) {
+    if (a == c.cells) return true;
+    int r = a / c.n;
+    return legal_point(s, c, r * kStride + (a - r * c.n));
   }
   // board bitset (stride 10) -> action-ordered bits (row*n + col) appended into words at bit offset `off`
   __device__ static __forceinline__ void deposit_rows(B128 x, const Cfg& c, u64* words, int off) {
@@ -246,7 +295,9 @@ struct GoRules {
       // capture enemy chains left without liberties
       B128 todo = b_and(nbp, opp), captured = {0, 0};
       while (b_any(todo)) {
-        B128 chain = flood(b_bit(b_ffs(todo)), opp, c);
+        B128 q = b_bit(b_ffs(todo));
+        if (b_any(b_and(nb4(q, c), empty))) { todo = b_andn(todo, q); continue; }   // that stone still has a liberty
+        B128 chain = flood(q, opp, c);
         if (!b_any(b_and(nb4(chain, c), empty))) captured = b_or(captured, chain);
         todo = b_andn(todo, chain);
       }

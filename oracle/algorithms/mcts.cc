@@ -9,8 +9,9 @@
 // kernels consume the identical function, so the search trees can be compared bit for bit:
 //   * expansion #e of a tree: Fisher-Yates over the ascending legal-action list, for i = n-1..1:
 //       j = RngUniform(key, e, i, 1, i + 1); swap(list[i], list[j])          (replaces std::shuffle, mcts.cc:294)
-//   * simulation #t, rollout #r, rollout ply p: index = RngUniform(key, t, p, 2 + r, num_legal)
-//                                                                          (replaces absl::Uniform, mcts.cc:54)
+//   * simulation #t, rollout #r, rollout ply p: draw q = 0, 1, ...: k = RngUniform(key, t, p + 4096 q, 2 + r, C)
+//       over the C rollout candidates (State::RolloutCandidates, = the legal actions except for go); the first
+//       legal candidate is played — a uniform draw over the legal actions    (replaces absl::Uniform, mcts.cc:54)
 //   key = seed + tree_index * 0x9E3779B97F4A7C15.
 #include <cmath>
 #include <limits>
@@ -44,6 +45,17 @@ bool CompareFinal(const Node& a, const Node& b) {                          // mc
   return a.total_reward < b.total_reward;
 }
 
+// Uniform random legal action by rejection from the candidate list; draw(b, n) supplies the random integers.
+template <typename Draw>
+int64_t SampleRolloutAction(const State& s, Draw draw, uint32_t ply) {
+  auto cand = s.RolloutCandidates();
+  auto legal = s.LegalActions();
+  for (uint32_t retry = 0;; ++retry) {
+    int64_t a = cand[draw(ply + 4096u * retry, (uint32_t)cand.size())];
+    for (auto l : legal) if (l == a) return a;
+  }
+}
+
 struct Search {
   uint64_t key;
   double uct_c, max_utility;
@@ -58,8 +70,7 @@ struct Search {
       auto ws = state.Clone();
       uint32_t ply = 0;
       while (!ws->IsTerminal()) {
-        auto actions = ws->LegalActions();
-        ws->ApplyAction(actions[RngUniform(key, sim, ply, 2 + r, (uint32_t)actions.size())]);
+        ws->ApplyAction(SampleRolloutAction(*ws, [&](uint32_t b, uint32_t n) { return RngUniform(key, sim, b, 2 + r, n); }, ply));
         ++ply;
       }
       auto returns = ws->Returns();

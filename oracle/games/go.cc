@@ -212,6 +212,17 @@ class GoState : public State {
     v.push_back(g_.n * g_.n);
     return v;
   }
+  std::vector<int64_t> RolloutCandidates() const override {
+    std::vector<int64_t> v;
+    if (IsTerminal()) return v;
+    for (int r = 0; r < g_.n; ++r)
+      for (int c = 0; c < g_.n; ++c) {
+        int p = Board::VPoint(r, c);
+        if (board_.color(p) == kEmpty && p != board_.ko()) v.push_back(r * g_.n + c);
+      }
+    v.push_back(g_.n * g_.n);
+    return v;
+  }
   // go.cc:225-230
   bool IsTerminal() const override {
     size_t h = history_.size();

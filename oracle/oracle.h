@@ -59,6 +59,11 @@ class State {
   virtual std::string InformationStateString(int) const { return ""; }
   virtual std::string ObservationString(int) const { return ToString(); }
   virtual std::vector<std::pair<int64_t, double>> ChanceOutcomes() const { return {}; }
+  // Superset of LegalActions() from which random playouts draw by rejection (a uniformly drawn candidate is kept
+  // iff it is legal, which is a uniform draw over the legal actions — what mcts.cc:51-55 asks for).  Default: the
+  // legal actions themselves (never rejected).  go overrides it with "empty points except the ko point, then
+  // pass", which spares the device the full 81-point legality scan on every playout ply.
+  virtual std::vector<int64_t> RolloutCandidates() const { return LegalActions(); }
   bool IsChanceNode() const { return CurrentPlayer() == kChancePlayerId; }
 
   // reference State::ApplyAction, open_spiel/spiel.cc:441-451

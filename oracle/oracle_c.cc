@@ -61,6 +61,11 @@ int orc_legal_actions(void* s, int64_t* out, int cap) {
   for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
   return (int)v.size();
 }
+int orc_rollout_candidates(void* s, int64_t* out, int cap) {
+  auto v = ((State*)s)->RolloutCandidates();
+  for (int i = 0; i < (int)v.size() && i < cap; ++i) out[i] = v[i];
+  return (int)v.size();
+}
 int orc_apply_action(void* s, int64_t a) {
   State* st = (State*)s;
   st->ApplyAction(a);

@@ -125,6 +125,13 @@ class OracleState:
         n = lib().orc_legal_actions(self._s, buf, cap)
         return list(buf[:n])
 
+    def rollout_candidates(self):
+        cap = max(self.game.num_distinct_actions, self.game.max_chance_outcomes, 1) + 8
+        buf = (C.c_int64 * cap)()
+        lib().orc_rollout_candidates.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+        n = lib().orc_rollout_candidates(self._s, buf, cap)
+        return list(buf[:n])
+
     def apply_action(self, a):
         if lib().orc_apply_action(self._s, int(a)):
             buf = C.create_string_buffer(256)

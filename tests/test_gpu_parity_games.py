@@ -153,8 +153,14 @@ def test_rollout_matches_oracle_given_same_random_stream():
             st = og.new_initial_state()
             ply = 0
             while not st.is_terminal():
-                la = st.legal_actions()
-                st.apply_action(la[philox_uniform(0x5EED, 1000 + i, ply, len(la))])
+                la, cand = st.legal_actions(), st.rollout_candidates()
+                retry = 0
+                while True:          # uniform over legal actions by rejection from the candidate list
+                    a = cand[philox_uniform(0x5EED, 1000 + i, ply + 4096 * retry, len(cand))]
+                    if a in la:
+                        break
+                    retry += 1
+                st.apply_action(a)
                 ply += 1
             assert ply == plies[i], (gs, i)
             assert st.returns() == rets[i].tolist(), (gs, i)
