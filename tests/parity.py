@@ -18,11 +18,13 @@ def mask_words_to_lists(words, width):
     return [np.nonzero(row)[0].tolist() for row in bits]
 
 
-def lockstep(game_string, n_lanes=512, seed=0, check_obs_every=3, max_plies=None, check_info_state=False):
-    """Play n_lanes random games in lock-step on device and oracle; assert equality of everything."""
+def lockstep(game_string, n_lanes=512, seed=0, check_obs_every=3, max_plies=None, check_info_state=False,
+             checker=OracleGame):
+    """Play n_lanes random games in lock-step on device and on the checker (the oracle restatement, or — passing
+    ref_lib.RefGame — the unmodified reference build); assert equality of everything after every move."""
     rng = np.random.RandomState(seed)
     game = b2.load_game(game_string)
-    ogame = OracleGame(game_string)
+    ogame = checker(game_string)
     assert game.num_distinct_actions() == ogame.num_distinct_actions
     assert game.max_game_length() == ogame.max_game_length
     assert game.num_players() == ogame.num_players
