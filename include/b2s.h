@@ -219,6 +219,11 @@ int  b2s_cfr_export(void* solver, double* regrets_h, double* cum_policy_h, doubl
 /* Restore tables (checkpoint / resume; cfr.cc:699-781 DeserializeCFRSolver).  iteration < 0 keeps the counter. */
 int  b2s_cfr_import(void* solver, const double* regrets_h, const double* cum_policy_h, const double* cur_policy_h,
                     int iteration, void* stream);
+/* NashConv of the average policy (use_average != 0; CFRAveragePolicy, cfr.cc:104-125) or of the current policy,
+ * computed on the device over the same flattened tree — replaces algorithms::NashConv / Exploitability
+ * (tabular_exploitability.cc) for the CFR loop of examples/cfr_example.cc:37-46; exploitability = nash_conv / 2.
+ * values_out (nullable): {best-response value p0, p1, on-policy value p0, p1}.  Synchronises `stream`. */
+int  b2s_cfr_nash_conv(void* solver, int use_average, double* nash_conv_out, double* values_out, void* stream);
 /* Device pointers of the three per-entry tables. */
 int  b2s_cfr_tables(void* solver, double** regrets_d, double** cum_policy_d, double** cur_policy_d);
 /* Multi-GPU CFR (the path's one real exchange step).  One player-traversal of iteration `iteration`

@@ -49,6 +49,7 @@ struct CfrDev {
   const int* is_off;           // [I + 1] offsets into the per-action tables
   const int* hist_off;         // [I + 1] offsets into hist
   const int* hist;             // decision nodes of each information state in DFS order
+  const int* is_level;         // [I] tree level of the information state's histories
   double* reach;               // [n][3]  (player 0, player 1, chance)
   double* edge_prob;           // [n]
   double* value;               // [n][2]
@@ -217,6 +218,98 @@ __global__ void __launch_bounds__(1024) k_cfr_apply(CfrDev d, int rm_plus) {
       double r = d.regrets[off + a];
       d.cur_policy[off + a] = sum > 0 ? (r > 0 ? __ddiv_rn(r, sum) : 0.0) : __ddiv_rn(1.0, (double)na);
     }
+  }
+}
+
+// ---- NashConv / exploitability of the average (or current) policy on the same flattened tree -------------------
+// Semantics: reference algorithms/tabular_exploitability.cc (NashConv = sum_p [BR_p(pi_-p) - v_p(pi)],
+// Exploitability = NashConv / num_players) with best responses as in algorithms/best_response.cc: at the
+// responder's information states the action maximising sum_h cf_reach(h) * value(child) is taken at every history.
+// out[0..1] = best-response values of players 0/1 at the root, out[2..3] = on-policy root values.
+__global__ void __launch_bounds__(1024) k_cfr_nashconv(CfrDev d, int use_average, double* pol, int* best, double* out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // the policy being evaluated (CFRAveragePolicy, cfr.cc:104-125: uniform where nothing was accumulated)
+  for (int I = tid; I < d.n_infosets; I += nt) {
+    int off = d.is_off[I], na = d.is_off[I + 1] - off;
+    if (use_average) {
+      double sum = 0.0;
+      for (int a = 0; a < na; ++a) sum += d.cum_policy[off + a];
+      for (int a = 0; a < na; ++a) pol[off + a] = sum == 0.0 ? 1.0 / na : d.cum_policy[off + a] / sum;
+    } else {
+      for (int a = 0; a < na; ++a) pol[off + a] = d.cur_policy[off + a];
+    }
+  }
+  __syncthreads();
+  // edge probabilities under the evaluated policy
+  for (int n = 1 + tid; n < d.n_nodes; n += nt) {
+    int par = d.parent[n];
+    d.edge_prob[n] = d.kind[par] == 1 ? d.chance_prob[n] : pol[d.is_off[d.infoset[par]] + d.aidx[n]];
+  }
+  __syncthreads();
+  // on-policy values
+  for (int l = d.n_levels - 1; l >= 0; --l) {
+    for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
+      double v0, v1;
+      if (d.kind[n] == 0) { v0 = d.ret[2 * n]; v1 = d.ret[2 * n + 1]; }
+      else {
+        v0 = 0.0; v1 = 0.0;
+        int fc = d.first_child[n];
+        for (int c = 0; c < d.nchild[n]; ++c) { v0 += d.edge_prob[fc + c] * d.value[2 * (fc + c)]; v1 += d.edge_prob[fc + c] * d.value[2 * (fc + c) + 1]; }
+      }
+      d.value[2 * n] = v0; d.value[2 * n + 1] = v1;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { out[2] = d.value[0]; out[3] = d.value[1]; }
+  __syncthreads();
+  for (int b = 0; b < 2; ++b) {
+    // counterfactual reach of every node for responder b: opponents' and chance's probabilities only
+    if (tid == 0) d.reach[0] = 1.0;
+    __syncthreads();
+    for (int l = 1; l < d.n_levels; ++l) {
+      for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
+        int par = d.parent[n];
+        double r = d.reach[3 * par];
+        if (!(d.kind[par] == 2 && d.actor[par] == b)) r *= d.edge_prob[n];
+        d.reach[3 * n] = r;
+      }
+      __syncthreads();
+    }
+    // best-response values bottom-up; value slot 0 is reused for V_b
+    for (int l = d.n_levels - 1; l >= 0; --l) {
+      // responder's information states at this level choose their action from their children's values
+      for (int I = tid; I < d.n_infosets; I += nt) {
+        if (d.is_player[I] != b || d.is_level[I] != l) continue;
+        int off = d.is_off[I], na = d.is_off[I + 1] - off;
+        int arg = 0;
+        double bestq = 0.0;
+        for (int a = 0; a < na; ++a) {
+          double q = 0.0;
+          for (int hh = d.hist_off[I]; hh < d.hist_off[I + 1]; ++hh) {
+            int h = d.hist[hh];
+            q += d.reach[3 * h] * d.value[2 * (d.first_child[h] + a)];
+          }
+          if (a == 0 || q > bestq) { bestq = q; arg = a; }
+        }
+        best[I] = arg;
+      }
+      __syncthreads();
+      for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
+        double v;
+        if (d.kind[n] == 0) v = d.ret[2 * n + b];
+        else if (d.kind[n] == 2 && d.actor[n] == b) v = d.value[2 * (d.first_child[n] + best[d.infoset[n]])];
+        else {
+          v = 0.0;
+          int fc = d.first_child[n];
+          for (int c = 0; c < d.nchild[n]; ++c) v += d.edge_prob[fc + c] * d.value[2 * (fc + c)];
+        }
+        d.value[2 * n] = v;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) out[b] = d.value[0];
+    __syncthreads();
+    // restore nothing: value/reach/edge_prob are scratch, rewritten by the next traversal
   }
 }
 
@@ -406,6 +499,16 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
   CK(upload(S, aidx, &d.aidx)); CK(upload(S, chance_prob, &d.chance_prob)); CK(upload(S, ret, &d.ret));
   CK(upload(S, infoset, &d.infoset)); CK(upload(S, S->is_player, &d.is_player)); CK(upload(S, S->is_off, &d.is_off));
   CK(upload(S, hist_off, &d.hist_off)); CK(upload(S, hist, &d.hist));
+  {
+    std::vector<int> node_level(N, 0), is_level(I, 0);
+    for (int l = 0; l + 1 < (int)level_off.size(); ++l)
+      for (int v = level_off[l]; v < level_off[l + 1]; ++v) node_level[v] = l;
+    for (int i = 0; i < I; ++i) {
+      is_level[i] = node_level[by_is[i][0]];
+      for (int v : by_is[i]) if (node_level[v] != is_level[i]) CK(fail("cfr: information state spans tree levels"));
+    }
+    CK(upload(S, is_level, &d.is_level));
+  }
   CK(alloc_d(S, 3 * (size_t)N, &d.reach)); CK(alloc_d(S, N, &d.edge_prob)); CK(alloc_d(S, 2 * (size_t)N, &d.value));
   CK(alloc_d(S, E, &d.regrets)); CK(alloc_d(S, E, &d.cum_policy)); CK(alloc_d(S, E, &d.cur_policy));
   CK(alloc_d(S, 2 * (size_t)E, &d.delta));
@@ -514,6 +617,29 @@ int b2s_cfr_delta_buffer(void* solver, double** delta_d) {
 int b2s_cfr_set_iteration(void* solver, int iteration) {
   if (!solver) return fail("cfr: null solver");
   ((CfrSolver*)solver)->iteration = iteration;
+  return 0;
+}
+
+// NashConv of the average policy (use_average != 0) or of the current policy; exploitability = nash_conv / 2.
+// values_out (nullable, 4 doubles): best-response values of players 0 and 1, on-policy values of players 0 and 1.
+int b2s_cfr_nash_conv(void* solver, int use_average, double* nash_conv_out, double* values_out, void* stream) {
+  if (!solver || !nash_conv_out) return fail("cfr: null argument");
+  CfrSolver* S = (CfrSolver*)solver;
+  B2S_CU(cudaSetDevice(S->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  double* pol = nullptr; int* best = nullptr; double* out = nullptr;
+  B2S_CU(cudaMalloc((void**)&pol, sizeof(double) * (S->d.n_entries + 1)));
+  B2S_CU(cudaMalloc((void**)&best, sizeof(int) * (S->d.n_infosets + 1)));
+  B2S_CU(cudaMalloc((void**)&out, sizeof(double) * 4));
+  k_cfr_nashconv<<<1, 1024, 0, st>>>(S->d, use_average, pol, best, out);
+  ++g_launches;
+  double h[4];
+  cudaError_t e = cudaMemcpyAsync(h, out, sizeof h, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(pol); cudaFree(best); cudaFree(out);
+  if (e != cudaSuccess) return cuda_fail(e, "k_cfr_nashconv");
+  *nash_conv_out = (h[0] - h[2]) + (h[1] - h[3]);
+  if (values_out) memcpy(values_out, h, sizeof h);
   return 0;
 }
 

@@ -513,6 +513,18 @@ class CFRSolver:
         check(lib().b2s_cfr_tables(self._h, C.byref(r), C.byref(c), C.byref(u)))
         return r.value, c.value, u.value
 
+    def nash_conv(self, average=True):
+        """algorithms::NashConv (tabular_exploitability.cc) of the average (default) or current policy, on the device."""
+        nc = C.c_double()
+        vals = (C.c_double * 4)()
+        check(lib().b2s_cfr_nash_conv(self._h, int(bool(average)), C.byref(nc), vals, None))
+        self.last_values = list(vals)
+        return nc.value
+
+    def exploitability(self, average=True):
+        """algorithms::Exploitability = NashConv / num_players."""
+        return self.nash_conv(average) / 2.0
+
     def average_policy(self):
         """CFRAveragePolicy (cfr.cc:104-125): {key bytes: [(action, prob)]}, uniform where nothing accumulated."""
         t = self.table()

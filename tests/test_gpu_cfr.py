@@ -105,3 +105,25 @@ def test_sharded_traversal_path_agrees_within_tolerance():
         assert np.abs(t1[f] - tr[f]).max() <= TOL
         assert np.abs(t3[f] - tr[f]).max() <= TOL
     assert np.abs(t1["regrets"]).max() > 1.0       # the tables are not trivially zero
+
+
+@pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("gs,checkpoints", [("kuhn_poker", [1, 10, 100, 300]), ("leduc_poker", [1, 5, 20])])
+def test_device_nash_conv_matches_reference(gs, checkpoints):
+    """The evaluation step of the CFR loop (examples/cfr_example.cc:37-46): NashConv / Exploitability of the average
+    policy, device vs the unmodified reference's tabular_exploitability.cc, to 1e-9."""
+    game = b2.load_game(gs)
+    dev = b2.CFRSolver(game)
+    ref = ref_lib.RefCFR(ref_lib.RefGame(gs))
+    done = 0
+    for it in checkpoints:
+        dev.evaluate_and_update_policy(it - done)
+        ref.iterate(it - done)
+        done = it
+        assert abs(dev.nash_conv() - ref.nash_conv()) <= 1e-9, (gs, it)
+        assert abs(dev.exploitability() - ref.exploitability()) <= 1e-9
+    if gs == "kuhn_poker":
+        assert dev.exploitability() <= 0.05                      # cfr_test.cc:36-62
+        assert abs(dev.last_values[2] - (-1.0 / 18.0)) <= 1e-3   # game value for player 0 (cfr_test.cc:40-41)
+    else:
+        assert dev.nash_conv() <= 2.0                            # cfr_test.cc:299-301 (after >= 10 iterations)
