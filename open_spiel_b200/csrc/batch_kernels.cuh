@@ -231,8 +231,7 @@ __global__ void __launch_bounds__(kBlock) k_rollout(Ctx ctx, typename R::Cfg cfg
   int ply = 0;
   while (!R::terminal(s, cfg) && ply < max_plies) {
     auto draw = [&](u32 b, u32 n) { return philox_uniform(seed, (u64)(i + lane_offset), b, n); };
-    int a = sample_action<R>(s, cfg, mask_words, draw, (u32)ply);
-    apply_known_legal<R>(s, a, cfg, ctx, i);
+    playout_step<R>(s, cfg, ctx, i, mask_words, draw, (u32)ply);
     ++ply;
   }
   R::store(s, ctx, i);

@@ -94,30 +94,34 @@ __device__ __forceinline__ bool apply_known_legal(S& s, int a, const Cfg& c, con
   return apply_known_legal_impl<R>(s, a, c, ctx, lane, 0);
 }
 
-// Uniform random legal action for playouts.  Rule cores may expose a cheap candidate superset
-// (R::num_candidates / R::candidate / R::is_legal_action, e.g. go: empty points + pass); a uniformly drawn candidate
-// is kept iff legal (rejection sampling = uniform over the legal actions), retry q draws at ply + 4096 q.
+// One playout step: choose a uniformly random legal action and apply it; returns the action.
+// Rule cores may expose a cheap candidate superset (R::num_candidates / R::candidate, e.g. go: empty non-ko points
+// + pass) together with R::play_candidate, which applies the candidate or reports it illegal: a uniformly drawn
+// candidate is kept iff legal (rejection sampling = uniform over the legal actions); retry q draws at ply + 4096 q.
 // Otherwise the action is the k-th set bit of the legal mask.  `draw(b, n)` returns a uniform integer in [0, n).
 template <class R, class S, class Cfg, class Draw>
-__device__ __forceinline__ auto sample_action_impl(const S& s, const Cfg& c, int /*mask_words*/, Draw& draw, u32 ply, int)
-    -> decltype(R::num_candidates(s, c)) {
+__device__ __forceinline__ auto playout_step_impl(S& s, const Cfg& c, const Ctx& ctx, long long lane, int /*mask_words*/,
+                                                  Draw& draw, u32 ply, int) -> decltype(R::num_candidates(s, c)) {
   int n = R::num_candidates(s, c);
   for (u32 retry = 0;; ++retry) {
     int a = R::candidate(s, c, (int)draw(ply + 4096u * retry, (u32)n));
-    if (R::is_legal_action(s, c, a)) return a;
+    if (R::play_candidate(s, a, c, ctx, lane)) return a;
   }
 }
 template <class R, class S, class Cfg, class Draw>
-__device__ __forceinline__ int sample_action_impl(const S& s, const Cfg& c, int mask_words, Draw& draw, u32 ply, long) {
+__device__ __forceinline__ int playout_step_impl(S& s, const Cfg& c, const Ctx& ctx, long long lane, int mask_words,
+                                                 Draw& draw, u32 ply, long) {
   u32 m[R::kMaskWords];
   R::legal_nonterminal(s, c, m);
   int cnt = 0;
   for (int w = 0; w < mask_words; ++w) cnt += __popc(m[w]);
-  return nth_set_bit(m, mask_words, (int)draw(ply, (u32)cnt));
+  int a = nth_set_bit(m, mask_words, (int)draw(ply, (u32)cnt));
+  apply_known_legal<R>(s, a, c, ctx, lane);
+  return a;
 }
 template <class R, class S, class Cfg, class Draw>
-__device__ __forceinline__ int sample_action(const S& s, const Cfg& c, int mask_words, Draw& draw, u32 ply) {
-  return sample_action_impl<R>(s, c, mask_words, draw, ply, 0);
+__device__ __forceinline__ int playout_step(S& s, const Cfg& c, const Ctx& ctx, long long lane, int mask_words, Draw& draw, u32 ply) {
+  return playout_step_impl<R>(s, c, ctx, lane, mask_words, draw, ply, 0);
 }
 
 // ---- 128-bit bitboards (hex: up to 121 cells; go: 9 rows x 10-bit stride) ------------------------------------

@@ -155,8 +155,7 @@ __global__ void __launch_bounds__(128) k_mcts(Ctx rootctx, Ctx workctx, typename
         u32 ply = 0;
         while (!R::terminal(w, cfg) && (int)ply < P.max_plies) {
           auto draw = [&](u32 b, u32 n) { return rng_uniform(key, (u32)sim, b, 2u + (u32)ro, n); };
-          int act = sample_action<R>(w, cfg, P.mask_words, draw, ply);
-          apply_known_legal<R>(w, act, cfg, workctx, tree);
+          playout_step<R>(w, cfg, workctx, tree, P.mask_words, draw, ply);
           ++ply;
         }
         float r[2];

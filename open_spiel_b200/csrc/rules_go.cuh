@@ -248,11 +248,6 @@ struct GoRules {
     int r = p / kStride;
     return r * c.n + (p - r * kStride);
   }
-  __device__ static __forceinline__ bool is_legal_action(const S& s, const Cfg& c, int a) {
-    if (a == c.cells) return true;
-    int r = a / c.n;
-    return legal_point(s, c, r * kStride + (a - r * c.n));
-  }
   // board bitset (stride 10) -> action-ordered bits (row*n + col) appended into words at bit offset `off`
   __device__ static __forceinline__ void deposit_rows(B128 x, const Cfg& c, u64* words, int off) {
     for (int r = 0; r < c.n; ++r) {
@@ -321,8 +316,20 @@ struct GoRules {
   __device__ static __forceinline__ bool apply(S& s, int a, const Cfg& c, const Ctx& ctx, long long lane) {
     return apply_impl(s, a, c, ctx, lane, false);
   }
-  // the caller guarantees `a` came from this state's legal set (rollouts, tree descent)
+  // the caller guarantees `a` came from this state's legal set (tree descent)
   __device__ static __forceinline__ bool apply_legal(S& s, int a, const Cfg& c, const Ctx& ctx, long long lane) {
+    return apply_impl(s, a, c, ctx, lane, true);
+  }
+  // playout step: try a candidate (an empty non-ko point or pass); false = it was illegal, state untouched.
+  // Two restructurings of this step were measured in the MCTS kernel and dropped: (i) replacing the per-chain walks by
+  // two liberty-seeded whole-board floods per move (35 % slower), (ii) one flattened loop over a per-move work list
+  // of chains with early exit on the first liberty (7-35 % slower: 148 registers/thread cost a resident warp per
+  // scheduler).  See profiles/README.md.
+  __device__ static __forceinline__ bool play_candidate(S& s, int a, const Cfg& c, const Ctx& ctx, long long lane) {
+    if (a != c.cells) {
+      int r = a / c.n;
+      if (!legal_point(s, c, r * kStride + (a - r * c.n))) return false;
+    }
     return apply_impl(s, a, c, ctx, lane, true);
   }
 
