@@ -403,7 +403,11 @@ const char* GameOpsT<R>::mcts(const Ctx& roots, const Ctx& work, long long n, co
     a.mask_words = info.mask_words;
     a.max_plies = info.max_game_length + 4;
     a.max_utility = info.max_utility;
-    k_mcts<R, R::kMaxPath><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(roots, work, cfg, a, n); ++g_launches;
+    // many trees: cap registers (6 CTAs of 128 threads per SM) so more warps are resident; few trees (deep
+    // searches are memory-limited to a few thousand roots): let the compiler keep everything in registers
+    if (n >= 100000) k_mcts<R, R::kMaxPath, 6><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(roots, work, cfg, a, n);
+    else k_mcts<R, R::kMaxPath, 1><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(roots, work, cfg, a, n);
+    ++g_launches;
     return nullptr;
   } else {
     return "mcts: games with chance nodes / imperfect information have no device MCTS";

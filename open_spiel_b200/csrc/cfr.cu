@@ -50,6 +50,9 @@ struct CfrDev {
   const int* hist_off;         // [I + 1] offsets into hist
   const int* hist;             // decision nodes of each information state in DFS order
   const int* is_level;         // [I] tree level of the information state's histories
+  const int* policy_index;     // [n] index into cur_policy of the edge into n (-1 when the parent is a chance node)
+  const signed char* par_actor;// [n] actor of the parent (0/1 player, 2 chance)
+  const double* chance_reach;  // [n] the chance player's reach of n (product of chance probabilities along the path)
   double* reach;               // [n][3]  (player 0, player 1, chance)
   double* edge_prob;           // [n]
   double* value;               // [n][2]
@@ -60,31 +63,39 @@ struct CfrDev {
 };
 
 __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration0, int linear_averaging, int rm_plus) {
+  // One traversal = (1) edge probabilities from the frozen policy, (2) L level steps in which the reach
+  // probabilities move one level DOWN while the state values move one level UP (the two sweeps are independent:
+  // the reference's all-zero-reach pruning, cfr.cc:350-355, only ever replaces values that are multiplied by a zero
+  // probability before they are used, so it cannot change any table entry), (3) one thread per information state of
+  // the updating player: regrets and average policy over its histories in DFS order, then regret matching.
+  // Regret matching of the other player's information states (cfr.cc:693-697 sweeps the whole table) would recompute
+  // the same policy from unchanged regrets, so it is skipped.
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int L = d.n_levels;
   for (int it = 0; it < iters; ++it) {
     const double iteration = (double)(iteration0 + it + 1);          // ++iteration_ (cfr.cc:264)
     for (int p = 0; p < 2; ++p) {
-      // ---- reach probabilities, top-down (new_reach_probabilities[current_player] *= prob, cfr.cc:457) ----
-      if (tid == 0) { d.reach[0] = 1.0; d.reach[1] = 1.0; d.reach[2] = 1.0; }
-      __syncthreads();
-      for (int l = 1; l < d.n_levels; ++l) {
-        for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
-          int par = d.parent[n];
-          double r0 = d.reach[3 * par], r1 = d.reach[3 * par + 1], r2 = d.reach[3 * par + 2];
-          double prob = d.kind[par] == 1 ? d.chance_prob[n] : d.cur_policy[d.is_off[d.infoset[par]] + d.aidx[n]];
-          int a = d.actor[par];
-          if (a == 0) r0 = __dmul_rn(r0, prob); else if (a == 1) r1 = __dmul_rn(r1, prob); else r2 = __dmul_rn(r2, prob);
-          d.reach[3 * n] = r0; d.reach[3 * n + 1] = r1; d.reach[3 * n + 2] = r2;
-          d.edge_prob[n] = prob;
-        }
-        __syncthreads();
+      for (int n = 1 + tid; n < d.n_nodes; n += nt) {
+        int pi = d.policy_index[n];
+        d.edge_prob[n] = pi >= 0 ? d.cur_policy[pi] : d.chance_prob[n];
       }
-      // ---- state values, bottom-up (state_value[i] += prob * child_value[i], cfr.cc:461-463) ----
-      for (int l = d.n_levels - 1; l >= 0; --l) {
-        for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
+      if (tid == 0) { d.reach[0] = 1.0; d.reach[1] = 1.0; }
+      __syncthreads();
+      for (int k = 0; k < L; ++k) {
+        int ld = k + 1;                       // reach: new_reach_probabilities[current_player] *= prob (cfr.cc:457)
+        if (ld < L) {
+          for (int n = d.level_off[ld] + tid; n < d.level_off[ld + 1]; n += nt) {
+            int par = d.parent[n];
+            double r0 = d.reach[2 * par], r1 = d.reach[2 * par + 1];
+            int a = d.par_actor[n];
+            if (a == 0) r0 = __dmul_rn(r0, d.edge_prob[n]); else if (a == 1) r1 = __dmul_rn(r1, d.edge_prob[n]);
+            d.reach[2 * n] = r0; d.reach[2 * n + 1] = r1;
+          }
+        }
+        int lu = L - 1 - k;                   // values: state_value[i] += prob * child_value[i] (cfr.cc:461-463)
+        for (int n = d.level_off[lu] + tid; n < d.level_off[lu + 1]; n += nt) {
           double v0, v1;
           if (d.kind[n] == 0) { v0 = d.ret[2 * n]; v1 = d.ret[2 * n + 1]; }
-          else if (d.kind[n] == 2 && d.reach[3 * n] == 0.0 && d.reach[3 * n + 1] == 0.0) { v0 = 0.0; v1 = 0.0; }
           else {
             v0 = 0.0; v1 = 0.0;
             int fc = d.first_child[n];
@@ -98,15 +109,15 @@ __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration
         }
         __syncthreads();
       }
-      // ---- regret and average-policy update for player p's information states (cfr.cc:379-405) ----
+      // regret / average-policy update (cfr.cc:379-405) + regret matching (cfr.cc:596-615) for player p
       for (int I = tid; I < d.n_infosets; I += nt) {
         if (d.is_player[I] != p) continue;
         int off = d.is_off[I], na = d.is_off[I + 1] - off;
         for (int hh = d.hist_off[I]; hh < d.hist_off[I + 1]; ++hh) {
           int h = d.hist[hh];
-          double self_reach = d.reach[3 * h + p];
-          double cfr_reach = 1.0;                                       // CounterFactualReachProb, index order
-          for (int i = 0; i < 3; ++i) if (i != p) cfr_reach = __dmul_rn(cfr_reach, d.reach[3 * h + i]);
+          double self_reach = d.reach[2 * h + p];
+          // CounterFactualReachProb: 1.0 * reach[other player] * reach[chance], in index order
+          double cfr_reach = __dmul_rn(__dmul_rn(1.0, d.reach[2 * h + (1 - p)]), d.chance_reach[h]);
           double vh = d.value[2 * h + p];
           int fc = d.first_child[h];
           for (int a = 0; a < na; ++a) {
@@ -117,11 +128,6 @@ __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration
             d.cum_policy[off + a] = __dadd_rn(d.cum_policy[off + a], inc);
           }
         }
-      }
-      __syncthreads();
-      // ---- regret matching over the whole table (cfr.cc:596-615, 683-697) ----
-      for (int I = tid; I < d.n_infosets; I += nt) {
-        int off = d.is_off[I], na = d.is_off[I + 1] - off;
         double sum = 0.0;
         for (int a = 0; a < na; ++a) {
           double r = d.regrets[off + a];
@@ -499,6 +505,19 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
   CK(upload(S, aidx, &d.aidx)); CK(upload(S, chance_prob, &d.chance_prob)); CK(upload(S, ret, &d.ret));
   CK(upload(S, infoset, &d.infoset)); CK(upload(S, S->is_player, &d.is_player)); CK(upload(S, S->is_off, &d.is_off));
   CK(upload(S, hist_off, &d.hist_off)); CK(upload(S, hist, &d.hist));
+  {
+    std::vector<int> policy_index(N, -1);
+    std::vector<signed char> par_actor(N, 2);
+    std::vector<double> chance_reach(N, 1.0);
+    for (int v = 1; v < N; ++v) {
+      int par = parent[v];
+      par_actor[v] = actor[par];
+      if (kind[par] == 2) policy_index[v] = S->is_off[infoset[par]] + aidx[v];
+      chance_reach[v] = kind[par] == 1 ? chance_reach[par] * chance_prob[v] : chance_reach[par];   // parents precede children
+    }
+    CK(upload(S, policy_index, &d.policy_index)); CK(upload(S, par_actor, &d.par_actor));
+    CK(upload(S, chance_reach, &d.chance_reach));
+  }
   {
     std::vector<int> node_level(N, 0), is_level(I, 0);
     for (int l = 0; l + 1 < (int)level_off.size(); ++l)

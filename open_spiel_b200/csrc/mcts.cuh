@@ -61,8 +61,8 @@ __device__ __forceinline__ double uct_value(const MctsNode& ch, u32 parent_visit
   return __dadd_rn(q, __dmul_rn(P.uct_c, u));
 }
 
-template <class R, int MAXPATH>
-__global__ void __launch_bounds__(128) k_mcts(Ctx rootctx, Ctx workctx, typename R::Cfg cfg, MctsArgs P, long long n_trees) {
+template <class R, int MAXPATH, int MINBLOCKS>
+__global__ void __launch_bounds__(128, MINBLOCKS) k_mcts(Ctx rootctx, Ctx workctx, typename R::Cfg cfg, MctsArgs P, long long n_trees) {
   long long tree = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tree >= n_trees) return;
   typename R::S root;

@@ -67,9 +67,8 @@ struct ConnectFourRules {
   // Legal mask = the free top cells (bits c*h1 + rows-1) gathered into bits 0..cols-1.  The top bits are split
   // at bit 32 into two 32-bit words; within a word the bits sit h1 apart, and one 32-bit multiply whose
   // partial products cannot collide packs them contiguously.  Checked for every column subset below.
-  static __host__ u32 gather_word(u32 w, int first_pos, int n, int h1, u32* mul, int* sh) {
-    // bits at first_pos + j*h1 (j < n) -> after >> first_pos at j*h1; multiplier sum_j 2^{(h1-1)*(n-1-j)}
-    (void)w;
+  static __host__ u32 gather_word(int n, int h1, u32* mul, int* sh) {
+    // n bits sitting h1 apart (at j*h1 after the shift) -> multiplier sum_j 2^{(h1-1)*(n-1-j)} packs them at *sh
     u32 m = 0;
     for (int j = 0; j < n; ++j) {
       int e = (h1 - 1) * (n - 1 - j);
@@ -96,8 +95,8 @@ struct ConnectFourRules {
     while (c.cols_lo < c.cols && c.cols_lo * c.h1 + c.rows - 1 < 32) ++c.cols_lo;
     if (c.cols > 24) return;
     u32 ok = 1;
-    if (c.cols_lo > 0) ok &= gather_word(0, c.rows - 1, c.cols_lo, c.h1, &c.gmul_lo, &c.gsh_lo);
-    if (c.cols_lo < c.cols) ok &= gather_word(0, 0, c.cols - c.cols_lo, c.h1, &c.gmul_hi, &c.gsh_hi);
+    if (c.cols_lo > 0) ok &= gather_word(c.cols_lo, c.h1, &c.gmul_lo, &c.gsh_lo);
+    if (c.cols_lo < c.cols) ok &= gather_word(c.cols - c.cols_lo, c.h1, &c.gmul_hi, &c.gsh_hi);
     if (!ok) return;
     for (u32 subset = 0; subset < (1u << c.cols); ++subset) {       // exhaustive check of the multiply trick
       u64 ft = 0;

@@ -9,12 +9,10 @@ std::unique_ptr<Game> LoadGame(const std::string& name, const Params& p) {
   if (name == "tic_tac_toe") return MakeTicTacToe(p);
   if (name == "connect_four") return MakeConnectFour(p);
   if (name == "breakthrough") return MakeBreakthrough(p);
-#ifndef ORACLE_MINIMAL
   if (name == "hex") return MakeHex(p);
   if (name == "go") return MakeGo(p);
   if (name == "kuhn_poker") return MakeKuhnPoker(p);
   if (name == "leduc_poker") return MakeLeducPoker(p);
-#endif
   return nullptr;
 }
 }  // namespace oracle
