@@ -406,7 +406,7 @@ const char* GameOpsT<R>::mcts(const Ctx& roots, const Ctx& work, long long n, co
     // many trees: cap registers (6 CTAs of 128 threads per SM) so more warps are resident; few trees (deep
     // searches are memory-limited to a few thousand roots): let the compiler keep everything in registers
     if (n >= 100000) k_mcts<R, R::kMaxPath, 6><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(roots, work, cfg, a, n);
-    else k_mcts<R, R::kMaxPath, 1><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(roots, work, cfg, a, n);
+    else k_mcts<R, R::kMaxPath, 4><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(roots, work, cfg, a, n);
     ++g_launches;
     return nullptr;
   } else {
