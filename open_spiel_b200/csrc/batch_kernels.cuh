@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kBlock) k_reset(Ctx ctx, typename R::Cfg cfg, 
 // access stays coalesced; all loads (action + packed state) are issued before any compute so that a thread
 // has ILP independent 128-bit requests in flight (the kernel is a pure HBM stream).
 template <class R, int ILP>
-__global__ void __launch_bounds__(kBlock) k_apply(Ctx ctx, typename R::Cfg cfg, const int* __restrict__ actions, long long n) {
+__global__ void __launch_bounds__(kBlock, R::kMinBlocks) k_apply(Ctx ctx, typename R::Cfg cfg, const int* __restrict__ actions, long long n) {
   pdl_wait();
   long long base = (long long)blockIdx.x * (kBlock * ILP) + threadIdx.x;
   int a[ILP];
