@@ -30,7 +30,7 @@ struct GoRules {
   static constexpr int kPlayers = 2;
   static constexpr int kMaxPath = 176;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kIlp = 1;
-  static constexpr int kMinBlocks = 1;
+  static constexpr int kMinBlocks = 4;
   static constexpr bool kHasInfoState = false;
   static constexpr int kStride = 10;
 

@@ -18,7 +18,7 @@ struct HexRules {
   static constexpr int kPlayers = 2;
   static constexpr int kMaxPath = 128;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kIlp = 1;
-  static constexpr int kMinBlocks = 1;
+  static constexpr int kMinBlocks = 4;
   static constexpr bool kHasInfoState = false;
 
   struct Cfg {

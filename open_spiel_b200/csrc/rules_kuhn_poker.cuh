@@ -16,7 +16,7 @@ struct KuhnRules {
   static constexpr int kPlayers = 2;
   static constexpr int kMaxPath = 0;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kIlp = 4;
-  static constexpr int kMinBlocks = 1;
+  static constexpr int kMinBlocks = 4;
   static constexpr bool kHasInfoState = true;
   struct Cfg { int dummy; };
   struct S { u32 h; };
