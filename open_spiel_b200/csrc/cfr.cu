@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration
   // the updating player: regrets and average policy over its histories in DFS order, then regret matching.
   // Regret matching of the other player's information states (cfr.cc:693-697 sweeps the whole table) would recompute
   // the same policy from unchanged regrets, so it is skipped.
+  // One CTA on purpose: the same kernel as an 8-CTA thread-block cluster (cluster.sync() = barrier.cluster + MEMBAR.GPU +
+  // L1 invalidate per level step, arrays in global memory) was measured at the same 11.2e3 it/s on Leduc and 3x slower
+  // on Kuhn — the level steps are latency-bound, and the cluster barrier costs what the extra threads save.
   const int tid = threadIdx.x, nt = blockDim.x;
   const int L = d.n_levels;
   for (int it = 0; it < iters; ++it) {
