@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(kBlock) k_step_fused(Ctx ctx, typename R::Cfg 
   }
 }
 
+// R::kObsBitPacked (optional): ObsPack is the tensor as a flat little-endian bit string in output order
+template <class R> constexpr auto obs_bitpacked(int) -> decltype(R::kObsBitPacked) { return R::kObsBitPacked; }
+template <class R> constexpr bool obs_bitpacked(long) { return false; }
+
 // ObservationTensor / InformationStateTensor.  A warp owns 32 consecutive lanes: every thread packs
 // its own state's tensor into shared memory (game-specific compact form), then the warp streams the
 // 32*size floats of its tile out as fully coalesced 16-byte stores.
@@ -208,10 +212,19 @@ __global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, in
     int st = (int)(((u64)e0 * magic) >> 32);         // e0 / size (magic verified on the host for the range)
     int within = e0 - st * size;
     float v[4];
+    if (obs_bitpacked<R>(0) && within + 4 <= size) {
+      // 0/1 tensors kept as a flat bit string in output order: one funnel shift yields the four bits of this float4
+      const u32* b = reinterpret_cast<const u32*>(&wp[st]);
+      int wi = within >> 5, sh = within & 31;
+      u32 lo = b[wi], hi = sh > 28 ? b[wi + 1] : 0u;    // (within+3)>>5 == wi+1 exactly when sh > 28: in range
+      u32 nib = __funnelshift_r(lo, hi, sh);
+      v[0] = (float)(nib & 1u); v[1] = (float)((nib >> 1) & 1u); v[2] = (float)((nib >> 2) & 1u); v[3] = (float)((nib >> 3) & 1u);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[j] = R::obs_elem(wp[st], cfg, within);
-      if (++within == size) { within = 0; ++st; }     // a float4 may straddle two lanes' tensors
+      for (int j = 0; j < 4; ++j) {
+        v[j] = R::obs_elem(wp[st], cfg, within);
+        if (++within == size) { within = 0; ++st; }     // a float4 may straddle two lanes' tensors
+      }
     }
     reinterpret_cast<float4*>(base)[q] = make_float4(v[0], v[1], v[2], v[3]);
   }

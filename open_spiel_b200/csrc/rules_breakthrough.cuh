@@ -134,6 +134,7 @@ struct BreakthroughRules {
     s.mover ^= 1;
     return true;
   }
+  static constexpr bool kObsBitPacked = true;   // ObsPack = the tensor as a flat bit string in output order
   struct ObsPack { u64 w[kObsWords]; };
   // planes 0 = black, 1 = white, 2 = empty; [plane][r][c] — breakthrough.cc:286-342
   __device__ static __forceinline__ void obs_pack(const S& s, const Cfg& c, int, int, ObsPack& p) {

@@ -31,6 +31,9 @@ struct ConnectFourRules {
     int gather;        // 1: legal mask by multiply-gather (verified exhaustively on the host)
     u32 gmul_lo, gmul_hi;   // per-32-bit-half gather multipliers
     int gsh_lo, gsh_hi, cols_lo;
+    int rgather;       // 1: row extraction (bits c*h1 -> bits 0..cols-1) by multiply-gather, verified on the host
+    u32 rmul_lo, rmul_hi;
+    int rsh_lo, rsh_hi, rcols_lo, rfirst_hi;
     u64 top;           // top playable cell of every column
     u64 board;         // all playable cells
   };
@@ -55,6 +58,7 @@ struct ConnectFourRules {
       c.board |= ((1ull << c.rows) - 1) << (col * c.h1);
     }
     make_gather(c);
+    make_row_gather(c);
     gi.num_players = 2;
     gi.num_distinct_actions = c.cols;              // connect_four.h:179
     gi.max_game_length = c.rows * c.cols;          // connect_four.h:200
@@ -105,6 +109,34 @@ struct ConnectFourRules {
       if (gather_eval(c, ft) != subset) return;
     }
     c.gather = 1;
+  }
+
+  // Row r of a column-major board = bits r + c*h1.  After shifting by r they sit at c*h1; the same verified
+  // multiply-gather as the legal mask packs them into bits 0..cols-1 (used by the observation tensor).
+  static __host__ __device__ __forceinline__ u32 row_gather_eval(const Cfg& c, u64 t) {
+    u32 lo = (u32)t, hi = (u32)(t >> 32);
+    u32 out = ((lo * c.rmul_lo) >> c.rsh_lo) & ((1u << c.rcols_lo) - 1);
+    if (c.rcols_lo < c.cols) out |= ((((hi >> c.rfirst_hi) * c.rmul_hi) >> c.rsh_hi) & ((1u << (c.cols - c.rcols_lo)) - 1)) << c.rcols_lo;
+    return out;
+  }
+  static __host__ void make_row_gather(Cfg& c) {
+    c.rgather = 0; c.rmul_lo = c.rmul_hi = 0; c.rsh_lo = c.rsh_hi = 0; c.rfirst_hi = 0;
+    c.rcols_lo = 0;
+    while (c.rcols_lo < c.cols && c.rcols_lo * c.h1 < 32) ++c.rcols_lo;
+    if (c.cols > 24) return;
+    u32 ok = 1;
+    if (c.rcols_lo > 0) ok &= gather_word(c.rcols_lo, c.h1, &c.rmul_lo, &c.rsh_lo);
+    if (c.rcols_lo < c.cols) { ok &= gather_word(c.cols - c.rcols_lo, c.h1, &c.rmul_hi, &c.rsh_hi); c.rfirst_hi = c.rcols_lo * c.h1 - 32; }
+    if (!ok) return;
+    u64 colbits = 0;
+    for (int col = 0; col < c.cols; ++col) colbits |= 1ull << (col * c.h1);
+    for (u32 subset = 0; subset < (1u << c.cols); ++subset) {       // exhaustive check, with every other bit set as noise
+      u64 t = 0;
+      for (int col = 0; col < c.cols; ++col) if ((subset >> col) & 1u) t |= 1ull << (col * c.h1);
+      if (row_gather_eval(c, t) != subset) return;
+    }
+    c.rgather = 1;
+    (void)colbits;
   }
 
   __device__ static __forceinline__ bool has_line(u64 b, const Cfg& c) {
@@ -202,6 +234,7 @@ struct ConnectFourRules {
   }
 
   // Observation tensor as a packed bit string in output (CHW) order.
+  static constexpr bool kObsBitPacked = true;   // ObsPack = the tensor as a flat bit string in output order
   struct ObsPack { u64 w[kObsWords]; };
   __device__ static __forceinline__ void obs_pack(const S& s, const Cfg& c, int player, int /*which*/, ObsPack& p) {
     u64 planes[3];
@@ -213,6 +246,17 @@ struct ConnectFourRules {
     }
     planes[2] = ~(xs(s, c) | s.o) & c.board;
     p.w[0] = p.w[1] = p.w[2] = 0;
+    if (c.rgather) {
+      u64 colbits = c.board & ~(c.board << 1);             // bit c*h1 of every column
+      int e = 0;
+      for (int pl = 0; pl < 3; ++pl)
+        for (int r = 0; r < c.rows; ++r, e += c.cols) {
+          u64 row = (u64)row_gather_eval(c, (planes[pl] >> r) & colbits);
+          p.w[e >> 6] |= row << (e & 63);
+          if ((e & 63) + c.cols > 64) p.w[(e >> 6) + 1] |= row >> (64 - (e & 63));
+        }
+      return;
+    }
     int e = 0;
     for (int pl = 0; pl < 3; ++pl)
       for (int r = 0; r < c.rows; ++r)

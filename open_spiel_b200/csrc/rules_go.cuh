@@ -335,6 +335,7 @@ struct GoRules {
   }
 
   // planes black, white, empty in board-point order, plane 3 = "white to play" (go.cc:138-158)
+  static constexpr bool kObsBitPacked = true;   // ObsPack = the tensor as a flat bit string in output order
   struct ObsPack { u64 w[6]; };
   __device__ static __forceinline__ void obs_pack(const S& s, const Cfg& c, int, int, ObsPack& p) {
     for (int k = 0; k < 6; ++k) p.w[k] = 0;

@@ -181,44 +181,51 @@ struct HexRules {
   }
   // Observation planes by label value + 4 (hex.h:68-78, hex.cc:392-396):
   // 0 WhiteWin, 1 WhiteWest, 2 WhiteEast, 3 White, 4 Empty, 5 Black, 6 BlackSouth, 7 BlackNorth, 8 BlackWin.
-  struct ObsPack { u64 w[18]; };      // plane k = words 2k (cells 0-63), 2k+1 (cells 64-127)
-  __device__ static __forceinline__ void put(ObsPack& p, int k, B128 v) { p.w[2 * k] = v.lo; p.w[2 * k + 1] = v.hi; }
+  static constexpr bool kObsBitPacked = true;   // ObsPack = the tensor as a flat bit string in output order
+  struct ObsPack { u64 w[18]; };      // up to 9 * 121 = 1089 bits
+  // OR the low `cells` bits of v into the flat string at bit offset `off`
+  __device__ static __forceinline__ void put_flat(ObsPack& p, int off, B128 v) {
+    int i = off >> 6, sh = off & 63;
+    p.w[i] |= v.lo << sh;
+    u64 c1 = sh ? (v.lo >> (64 - sh)) : 0ull;
+    if (i + 1 < 18) p.w[i + 1] |= c1 | (v.hi << sh);
+    if (i + 2 < 18 && sh) p.w[i + 2] |= v.hi >> (64 - sh);
+  }
   __device__ static __forceinline__ void obs_pack(const S& s, const Cfg& c, int, int, ObsPack& p) {
     B128 both = b_and(s.la, s.lb), onlyA = b_andn(s.la, s.lb), onlyB = b_andn(s.lb, s.la), any = b_or(s.la, s.lb);
-    B128 empty = b_andn(c.board, b_or(s.black, s.white)), z = {0, 0};
+    B128 empty = b_andn(c.board, b_or(s.black, s.white));
+    for (int k = 0; k < 18; ++k) p.w[k] = 0;
     if (c.plain) {            // CellStateToPlainPlane, hex.cc:76-93: 0 black, 1 white, 2 empty
-      put(p, 0, s.black); put(p, 1, s.white); put(p, 2, empty);
-      for (int k = 3; k < 9; ++k) put(p, k, z);
+      B128 pl[3] = {s.black, s.white, empty};
+      if (c.cols == c.rows) {
+        for (int k = 0; k < 3; ++k) put_flat(p, k * c.cells, pl[k]);
+      } else {
+        // TensorView<3>{3, num_cols, num_rows} indexed {plane, cell / num_cols, cell % num_cols} (hex.cc:383-388):
+        // offset = plane*cells + a*num_rows + b with a = cell / num_cols, b = cell % num_cols; on non-square boards
+        // several cells alias one offset and the reference stores 1.0 for each, i.e. the bits are OR-ed.
+        for (int k = 0; k < 3; ++k)
+          for (int cell = 0; cell < c.cells; ++cell)
+            if (b_test(pl[k], cell)) {
+              int e = k * c.cells + (cell / c.cols) * c.rows + (cell % c.cols);
+              p.w[e >> 6] |= 1ull << (e & 63);
+            }
+      }
       return;
     }
-    put(p, 0, b_and(s.white, both));
-    put(p, 1, b_and(s.white, onlyA));
-    put(p, 2, b_and(s.white, onlyB));
-    put(p, 3, b_andn(s.white, any));
-    put(p, 4, empty);
-    put(p, 5, b_andn(s.black, any));
-    put(p, 6, b_and(s.black, onlyB));
-    put(p, 7, b_and(s.black, onlyA));
-    put(p, 8, b_and(s.black, both));
+    // planes by label value + 4 (hex.h:68-78, hex.cc:392-396):
+    // 0 WhiteWin, 1 WhiteWest, 2 WhiteEast, 3 White, 4 Empty, 5 Black, 6 BlackSouth, 7 BlackNorth, 8 BlackWin
+    put_flat(p, 0 * c.cells, b_and(s.white, both));
+    put_flat(p, 1 * c.cells, b_and(s.white, onlyA));
+    put_flat(p, 2 * c.cells, b_and(s.white, onlyB));
+    put_flat(p, 3 * c.cells, b_andn(s.white, any));
+    put_flat(p, 4 * c.cells, empty);
+    put_flat(p, 5 * c.cells, b_andn(s.black, any));
+    put_flat(p, 6 * c.cells, b_and(s.black, onlyB));
+    put_flat(p, 7 * c.cells, b_and(s.black, onlyA));
+    put_flat(p, 8 * c.cells, b_and(s.black, both));
   }
-  __device__ static __forceinline__ u32 bit_at(const ObsPack& p, int plane, int cell) {
-    return (u32)(p.w[2 * plane + (cell >> 6)] >> (cell & 63)) & 1u;
-  }
-  __device__ static __forceinline__ float obs_elem(const ObsPack& p, const Cfg& c, int e) {
-    int plane = (int)(((u64)(u32)e * c.cells_magic) >> 32);
-    int w = e - plane * c.cells;
-    if (c.plain) {
-      // TensorView<3>{3, num_cols, num_rows} indexed {plane, cell / num_cols, cell % num_cols} (hex.cc:383-388):
-      // offset = plane*cells + a*num_rows + b with a = cell / num_cols (< rows), b = cell % num_cols (< cols).
-      // On non-square boards several cells alias one offset; the reference stores 1.0 for each, so OR them.
-      u32 on = 0;
-      for (int a = 0; a < c.rows; ++a) {
-        int b = w - a * c.rows;
-        if (b >= 0 && b < c.cols) on |= bit_at(p, plane, a * c.cols + b);
-      }
-      return on ? 1.f : 0.f;
-    }
-    return bit_at(p, plane, w) ? 1.f : 0.f;
+  __device__ static __forceinline__ float obs_elem(const ObsPack& p, const Cfg&, int e) {
+    return (float)((p.w[e >> 6] >> (e & 63)) & 1ull);
   }
 };
 

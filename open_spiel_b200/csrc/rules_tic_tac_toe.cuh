@@ -63,6 +63,7 @@ struct TicTacToeRules {
     s.b |= 1u << (a + 9 * mover(s));
     return true;
   }
+  static constexpr bool kObsBitPacked = true;   // ObsPack = the tensor as a flat bit string in output order
   struct ObsPack { u32 w; };
   // planes by CellState enum: 0 empty, 1 nought (player 1), 2 cross (player 0) — tic_tac_toe.h:51-55
   __device__ static __forceinline__ void obs_pack(const S& s, const Cfg&, int, int, ObsPack& p) {
