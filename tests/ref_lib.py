@@ -193,3 +193,15 @@ class RefCFR:
 
     def nash_conv(self):
         return lib().ref_cfr_nash_conv(self.game._g, self._c)
+
+
+def ref_mcts(game, state, uct_c, max_simulations, n_rollouts=1, solve=True, seed=0):
+    """The unmodified reference's MCTSBot::MCTSearch (RandomRolloutEvaluator); returns root children stats."""
+    L = lib()
+    cap = game.num_distinct_actions + 4
+    acts, vis, rew = (C.c_int64 * cap)(), (C.c_int * cap)(), (C.c_double * cap)()
+    best, rv = C.c_int64(), C.c_int()
+    n = L.ref_mcts_search(game._g, state._s, uct_c, max_simulations, n_rollouts, int(solve), seed, acts, vis, rew, cap,
+                          C.byref(best), C.byref(rv))
+    assert n >= 0, L.ref_last_error()
+    return {"children": [(acts[i], vis[i], rew[i]) for i in range(n)], "best_action": best.value, "root_visits": rv.value}

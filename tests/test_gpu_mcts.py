@@ -120,3 +120,40 @@ def test_mcts_root_invariants_many_trees():
     assert not torch.equal(out["visits"], out3["visits"])
     # different trees use different random streams
     assert len({tuple(r) for r in v[:64].cpu().tolist()}) > 32
+
+
+def test_device_mcts_matches_reference_mctsbot_in_distribution():
+    """The reference's RNG streams (std::shuffle, absl::Uniform) cannot be reproduced (SURVEY §8c), so against the
+    UNMODIFIED MCTSBot the comparison is statistical: over many independent searches of the same connect_four
+    position, the mean share of simulations each root action receives must agree (uct_c = 2, 400 simulations, no
+    solver), and so must the mean root value."""
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not shipped")
+    gs, prefix = "connect_four", [3, 3, 2]
+    sims, trees = 400, 512
+    game = b2.load_game(gs)
+    batch = game.new_batch(trees)
+    for a in prefix:
+        batch.apply_actions(torch.full((trees,), a, dtype=torch.int32, device=batch._dev))
+    out = b2.mcts_search(batch, sims, uct_c=2.0, n_rollouts=1, solve=False, seed=2024)
+    v = out["visits"].double()
+    dev_share = (v / v.sum(dim=1, keepdim=True)).mean(dim=0).cpu().numpy()
+    dev_value = float((out["total_reward"].sum(dim=1) / v.sum(dim=1)).mean())
+    rg = ref_lib.RefGame(gs)
+    st = rg.new_initial_state()
+    for a in prefix:
+        st.apply_action(a)
+    n_ref = 256
+    share = np.zeros(7)
+    value = 0.0
+    for seed in range(n_ref):
+        r = ref_lib.ref_mcts(rg, st, 2.0, sims, 1, False, seed + 1)
+        tot = sum(vv for _, vv, _ in r["children"])
+        for a, vv, _ in r["children"]:
+            share[a] += vv / tot / n_ref
+        value += sum(rw for _, _, rw in r["children"]) / tot / n_ref
+    # standard error of a mean share over a few hundred searches is ~0.005; allow 0.03
+    assert np.abs(dev_share - share).max() < 0.03, (dev_share, share)
+    assert abs(dev_value - value) < 0.05, (dev_value, value)
+    assert int(np.argmax(dev_share)) == int(np.argmax(share))
