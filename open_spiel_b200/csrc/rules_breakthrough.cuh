@@ -135,6 +135,27 @@ struct BreakthroughRules {
     return true;
   }
   static constexpr bool kObsBitPacked = true;   // ObsPack = the tensor as a flat bit string in output order
+  // playout candidates: piece k/3 (ascending cell order) moving in direction k%3; -1 when it leaves the board,
+  // the capture id when a diagonal lands on an enemy piece, else the plain-move id (apply() rejects blocked moves)
+  __device__ static __forceinline__ int num_candidates(const S& s, const Cfg& c) {
+    return 3 * __popcll(s.mover == 0 ? s.b : (s.w & c.board));
+  }
+  __device__ static __forceinline__ int candidate(const S& s, const Cfg& c, int k) {
+    u64 white = s.w & c.board;
+    u64 mine = s.mover == 0 ? s.b : white, theirs = s.mover == 0 ? white : s.b;
+    int pi = k / 3, o = k - 3 * pi;
+    int c0 = __popc((u32)mine);
+    int cell = pi < c0 ? (int)__fns((u32)mine, 0, pi + 1) : 32 + (int)__fns((u32)(mine >> 32), 0, pi - c0 + 1);
+    int r = cell / c.cols, col = cell - r * c.cols;
+    int rp = s.mover == 0 ? r + 1 : r - 1, cp = col + o - 1;
+    if (rp < 0 || rp >= c.rows || cp < 0 || cp >= c.cols) return -1;
+    int dir = s.mover * 3 + o;
+    int cap = (o != 1 && ((theirs >> (rp * c.cols + cp)) & 1ull)) ? 1 : 0;
+    return (cell * 6 + dir) * 2 + cap;
+  }
+  __device__ static __forceinline__ bool play_candidate(S& s, int a, const Cfg& c, const Ctx& ctx, long long lane) {
+    return a >= 0 && apply(s, a, c, ctx, lane);
+  }
   struct ObsPack { u64 w[kObsWords]; };
   // planes 0 = black, 1 = white, 2 = empty; [plane][r][c] — breakthrough.cc:286-342
   __device__ static __forceinline__ void obs_pack(const S& s, const Cfg& c, int, int, ObsPack& p) {

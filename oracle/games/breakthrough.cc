@@ -41,6 +41,25 @@ class BtState : public State {
       }
     return v;
   }
+  // Playout candidates (see oracle.h): for every own piece in ascending cell order, its three forward moves
+  // (left diagonal, straight, right diagonal); a move that leaves the board is listed as -1 (never legal), a
+  // diagonal onto an enemy piece as the capture id, anything else as the plain-move id (legal iff the target is empty).
+  std::vector<int64_t> RolloutCandidates() const override {
+    std::vector<int64_t> v;
+    if (IsTerminal()) return v;
+    int mine = cur_ == 0 ? kBlack : kWhite, theirs = cur_ == 0 ? kWhite : kBlack;
+    for (int r = 0; r < rows_; ++r)
+      for (int c = 0; c < cols_; ++c) {
+        if (At(r, c) != mine) continue;
+        for (int o = 0; o < 3; ++o) {
+          int dir = cur_ * 3 + o, rp = r + kDR[dir], cp = c + kDC[dir];
+          if (!In(rp, cp)) { v.push_back(-1); continue; }
+          int64_t base = ((int64_t)(r * cols_ + c) * 6 + dir) * 2;
+          v.push_back(base + ((o != 1 && At(rp, cp) == theirs) ? 1 : 0));
+        }
+      }
+    return v;
+  }
   bool IsTerminal() const override { return winner_ >= 0 || pieces_[0] == 0 || pieces_[1] == 0; }  // :308-310
   std::vector<double> Returns() const override {   // :312-320
     if (winner_ == 0 || pieces_[1] == 0) return {1.0, -1.0};
