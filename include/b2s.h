@@ -160,18 +160,19 @@ int b2s_rollout(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, floa
 /* ---- MCTS ---------------------------------------------------------------------------------- */
 
 /* Replaces algorithms::MCTSBot (open_spiel/algorithms/mcts.h:149-230) with a RandomRolloutEvaluator
- * (mcts.h:97-111) for n independent search roots at once: one tree per root, UCT selection, optional
+ * (mcts.h:97-111) for n independent search roots at once: one tree per root, UCT or PUCT selection, optional
  * MCTS-Solver, run entirely on the device.  Field meaning = the MCTSBot constructor arguments
  * (mcts.h:161-169): uct_c, max_simulations, solve, seed; n_rollouts = RandomRolloutEvaluator's.
  * Deterministic perfect-information games only (tic_tac_toe, connect_four, breakthrough, hex, go).
  * The reference's max_memory_mb garbage collection is not reproduced: max_nodes_total bounds the node
  * arena shared by all trees (0 = size from free device memory); a tree that cannot allocate stops and is
  * counted by b2s_error_count. */
+enum { B2S_MCTS_UCT = 0, B2S_MCTS_PUCT = 1 };   /* UCTValue mcts.cc:90-101 / PUCTValue :103-112 (uniform prior, :74-87) */
 typedef struct b2s_mcts_config {
   int32_t max_simulations;
   int32_t n_rollouts;
   int32_t solve;
-  int32_t reserved;
+  int32_t child_selection_policy;   /* ChildSelectionPolicy (mcts.h:148): B2S_MCTS_UCT or B2S_MCTS_PUCT */
   double uct_c;
   uint64_t seed;
   int64_t tree_index_offset;   /* tree i uses random stream (seed, i + tree_index_offset): shard roots across GPUs */

@@ -38,7 +38,7 @@ class GameInfo(C.Structure):
 
 class MctsConfig(C.Structure):
     _fields_ = [("max_simulations", C.c_int32), ("n_rollouts", C.c_int32), ("solve", C.c_int32),
-                ("reserved", C.c_int32), ("uct_c", C.c_double), ("seed", C.c_uint64),
+                ("child_selection_policy", C.c_int32), ("uct_c", C.c_double), ("seed", C.c_uint64),
                 ("tree_index_offset", C.c_int64), ("max_nodes_total", C.c_int64)]
 
 

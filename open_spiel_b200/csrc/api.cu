@@ -360,6 +360,8 @@ int b2s_mcts_search(void* roots_batch, int64_t n_trees, const b2s_mcts_config* c
   if (int r = check(roots_batch, n_trees)) return r;
   if (!cfg || !visit_counts_d || !total_reward_d || !best_action_d) return fail("mcts: null argument");
   if (cfg->max_simulations < 1 || cfg->n_rollouts < 1) return fail("mcts: max_simulations and n_rollouts must be >= 1");
+  if (cfg->child_selection_policy != B2S_MCTS_UCT && cfg->child_selection_policy != B2S_MCTS_PUCT)
+    return fail("mcts: unknown child_selection_policy");
   if (n_trees == 0) return 0;
   Batch* B = (Batch*)roots_batch;
   cudaStream_t st = (cudaStream_t)stream;
@@ -408,6 +410,7 @@ int b2s_mcts_search(void* roots_batch, int64_t n_trees, const b2s_mcts_config* c
   MctsArgs a;
   memset(&a, 0, sizeof a);
   a.sims = cfg->max_simulations; a.n_rollouts = cfg->n_rollouts; a.solve = cfg->solve; a.uct_c = cfg->uct_c;
+  a.puct = cfg->child_selection_policy == B2S_MCTS_PUCT;
   a.seed = cfg->seed; a.tree_offset = cfg->tree_index_offset; a.log_table = B->mcts_log;
   a.pool = B->mcts_pool; a.pool_top = B->mcts_top; a.pool_cap = B->mcts_pool_cap;
   a.visits_out = visit_counts_d; a.reward_out = total_reward_d; a.outcome_out = outcome_p0_d;

@@ -12,7 +12,8 @@
 //     (the legal actions; for go: empty non-ko points + pass), q = 0,1,.. until the candidate is legal
 // UCT arithmetic is done with explicitly rounded double operations (no FMA contraction) and log(N_parent)
 // comes from a table the HOST fills with std::log, so values equal the CPU's to the last bit.
-// Not implemented: chance nodes in the tree, PUCT / Dirichlet noise, the reference's node-budget garbage
+// Both child selection policies (UCT, PUCT with the rollout evaluator's uniform prior) are implemented.
+// Not implemented: chance nodes in the tree, Dirichlet noise, the reference's node-budget garbage
 // collection (mcts.cc:441-482) — a tree that exhausts the arena stops and is reported as an error.
 #pragma once
 #include "common.cuh"
@@ -32,7 +33,7 @@ struct __align__(16) MctsNode {     // SearchNode (mcts.h:114-146) without the h
 };
 
 struct MctsArgs {
-  int sims, n_rollouts, solve, num_actions, mask_words, max_plies;
+  int sims, n_rollouts, solve, num_actions, mask_words, max_plies, puct;
   double uct_c, max_utility;
   u64 seed;
   long long tree_offset;
@@ -59,6 +60,15 @@ __device__ __forceinline__ double uct_value(const MctsNode& ch, u32 parent_visit
   double q = __ddiv_rn(ch.total_reward, n);
   double u = __dsqrt_rn(__ddiv_rn(P.log_table[parent_visits], n));
   return __dadd_rn(q, __dmul_rn(P.uct_c, u));
+}
+
+// PUCTValue (mcts.cc:103-112) with RandomRolloutEvaluator's uniform prior 1/|children| (mcts.cc:74-87); `cp` is
+// (uct_c * prior) * sqrt(N_parent), the part shared by all children of one parent, in the reference's
+// left-to-right evaluation order.
+__device__ __forceinline__ double puct_value(const MctsNode& ch, double cp) {
+  if (ch.has_outcome) return (double)(ch.player == 0 ? ch.out0 : ch.out1);
+  double q = ch.visits ? __ddiv_rn(ch.total_reward, (double)ch.visits) : 0.0;
+  return __dadd_rn(q, __ddiv_rn(cp, (double)(ch.visits + 1u)));
 }
 
 template <class R, int MAXPATH, int MINBLOCKS>
@@ -129,9 +139,17 @@ __global__ void __launch_bounds__(128, MINBLOCKS) k_mcts(Ctx rootctx, Ctx workct
       int nch = pool[cur].nchild;
       double best = __longlong_as_double(0xfff0000000000000LL);
       u32 chosen = first;
-      for (int i = 0; i < nch; ++i) {
-        double v = uct_value(pool[first + i], pv, P);
-        if (v > best) { best = v; chosen = first + i; }
+      if (P.puct) {
+        double cp = __dmul_rn(__dmul_rn(P.uct_c, __ddiv_rn(1.0, (double)nch)), __dsqrt_rn((double)pv));
+        for (int i = 0; i < nch; ++i) {
+          double v = puct_value(pool[first + i], cp);
+          if (v > best) { best = v; chosen = first + i; }
+        }
+      } else {
+        for (int i = 0; i < nch; ++i) {
+          double v = uct_value(pool[first + i], pv, P);
+          if (v > best) { best = v; chosen = first + i; }
+        }
       }
       cur = chosen;
       apply_known_legal<R>(s, (int)pool[cur].action, cfg, workctx, tree);

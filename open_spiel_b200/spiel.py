@@ -396,8 +396,14 @@ def _reset_errors(self):
 BatchedState._reset_errors = _reset_errors
 
 
+class ChildSelectionPolicy:
+    """algorithms::ChildSelectionPolicy (mcts.h:148)."""
+    UCT = 0
+    PUCT = 1
+
+
 def mcts_search(batch, max_simulations, uct_c=2.0, n_rollouts=1, solve=True, seed=0, tree_index_offset=0,
-                n_trees=None, max_nodes_total=0):
+                n_trees=None, max_nodes_total=0, child_selection_policy=ChildSelectionPolicy.UCT):
     """Batched MCTSBot.mcts_search (python/pybind11/bots.cc:129-149 -> algorithms/mcts.cc:353-467) over the lanes of
     `batch`.  Returns dict of device tensors: visits [n, A] int32, total_reward [n, A] float64, outcome_p0 [n, A]
     float32 (NaN = unproven), best_action [n] int32, sims_run [n] int32."""
@@ -412,7 +418,7 @@ def mcts_search(batch, max_simulations, uct_c=2.0, n_rollouts=1, solve=True, see
         "best_action": torch.empty((n,), dtype=torch.int32, device=dev),
         "sims_run": torch.empty((n,), dtype=torch.int32, device=dev),
     }
-    cfg = MctsConfig(int(max_simulations), int(n_rollouts), int(bool(solve)), 0, float(uct_c), int(seed),
+    cfg = MctsConfig(int(max_simulations), int(n_rollouts), int(bool(solve)), int(child_selection_policy), float(uct_c), int(seed),
                      int(tree_index_offset), int(max_nodes_total))
     check(lib().b2s_mcts_search(batch._h, n, C.byref(cfg), out["visits"].data_ptr(), out["total_reward"].data_ptr(),
                                 out["outcome_p0"].data_ptr(), out["best_action"].data_ptr(), out["sims_run"].data_ptr(),
@@ -435,20 +441,22 @@ class RandomRolloutEvaluator:
 
 
 class MCTSBot:
-    """Mirror of pyspiel.MCTSBot(game, evaluator, uct_c, max_simulations, max_memory_mb, solve, seed, verbose)
-    (python/pybind11/bots.cc:129-149, algorithms/mcts.h:161-169) over the device search."""
+    """Mirror of pyspiel.MCTSBot(game, evaluator, uct_c, max_simulations, max_memory_mb, solve, seed, verbose,
+    child_selection_policy) (python/pybind11/bots.cc:129-149, algorithms/mcts.h:161-169) over the device search."""
 
-    def __init__(self, game, evaluator, uct_c, max_simulations, max_memory_mb=1000, solve=True, seed=0, verbose=False):
+    def __init__(self, game, evaluator, uct_c, max_simulations, max_memory_mb=1000, solve=True, seed=0, verbose=False,
+                 child_selection_policy=ChildSelectionPolicy.UCT):
         if not isinstance(evaluator, RandomRolloutEvaluator):
             raise B2SError("the device MCTSBot supports RandomRolloutEvaluator only")
         self.game, self.evaluator = game, evaluator
         self.uct_c, self.max_simulations, self.solve, self.seed = float(uct_c), int(max_simulations), bool(solve), int(seed)
         self.max_nodes = (int(max_memory_mb) << 20) // 32        # arena nodes are 32 B
+        self.child_selection_policy = int(child_selection_policy)
 
     def mcts_search(self, state):
         """Returns the root statistics of one search from `state` (a scalar State adapter)."""
         return mcts_search(state._b, self.max_simulations, self.uct_c, self.evaluator.n_rollouts, self.solve, self.seed,
-                           n_trees=1, max_nodes_total=self.max_nodes)
+                           n_trees=1, max_nodes_total=self.max_nodes, child_selection_policy=self.child_selection_policy)
 
     def step(self, state):
         """Bot::Step (mcts.cc:233-266): the best action at `state`."""

@@ -37,6 +37,12 @@ double UctValue(const Node& n, int parent_explore_count, double uct_c) {   // mc
   return n.total_reward / n.explore_count + uct_c * std::sqrt(std::log(parent_explore_count) / n.explore_count);
 }
 
+double PuctValue(const Node& n, int parent_explore_count, double uct_c, double prior) {   // mcts.cc:103-112
+  if (!n.outcome.empty()) return n.outcome[n.player];
+  return ((n.explore_count != 0 ? n.total_reward / n.explore_count : 0) +
+          uct_c * prior * std::sqrt(parent_explore_count) / (n.explore_count + 1));
+}
+
 bool CompareFinal(const Node& a, const Node& b) {                          // mcts.cc:114-125
   double out = (a.player >= 0 && a.player < (int)a.outcome.size()) ? a.outcome[a.player] : 0;
   double out_b = (b.player >= 0 && b.player < (int)b.outcome.size()) ? b.outcome[b.player] : 0;
@@ -59,6 +65,7 @@ int64_t SampleRolloutAction(const State& s, Draw draw, uint32_t ply) {
 struct Search {
   uint64_t key;
   double uct_c, max_utility;
+  bool puct = false;               // ChildSelectionPolicy (mcts.h:148)
   int n_rollouts;
   bool solve;
   uint32_t expansions = 0;
@@ -98,7 +105,9 @@ struct Search {
       Node* chosen = nullptr;
       double max_value = -std::numeric_limits<double>::infinity();
       for (Node& child : cur->children) {
-        double val = UctValue(child, cur->explore_count, uct_c);
+        // the prior is RandomRolloutEvaluator::Prior's 1.0 / legal_actions.size() (mcts.cc:74-87)
+        double val = puct ? PuctValue(child, cur->explore_count, uct_c, 1.0 / cur->children.size())
+                          : UctValue(child, cur->explore_count, uct_c);
         if (val > max_value) { max_value = val; chosen = &child; }
       }
       cur = chosen;
@@ -158,7 +167,8 @@ extern "C" {
 int orc_mcts_search(void* game, void* state, double uct_c, int max_simulations, int n_rollouts, int solve,
                     uint64_t seed, uint64_t tree_index, int64_t* child_actions, int* child_visits,
                     double* child_rewards, double* child_outcome_p0, int cap, int64_t* best_action,
-                    int* root_visits, double* root_outcome_p0, long* nodes_out, int* sims_run) {
+                    int* root_visits, double* root_outcome_p0, long* nodes_out, int* sims_run,
+                    int child_selection_policy) {
   using namespace oracle;
   Game* g = (Game*)game;
   State* s = (State*)state;
@@ -168,6 +178,7 @@ int orc_mcts_search(void* game, void* state, double uct_c, int max_simulations, 
   srch.max_utility = g->info.max_utility;
   srch.n_rollouts = n_rollouts;
   srch.solve = solve != 0;
+  srch.puct = child_selection_policy == 1;
   Node root;
   root.player = s->CurrentPlayer();
   int ran = srch.Run(&root, *s, max_simulations);

@@ -53,16 +53,35 @@ CASES = [
 ]
 
 
+PUCT_CASES = [
+    ("tic_tac_toe", 48, 4, 300, 1, True),
+    ("connect_four", 32, 10, 300, 1, True),
+    ("breakthrough(rows=6,columns=6)", 16, 8, 150, 1, False),
+    ("go(board_size=5)", 24, 8, 150, 1, True),
+]
+
+
 @pytest.mark.parametrize("gs,n,prefix,sims,nroll,solve", CASES, ids=["%s-%d" % (c[0], c[3]) for c in CASES])
 def test_device_mcts_equals_oracle_mcts(gs, n, prefix, sims, nroll, solve):
-    game, batch, states = make_roots(gs, n, prefix, seed=hash(gs) % 1000)
+    _check_against_oracle(gs, n, prefix, sims, nroll, solve, puct=False)
+
+
+@pytest.mark.parametrize("gs,n,prefix,sims,nroll,solve", PUCT_CASES, ids=["%s-%d" % (c[0], c[3]) for c in PUCT_CASES])
+def test_device_puct_equals_oracle_puct(gs, n, prefix, sims, nroll, solve):
+    """ChildSelectionPolicy::PUCT (mcts.cc:103-112, 328-335) with the rollout evaluator's uniform prior."""
+    _check_against_oracle(gs, n, prefix, sims, nroll, solve, puct=True)
+
+
+def _check_against_oracle(gs, n, prefix, sims, nroll, solve, puct):
+    game, batch, states = make_roots(gs, n, prefix, seed=sum(map(ord, gs)) % 1000)
     seed, offset = 0xC0FFEE, 17
-    out = b2.mcts_search(batch, sims, uct_c=2.0, n_rollouts=nroll, solve=solve, seed=seed, tree_index_offset=offset)
+    out = b2.mcts_search(batch, sims, uct_c=2.0, n_rollouts=nroll, solve=solve, seed=seed, tree_index_offset=offset,
+                         child_selection_policy=b2.ChildSelectionPolicy.PUCT if puct else b2.ChildSelectionPolicy.UCT)
     assert batch.error_count()[0] == 0
     visits, reward = out["visits"].cpu().numpy(), out["total_reward"].cpu().numpy()
     outcome, best, ran = out["outcome_p0"].cpu().numpy(), out["best_action"].cpu().numpy(), out["sims_run"].cpu().numpy()
     for i, st in enumerate(states):
-        o = oracle_mcts(st, 2.0, sims, nroll, solve, seed, tree_index=i + offset)
+        o = oracle_mcts(st, 2.0, sims, nroll, solve, seed, tree_index=i + offset, puct=puct)
         assert ran[i] == o["sims_run"], (gs, i)
         assert int(visits[i].sum()) == sum(v for _, v, _, _ in o["children"])
         for a, v, r, oc in o["children"]:
