@@ -157,6 +157,38 @@ int b2s_gather_states(void* dst_batch, void* src_batch, const int64_t* src_lanes
  * states.  returns_d [n][num_players] float32 and plies_d [n] int32 (plies played) may be NULL. */
 int b2s_rollout(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, float* returns_d, int32_t* plies_d, void* stream);
 
+/* ---- self-play trajectories ----------------------------------------------------------------- */
+
+/* Replaces algorithms::RecordBatchedTrajectory (open_spiel/algorithms/trajectories.h:34-100,
+ * trajectories.cc:98-200) with uniform-random policies (GetUniformPolicy) for n episodes at once, started from
+ * every lane's current state and played to the end (the batch is left at the terminal states).  Only decision
+ * nodes are recorded; chance nodes are sampled and applied in between (trajectories.cc:152-157).  The fields are
+ * the BatchedTrajectory fields, TIME-MAJOR: row t of every array is step t of all n episodes (the reference's
+ * [B][T] layout is the transposed view), padded like BatchedTrajectory::ResizeFields (trajectories.cc:62-96):
+ * legal mask all ones, everything else 0.  Device pointers; any may be NULL.
+ *   observations      [T][n][F] float32  State::InformationStateTensor() of the acting player when the game has one
+ *                                        (the reference's include_full_observations), else ObservationTensor()
+ *   legal_mask        [T][n][mask_words] uint32  State::LegalActionsMask as bits (bit a of word a/32)
+ *   actions           [T][n] int32,  player_ids [T][n] int8,  valid [T][n] uint8,  next_is_terminal [T][n] uint8
+ *   rewards           [n][num_players] float32  terminal Returns()
+ *   lengths           [n] int32  recorded steps per episode
+ * player_policies is not materialised: it is 1/popcount(legal_mask) on the legal actions (padding: 1).
+ * T = max_unroll_length must cover the longest episode (0: game max_game_length); an episode still running after
+ * T decisions is counted by b2s_error_count (the reference CHECK-fails, trajectories.cc:64-68).  Random stream:
+ * Philox4x32-10 keyed by (seed, lane + lane_offset, step), see csrc/batch_kernels.cuh. */
+typedef struct b2s_trajectory_out {
+  float*    observations;
+  uint32_t* legal_mask;
+  int32_t*  actions;
+  int8_t*   player_ids;
+  uint8_t*  valid;
+  uint8_t*  next_is_terminal;
+  float*    rewards;
+  int32_t*  lengths;
+} b2s_trajectory_out;
+int b2s_record_trajectories(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, int32_t max_unroll_length,
+                            const b2s_trajectory_out* out, void* stream);
+
 /* ---- MCTS ---------------------------------------------------------------------------------- */
 
 /* Replaces algorithms::MCTSBot (open_spiel/algorithms/mcts.h:149-230) with a RandomRolloutEvaluator

@@ -42,6 +42,12 @@ class MctsConfig(C.Structure):
                 ("tree_index_offset", C.c_int64), ("max_nodes_total", C.c_int64)]
 
 
+class TrajectoryOut(C.Structure):
+    _fields_ = [("observations", C.c_void_p), ("legal_mask", C.c_void_p), ("actions", C.c_void_p),
+                ("player_ids", C.c_void_p), ("valid", C.c_void_p), ("next_is_terminal", C.c_void_p),
+                ("rewards", C.c_void_p), ("lengths", C.c_void_p)]
+
+
 class CfrInfo(C.Structure):
     _fields_ = [("num_nodes", C.c_int32), ("num_levels", C.c_int32), ("num_infosets", C.c_int32),
                 ("num_entries", C.c_int32), ("key_floats", C.c_int32), ("iteration", C.c_int32),
@@ -74,6 +80,7 @@ SIGNATURES = {
     "b2s_broadcast_state": (C.c_int, [_VP, _I64, _I64, _VP, _I64, _VP]),
     "b2s_copy_states": (C.c_int, [_VP, _I64, _VP, _I64, _I64, _VP]),
     "b2s_rollout": (C.c_int, [_VP, _U64, _I64, _I64, _VP, _VP, _VP]),
+    "b2s_record_trajectories": (C.c_int, [_VP, _U64, _I64, _I64, C.c_int32, C.POINTER(TrajectoryOut), _VP]),
     "b2s_mcts_search": (C.c_int, [_VP, _I64, C.POINTER(MctsConfig), _VP, _VP, _VP, _VP, _VP, _VP]),
     "b2s_mcts_nodes_used": (C.c_int, [_VP, C.POINTER(_I64)]),
     "b2s_gather_states": (C.c_int, [_VP, _VP, _VP, _I64, _VP]),

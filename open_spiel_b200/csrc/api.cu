@@ -218,7 +218,7 @@ int b2s_observation(void* batch, int player, float* obs_d, int64_t n, void* stre
   Batch* B = (Batch*)batch;
   if (!obs_d) return fail("null obs");
   if (player >= B->info.num_players) return fail("player out of range");
-  const char* e = B->ops->obs(B->ctx(), player, 0, obs_d, n, (cudaStream_t)stream);
+  const char* e = B->ops->obs(B->ctx(), player, 0, 0, obs_d, n, (cudaStream_t)stream);
   if (e) return fail(e);
   return post();
 }
@@ -228,7 +228,7 @@ int b2s_information_state(void* batch, int player, float* out_d, int64_t n, void
   Batch* B = (Batch*)batch;
   if (!out_d) return fail("null out");
   if (player >= B->info.num_players) return fail("player out of range");
-  const char* e = B->ops->obs(B->ctx(), player, 1, out_d, n, (cudaStream_t)stream);
+  const char* e = B->ops->obs(B->ctx(), player, 1, 0, out_d, n, (cudaStream_t)stream);
   if (e) return fail(e);
   return post();
 }
@@ -339,6 +339,36 @@ int b2s_rollout(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, floa
   if (int r = check(batch, n)) return r;
   Batch* B = (Batch*)batch;
   B->ops->rollout(B->ctx(), seed, lane_offset, rets_d, plies_d, n, (cudaStream_t)stream);
+  return post();
+}
+
+int b2s_record_trajectories(void* batch, uint64_t seed, int64_t lane_offset, int64_t n, int32_t max_unroll_length,
+                            const b2s_trajectory_out* out, void* stream) {
+  if (int r = check(batch, n)) return r;
+  if (!out) return fail("trajectories: null output descriptor");
+  Batch* B = (Batch*)batch;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = max_unroll_length > 0 ? max_unroll_length : B->info.max_game_length;
+  const int which = B->info.information_state_tensor_size > 0 ? 1 : 0;
+  const size_t F = (size_t)(which ? B->info.information_state_tensor_size : B->info.observation_tensor_size);
+  const size_t W = (size_t)B->info.mask_words, N = (size_t)n;
+  B->ops->traj_begin(B->ctx(), seed, lane_offset, out->lengths, n, st);
+  for (int t = 0; t < T; ++t) {
+    if (out->observations) {
+      // tensor of the state the decision is taken in (acting player's view); zeros once the episode is over
+      const char* e = B->ops->obs(B->ctx(), -1, which, 1, out->observations + (size_t)t * N * F, n, st);
+      if (e) return fail(e);
+    }
+    TrajStepOut o;
+    o.mask = out->legal_mask ? out->legal_mask + (size_t)t * N * W : nullptr;
+    o.actions = out->actions ? out->actions + (size_t)t * N : nullptr;
+    o.players = out->player_ids ? out->player_ids + (size_t)t * N : nullptr;
+    o.valid = out->valid ? out->valid + (size_t)t * N : nullptr;
+    o.next_is_terminal = out->next_is_terminal ? out->next_is_terminal + (size_t)t * N : nullptr;
+    o.lengths = out->lengths;
+    B->ops->traj_step(B->ctx(), seed, lane_offset, t, o, n, st);
+  }
+  B->ops->traj_finish(B->ctx(), out->rewards, n, st);
   return post();
 }
 

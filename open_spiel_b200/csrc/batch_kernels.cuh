@@ -188,13 +188,15 @@ template <class R> constexpr bool obs_bitpacked(long) { return false; }
 // its own state's tensor into shared memory (game-specific compact form), then the warp streams the
 // 32*size floats of its tile out as fully coalesced 16-byte stores.
 template <class R>
-__global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, int player, int which, float* __restrict__ out, int size, u32 magic, long long n) {
+__global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, int player, int which, int zero_terminal, float* __restrict__ out, int size, u32 magic, long long n) {
   __shared__ typename R::ObsPack packs[kBlock];
+  __shared__ unsigned char dead_flags[kBlock];      // zero_terminal: lanes whose tensor is all-zero padding
   long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (i < n) {
     typename R::S s;
     R::load(s, ctx, i);
+    if (zero_terminal) dead_flags[threadIdx.x] = R::terminal(s, cfg) ? 1 : 0;
     int pl = player;
     if (pl < 0) { pl = R::cur_player(s, cfg); if (pl < 0) pl = 0; }
     R::obs_pack(s, cfg, pl, which, packs[threadIdx.x]);
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, in
   int total = lanes_here * size;                                       // floats in this tile
   float* base = out + tile0 * size;                                    // 16B aligned: 32*size*4 % 16 == 0
   const typename R::ObsPack* wp = packs + warp * 32;
+  const unsigned char* dead = dead_flags + warp * 32;
   int nvec = total >> 2;
   for (int q = lane; q < nvec; q += 32) {
     int e0 = q << 2;
@@ -218,11 +221,12 @@ __global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, in
       int wi = within >> 5, sh = within & 31;
       u32 lo = b[wi], hi = sh > 28 ? b[wi + 1] : 0u;    // (within+3)>>5 == wi+1 exactly when sh > 28: in range
       u32 nib = __funnelshift_r(lo, hi, sh);
+      if (zero_terminal && dead[st]) nib = 0;
       v[0] = (float)(nib & 1u); v[1] = (float)((nib >> 1) & 1u); v[2] = (float)((nib >> 2) & 1u); v[3] = (float)((nib >> 3) & 1u);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        v[j] = R::obs_elem(wp[st], cfg, within);
+        v[j] = (zero_terminal && dead[st]) ? 0.f : R::obs_elem(wp[st], cfg, within);
         if (++within == size) { within = 0; ++st; }     // a float4 may straddle two lanes' tensors
       }
     }
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, in
   }
   for (int e = (nvec << 2) + lane; e < total; e += 32) {               // ragged tail of the last tile
     int st = (int)(((u64)e * magic) >> 32);
-    base[e] = R::obs_elem(wp[st], cfg, e - st * size);
+    base[e] = (zero_terminal && dead[st]) ? 0.f : R::obs_elem(wp[st], cfg, e - st * size);
   }
 }
 
@@ -253,6 +257,105 @@ __global__ void __launch_bounds__(kBlock) k_rollout(Ctx ctx, typename R::Cfg cfg
     float r[R::kPlayers];
     R::returns(s, cfg, r);
     for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+  }
+}
+
+// ---- self-play trajectory recorder (algorithms/trajectories.cc RecordTrajectory :140-200) -------------------
+// The reference plays one episode at a time and pads afterwards; here every lane advances by one *decision* per
+// launch, so step t of all episodes is written as one coalesced [n]-row of the time-major outputs.  Chance nodes
+// are sampled and applied but not recorded (trajectories.cc:152-157).  Random numbers, lane g = lane_offset + i:
+//   decision of step t      k = philox_uniform(seed, g, 64 (t+1),         #legal)  -> k-th legal action (ascending)
+//   j-th chance node after   k = philox_uniform(seed, g, 64 (t+1) + 1 + j, #outcomes)   (before step 0: 64*0 + 1 + j)
+// (uniform policy = GetUniformPolicy; the chance distributions of kuhn / leduc are uniform over the listed outcomes).
+template <class R>
+__device__ __forceinline__ void traj_resolve_chance(typename R::S& s, const typename R::Cfg& cfg, const Ctx& ctx, long long i,
+                                                    u64 seed, u64 g, int mask_words, u32 b0) {
+  u32 j = 0;
+  while (R::cur_player(s, cfg) == kChancePlayerId) {
+    u32 m[R::kMaskWords];
+    R::legal_nonterminal(s, cfg, m);
+    int cnt = 0;
+    for (int w = 0; w < mask_words; ++w) cnt += __popc(m[w]);
+    int a = nth_set_bit(m, mask_words, (int)philox_uniform(seed, g, b0 + 1u + j, (u32)cnt));
+    apply_known_legal<R>(s, a, cfg, ctx, i);
+    ++j;
+  }
+}
+
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_traj_begin(Ctx ctx, typename R::Cfg cfg, u64 seed, long long lane_offset, int mask_words, int* __restrict__ lengths, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  if (lengths) lengths[i] = 0;
+  typename R::S s;
+  R::load(s, ctx, i);
+  if (R::cur_player(s, cfg) != kChancePlayerId) return;
+  traj_resolve_chance<R>(s, cfg, ctx, i, seed, (u64)(i + lane_offset), mask_words, 0u);
+  R::store(s, ctx, i);
+}
+
+struct TrajStepOut {          // row t of the time-major outputs; any pointer may be null
+  u32* mask;                  // [n][mask_words]
+  int* actions;               // [n]
+  signed char* players;       // [n]
+  unsigned char* valid;       // [n]
+  unsigned char* next_is_terminal;   // [n]
+  int* lengths;               // [n] (not a row: set to t+1 by the step that ends the episode)
+};
+
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_traj_step(Ctx ctx, typename R::Cfg cfg, u64 seed, long long lane_offset, int t, int mask_words, int num_actions, TrajStepOut o, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  typename R::S s;
+  R::load(s, ctx, i);
+  u32 m[R::kMaskWords];
+  int a = 0, pl = 0;
+  unsigned char valid = 0, nit = 0;
+  if (R::terminal(s, cfg)) {
+    // padding as BatchedTrajectory::ResizeFields (trajectories.cc:62-96): legal mask all ones, everything else 0
+    for (int w = 0; w < R::kMaskWords; ++w) {
+      int bits = num_actions - 32 * w;
+      m[w] = bits >= 32 ? 0xffffffffu : (bits > 0 ? (1u << bits) - 1u : 0u);
+    }
+  } else {
+    const u64 g = (u64)(i + lane_offset);
+    const u32 b0 = 64u * (u32)(t + 1);
+    R::legal_nonterminal(s, cfg, m);
+    int cnt = 0;
+    for (int w = 0; w < mask_words; ++w) cnt += __popc(m[w]);
+    a = nth_set_bit(m, mask_words, (int)philox_uniform(seed, g, b0, (u32)cnt));
+    pl = R::cur_player(s, cfg);
+    valid = 1;
+    apply_known_legal<R>(s, a, cfg, ctx, i);
+    traj_resolve_chance<R>(s, cfg, ctx, i, seed, g, mask_words, b0);
+    nit = R::terminal(s, cfg) ? 1 : 0;
+    R::store(s, ctx, i);
+    if (nit && o.lengths) o.lengths[i] = t + 1;
+  }
+  if (o.mask) {
+    if (R::kMaskWords == 1) o.mask[i] = m[0];
+    else for (int w = 0; w < mask_words; ++w) o.mask[i * mask_words + w] = m[w];
+  }
+  if (o.actions) o.actions[i] = a;
+  if (o.players) o.players[i] = (signed char)pl;
+  if (o.valid) o.valid[i] = valid;
+  if (o.next_is_terminal) o.next_is_terminal[i] = nit;
+}
+
+// Terminal Returns() of every episode (trajectories.cc:190); an episode still running after the last recorded
+// step is an error (the reference CHECKs max_unroll_length >= the longest episode, trajectories.cc:64-68).
+template <class R>
+__global__ void __launch_bounds__(kBlock) k_traj_finish(Ctx ctx, typename R::Cfg cfg, float* __restrict__ rewards, long long n) {
+  long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  typename R::S s;
+  R::load(s, ctx, i);
+  if (!R::terminal(s, cfg)) flag_error(ctx.err, i);
+  if (rewards) {
+    float r[R::kPlayers];
+    R::returns(s, cfg, r);
+    for (int p = 0; p < R::kPlayers; ++p) rewards[i * R::kPlayers + p] = r[p];
   }
 }
 
@@ -310,12 +413,15 @@ struct GameOps {
   virtual void legal_mask(const Ctx&, u32* m, long long n, cudaStream_t) = 0;
   virtual void legal_list(const Ctx&, short* out, int* counts, int stride, long long n, cudaStream_t) = 0;
   virtual void status(const Ctx&, signed char* cur, unsigned char* term, float* rets, long long n, cudaStream_t) = 0;
-  virtual const char* obs(const Ctx&, int player, int which, float* out, long long n, cudaStream_t) = 0;
+  virtual const char* obs(const Ctx&, int player, int which, int zero_terminal, float* out, long long n, cudaStream_t) = 0;
   virtual void step_fused(const Ctx&, const int* a, u32* m, unsigned char* term, float* rets, long long n, cudaStream_t) = 0;
   virtual void rollout(const Ctx&, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t) = 0;
   virtual void broadcast(const Ctx& dst, long long dst0, long long count, const Ctx& src, long long srclane, cudaStream_t) = 0;
   virtual void copy(const Ctx& dst, long long dst0, const Ctx& src, long long src0, long long count, cudaStream_t) = 0;
   virtual void gather(const Ctx& dst, const Ctx& src, const long long* src_lanes, long long count, cudaStream_t) = 0;
+  virtual void traj_begin(const Ctx&, u64 seed, long long lane_offset, int* lengths, long long n, cudaStream_t) = 0;
+  virtual void traj_step(const Ctx&, u64 seed, long long lane_offset, int t, const TrajStepOut& o, long long n, cudaStream_t) = 0;
+  virtual void traj_finish(const Ctx&, float* rewards, long long n, cudaStream_t) = 0;
   // MCTS over n roots (mcts.cuh); returns an error string when the game has no device MCTS
   virtual const char* mcts(const Ctx& roots, const Ctx& work, long long n, const struct MctsArgs& args, cudaStream_t) = 0;
   b2s_game_info info;
@@ -370,14 +476,14 @@ struct GameOpsT : GameOps {
     if (n <= 0) return;
     k_status<R, R::kIlp><<<grid_for(n, R::kIlp), kBlock, 0, st>>>(c, cfg, cur, term, rets, n); ++g_launches;
   }
-  const char* obs(const Ctx& c, int player, int which, float* out, long long n, cudaStream_t st) override {
+  const char* obs(const Ctx& c, int player, int which, int zero_terminal, float* out, long long n, cudaStream_t st) override {
     int size = which == 0 ? info.observation_tensor_size : info.information_state_tensor_size;
     if (size <= 0) return "game provides no such tensor";
     if (which == 1 && !R::kHasInfoState) return "game provides no information state tensor";
     if (n <= 0) return nullptr;
     u32 magic;
     if (!make_magic(size, 32 * size, &magic)) return "internal: no division magic";
-    k_obs<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, player, which, out, size, magic, n); ++g_launches;
+    k_obs<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, player, which, zero_terminal, out, size, magic, n); ++g_launches;
     return nullptr;
   }
   void step_fused(const Ctx& c, const int* a, u32* m, unsigned char* term, float* rets, long long n, cudaStream_t st) override {
@@ -391,6 +497,18 @@ struct GameOpsT : GameOps {
   void broadcast(const Ctx& dst, long long dst0, long long count, const Ctx& src, long long srclane, cudaStream_t st) override {
     if (count <= 0) return;
     k_broadcast<R><<<grid_for(count), kBlock, 0, st>>>(dst, dst0, count, src, srclane, cfg); ++g_launches;
+  }
+  void traj_begin(const Ctx& c, u64 seed, long long lane_offset, int* lengths, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    k_traj_begin<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, seed, lane_offset, info.mask_words, lengths, n); ++g_launches;
+  }
+  void traj_step(const Ctx& c, u64 seed, long long lane_offset, int t, const TrajStepOut& o, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    k_traj_step<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, seed, lane_offset, t, info.mask_words, info.num_distinct_actions, o, n); ++g_launches;
+  }
+  void traj_finish(const Ctx& c, float* rewards, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    k_traj_finish<R><<<grid_for(n), kBlock, 0, st>>>(c, cfg, rewards, n); ++g_launches;
   }
   const char* mcts(const Ctx& roots, const Ctx& work, long long n, const MctsArgs& args, cudaStream_t st) override;
   void gather(const Ctx& dst, const Ctx& src, const long long* src_lanes, long long count, cudaStream_t st) override {

@@ -254,6 +254,28 @@ class BatchedState:
         check(lib().b2s_rollout(self._h, int(seed), int(lane_offset), n, rets.data_ptr(), plies.data_ptr(), self._stream()))
         return rets, plies
 
+    def record_trajectories(self, seed, lane_offset=0, n=None, max_unroll_length=None, include_full_observations=True):
+        """Batched algorithms::RecordBatchedTrajectory (trajectories.cc:98-200) with uniform-random policies: plays
+        every lane from its current state to the end and returns a BatchedTrajectory of device tensors."""
+        from ._lib import TrajectoryOut
+        n = self._n(n)
+        T = int(max_unroll_length) if max_unroll_length else self.info.max_game_length
+        info, dev = self.info, self._dev
+        F = info.information_state_tensor_size if info.information_state_tensor_size > 0 else info.observation_tensor_size
+        tm = {      # time-major device buffers
+            "observations": torch.empty((T, n, F), dtype=torch.float32, device=dev) if include_full_observations else None,
+            "legal_mask": torch.empty((T, n, info.mask_words), dtype=torch.int32, device=dev),
+            "actions": torch.empty((T, n), dtype=torch.int32, device=dev),
+            "player_ids": torch.empty((T, n), dtype=torch.int8, device=dev),
+            "valid": torch.empty((T, n), dtype=torch.uint8, device=dev),
+            "next_is_terminal": torch.empty((T, n), dtype=torch.uint8, device=dev),
+            "rewards": torch.empty((n, info.num_players), dtype=torch.float32, device=dev),
+            "lengths": torch.empty((n,), dtype=torch.int32, device=dev),
+        }
+        out = TrajectoryOut(**{k: (v.data_ptr() if v is not None else None) for k, v in tm.items()})
+        check(lib().b2s_record_trajectories(self._h, int(seed), int(lane_offset), n, T, C.byref(out), self._stream()))
+        return BatchedTrajectory(n, T, info.num_distinct_actions, tm)
+
     def error_count(self):
         cnt, first = C.c_int64(), C.c_int64()
         check(lib().b2s_error_count(self._h, C.byref(cnt), C.byref(first), self._stream()))
@@ -394,6 +416,31 @@ def _reset_errors(self):
 
 
 BatchedState._reset_errors = _reset_errors
+
+
+class BatchedTrajectory:
+    """Mirror of algorithms::BatchedTrajectory (trajectories.h:34-75).  The fields are [B, T, ...] views of the
+    time-major device buffers the recorder fills (no copy): observations, legal_mask (bit-packed; legal_actions()
+    expands it to the reference's [B, T, A] 0/1 ints), actions, player_ids, valid, next_is_terminal; rewards is
+    [B, num_players] and lengths [B]."""
+
+    def __init__(self, batch_size, T, num_actions, tm):
+        self.batch_size, self.max_trajectory_length, self._A = batch_size, T, num_actions
+        self.time_major = tm
+        for k in ("observations", "legal_mask", "actions", "player_ids", "valid", "next_is_terminal"):
+            setattr(self, k, tm[k].transpose(0, 1) if tm[k] is not None else None)
+        self.rewards, self.lengths = tm["rewards"], tm["lengths"]
+
+    def legal_actions(self):
+        """[B, T, A] int32 0/1 as BatchedTrajectory::legal_actions (padding rows are all ones)."""
+        shifts = torch.arange(32, device=self.legal_mask.device, dtype=torch.int32)
+        bits = (self.legal_mask.unsqueeze(-1) >> shifts) & 1            # [B, T, W, 32]
+        return bits.reshape(*self.legal_mask.shape[:2], -1)[..., :self._A].to(torch.int32)
+
+    def player_policies(self):
+        """[B, T, A] float64: the uniform policy that generated the actions (padding rows are all ones)."""
+        la = self.legal_actions().to(torch.float64)
+        return la / la.sum(-1, keepdim=True).clamp_(min=1) * self.valid.unsqueeze(-1) + la * (1 - self.valid.unsqueeze(-1))
 
 
 class ChildSelectionPolicy:

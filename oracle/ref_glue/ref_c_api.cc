@@ -10,6 +10,8 @@
 #include "open_spiel/algorithms/cfr.h"
 #include "open_spiel/algorithms/mcts.h"
 #include "open_spiel/algorithms/tabular_exploitability.h"
+#include "open_spiel/algorithms/trajectories.h"
+#include "open_spiel/policy.h"
 #include "open_spiel/spiel.h"
 #include "open_spiel/spiel_utils.h"
 
@@ -155,6 +157,39 @@ int ref_mcts_search(void* g, void* state, double uct_c, int max_simulations, int
     if (best_action) *best_action = root->BestChild().action;
     if (root_visits) *root_visits = root->explore_count;
     return n;
+  } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// ---- RecordBatchedTrajectory (algorithms/trajectories.h:86-100) with GetUniformPolicy for every player -----------
+// Flattens the reference's BatchedTrajectory: observations [B][T][F], legal [B][T][A], policies [B][T][A], actions /
+// players / valid / next_is_terminal [B][T], rewards [B][P].  Returns max_trajectory_length (== T after ResizeFields).
+int ref_record_batched_trajectory(void* g, int batch_size, int seed, int T, float* observations, int* legal,
+                                  double* policies, int64_t* actions, int* players, int* valid, int* next_is_terminal,
+                                  double* rewards) {
+  try {
+    auto game = ((GameHolder*)g)->game;
+    std::vector<open_spiel::TabularPolicy> pol(game->NumPlayers(), open_spiel::GetUniformPolicy(*game));
+    open_spiel::algorithms::BatchedTrajectory bt = open_spiel::algorithms::RecordBatchedTrajectory(
+        *game, pol, /*state_to_index=*/{}, batch_size, /*include_full_observations=*/true, seed, T);
+    const int A = game->NumDistinctActions(), P = game->NumPlayers();
+    const int len = (int)bt.max_trajectory_length;
+    for (int b = 0; b < batch_size; ++b) {
+      for (int t = 0; t < len; ++t) {
+        const auto& o = bt.observations[b][t];
+        const size_t F = o.size();
+        for (size_t f = 0; f < F; ++f) observations[((size_t)b * len + t) * F + f] = o[f];
+        for (int a = 0; a < A; ++a) {
+          legal[((size_t)b * len + t) * A + a] = bt.legal_actions[b][t][a];
+          policies[((size_t)b * len + t) * A + a] = bt.player_policies[b][t][a];
+        }
+        actions[(size_t)b * len + t] = bt.actions[b][t];
+        players[(size_t)b * len + t] = bt.player_ids[b][t];
+        valid[(size_t)b * len + t] = bt.valid[b][t];
+        next_is_terminal[(size_t)b * len + t] = bt.next_is_terminal[b][t];
+      }
+      for (int p = 0; p < P; ++p) rewards[(size_t)b * P + p] = bt.rewards[b][p];
+    }
+    return len;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 

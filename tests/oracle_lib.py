@@ -204,6 +204,30 @@ def oracle_mcts(state, uct_c, max_simulations, n_rollouts=1, solve=True, seed=0,
             "root_visits": rv.value, "root_outcome_p0": ro.value, "nodes": nodes.value, "sims_run": ran.value}
 
 
+def oracle_record_trajectory(state, seed, lane, T, forced=None):
+    """oracle/algorithms/trajectories.cc: one episode from `state`; dict of [T]-padded numpy rows + rewards + length."""
+    import numpy as np
+    L = lib()
+    g = state.game
+    use_info = g.information_state_tensor_size > 0
+    A, F, P = g.num_distinct_actions, (g.information_state_tensor_size if use_info else g.observation_tensor_size), g.num_players
+    legal = np.zeros((T, A), dtype=np.int32)
+    obs = np.zeros((T, F), dtype=np.float32)
+    actions = np.zeros(T, dtype=np.int64)
+    players, valid, nit = (np.zeros(T, dtype=np.int32) for _ in range(3))
+    rewards = np.zeros(P, dtype=np.float64)
+    L.orc_record_trajectory.restype = C.c_int
+    L.orc_record_trajectory.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int] + [C.c_void_p] * 7 + \
+                                       [C.c_void_p, C.c_int]
+    fa = np.asarray(forced, dtype=np.int64) if forced is not None else None
+    n = L.orc_record_trajectory(g._g, state._s, seed, lane, T, int(use_info), legal.ctypes.data, obs.ctypes.data,
+                                actions.ctypes.data, players.ctypes.data, valid.ctypes.data, nit.ctypes.data,
+                                rewards.ctypes.data, fa.ctypes.data if fa is not None else None,
+                                len(fa) if fa is not None else 0)
+    return {"length": n, "legal_actions": legal, "observations": obs, "actions": actions, "player_ids": players,
+            "valid": valid, "next_is_terminal": nit, "rewards": rewards}
+
+
 class OracleCFR:
     """oracle/algorithms/cfr.cc: restatement of algorithms::CFRSolver / CFRPlusSolver."""
 

@@ -205,3 +205,25 @@ def ref_mcts(game, state, uct_c, max_simulations, n_rollouts=1, solve=True, seed
                           C.byref(best), C.byref(rv))
     assert n >= 0, L.ref_last_error()
     return {"children": [(acts[i], vis[i], rew[i]) for i in range(n)], "best_action": best.value, "root_visits": rv.value}
+
+
+def ref_record_batched_trajectory(game, batch_size, seed, T):
+    """The unmodified reference's RecordBatchedTrajectory (algorithms/trajectories.cc:98-118) with GetUniformPolicy for
+    every player and include_full_observations; dict of [B, T, ...] numpy arrays."""
+    import numpy as np
+    L = lib()
+    A, P, F = game.num_distinct_actions, game.num_players, game.information_state_tensor_size
+    obs = np.zeros((batch_size, T, F), dtype=np.float32)
+    legal = np.zeros((batch_size, T, A), dtype=np.int32)
+    pol = np.zeros((batch_size, T, A), dtype=np.float64)
+    actions = np.zeros((batch_size, T), dtype=np.int64)
+    players, valid, nit = (np.zeros((batch_size, T), dtype=np.int32) for _ in range(3))
+    rewards = np.zeros((batch_size, P), dtype=np.float64)
+    L.ref_record_batched_trajectory.restype = C.c_int
+    L.ref_record_batched_trajectory.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
+    n = L.ref_record_batched_trajectory(game._g, batch_size, seed, T, obs.ctypes.data, legal.ctypes.data, pol.ctypes.data,
+                                        actions.ctypes.data, players.ctypes.data, valid.ctypes.data, nit.ctypes.data,
+                                        rewards.ctypes.data)
+    assert n == T, L.ref_last_error()
+    return {"observations": obs, "legal_actions": legal, "player_policies": pol, "actions": actions, "player_ids": players,
+            "valid": valid, "next_is_terminal": nit, "rewards": rewards}
