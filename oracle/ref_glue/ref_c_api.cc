@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "open_spiel/algorithms/cfr.h"
+#include "open_spiel/algorithms/external_sampling_mccfr.h"
 #include "open_spiel/algorithms/mcts.h"
 #include "open_spiel/algorithms/tabular_exploitability.h"
 #include "open_spiel/algorithms/trajectories.h"
@@ -191,6 +192,42 @@ int ref_record_batched_trajectory(void* g, int batch_size, int seed, int T, floa
     }
     return len;
   } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// ---- ExternalSamplingMCCFRSolver (algorithms/external_sampling_mccfr.h:55-110), AverageType::kSimple ----------
+void* ref_mccfr_new(void* g, int seed) {
+  GUARD(return new open_spiel::algorithms::ExternalSamplingMCCFRSolver(*((GameHolder*)g)->game, seed), return nullptr);
+}
+void ref_mccfr_free(void* c) { delete (open_spiel::algorithms::ExternalSamplingMCCFRSolver*)c; }
+int ref_mccfr_iterate(void* c, int iters) {
+  GUARD(for (int i = 0; i < iters; ++i) ((open_spiel::algorithms::ExternalSamplingMCCFRSolver*)c)->RunIteration(); return 0,
+        return 1);
+}
+int ref_mccfr_keys(void* c, char* buf, int cap) {
+  auto& table = ((open_spiel::algorithms::ExternalSamplingMCCFRSolver*)c)->InfoStateValuesTable();
+  std::vector<std::string> keys;
+  for (auto& kv : table) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end());
+  std::string s;
+  for (auto& k : keys) { s += k; s += '\n'; }
+  return CopyStr(s, buf, cap);
+}
+int ref_mccfr_get(void* c, const char* key, int64_t* legal, double* regrets, double* cum_policy, int cap) {
+  auto& table = ((open_spiel::algorithms::ExternalSamplingMCCFRSolver*)c)->InfoStateValuesTable();
+  auto it = table.find(key);
+  if (it == table.end()) return -1;
+  const auto& v = it->second;
+  int n = (int)v.legal_actions.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    legal[i] = v.legal_actions[i];
+    regrets[i] = v.cumulative_regrets[i];
+    cum_policy[i] = v.cumulative_policy[i];
+  }
+  return n;
+}
+double ref_mccfr_nash_conv(void* g, void* c) {
+  auto* solver = (open_spiel::algorithms::ExternalSamplingMCCFRSolver*)c;
+  GUARD(return open_spiel::algorithms::NashConv(*((GameHolder*)g)->game, *solver->AveragePolicy()), return -1.0);
 }
 
 }  // extern "C"

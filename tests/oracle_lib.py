@@ -267,6 +267,45 @@ class OracleCFR:
         return out
 
 
+class OracleMCCFR:
+    """oracle/algorithms/mccfr.cc: restatement of algorithms::ExternalSamplingMCCFRSolver (kSimple averaging).
+    rng_mode 0 = the reference's std::mt19937 stream, 1 = the device solver's position-keyed Philox stream."""
+
+    def __init__(self, game, seed=0, rng_mode=1, traversals_per_update=1):
+        L = lib()
+        L.orc_mccfr_new.restype = C.c_void_p
+        L.orc_mccfr_new.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+        L.orc_mccfr_free.argtypes = [C.c_void_p]
+        L.orc_mccfr_iterate.argtypes = [C.c_void_p, C.c_int]
+        L.orc_mccfr_num_infosets.argtypes = [C.c_void_p]
+        L.orc_mccfr_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+        self.game = game
+        self._c = L.orc_mccfr_new(game._g, seed, rng_mode, traversals_per_update)
+
+    def __del__(self):
+        try:
+            lib().orc_mccfr_free(self._c)
+        except Exception:
+            pass
+
+    def iterate(self, iters=1):
+        assert lib().orc_mccfr_iterate(self._c, iters) == 0, "sampling failed (sum of probabilities < z)"
+
+    def table(self):
+        L = lib()
+        out = {}
+        for k in range(L.orc_mccfr_num_infosets(self._c)):
+            key = C.create_string_buffer(512)
+            legal = (C.c_int64 * 16)()
+            r, cu = (C.c_double * 16)(), (C.c_double * 16)()
+            pl = C.c_int()
+            n = L.orc_mccfr_get(self._c, k, key, 512, legal, r, cu, 16, C.byref(pl))
+            out[key.value.decode()] = {"legal": list(legal[:n]), "regrets": list(r[:n]), "cum_policy": list(cu[:n]),
+                                       "player": pl.value}
+        return out
+
+
 def infostate_tensors(game):
     """{info_state_string: information-state tensor bytes} for every decision node of the oracle's game tree."""
     out = {}

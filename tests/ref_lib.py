@@ -227,3 +227,47 @@ def ref_record_batched_trajectory(game, batch_size, seed, T):
     assert n == T, L.ref_last_error()
     return {"observations": obs, "legal_actions": legal, "player_policies": pol, "actions": actions, "player_ids": players,
             "valid": valid, "next_is_terminal": nit, "rewards": rewards}
+
+
+class RefMCCFR:
+    """The unmodified reference's algorithms::ExternalSamplingMCCFRSolver(game, seed) (AverageType::kSimple)."""
+
+    def __init__(self, game, seed=0):
+        L = lib()
+        L.ref_mccfr_new.restype = C.c_void_p
+        L.ref_mccfr_new.argtypes = [C.c_void_p, C.c_int]
+        L.ref_mccfr_free.argtypes = [C.c_void_p]
+        L.ref_mccfr_iterate.argtypes = [C.c_void_p, C.c_int]
+        L.ref_mccfr_keys.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.ref_mccfr_get.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.c_int]
+        L.ref_mccfr_nash_conv.restype = C.c_double
+        L.ref_mccfr_nash_conv.argtypes = [C.c_void_p, C.c_void_p]
+        self.game = game
+        self._c = L.ref_mccfr_new(game._g, seed)
+
+    def __del__(self):
+        try:
+            lib().ref_mccfr_free(self._c)
+        except Exception:
+            pass
+
+    def iterate(self, iters=1):
+        assert lib().ref_mccfr_iterate(self._c, iters) == 0, lib().ref_last_error()
+
+    def table(self):
+        L = lib()
+        buf = C.create_string_buffer(1 << 20)
+        L.ref_mccfr_keys(self._c, buf, 1 << 20)
+        out = {}
+        for key in buf.value.decode().split("\n"):
+            legal = (C.c_int64 * 16)()
+            r, cu = (C.c_double * 16)(), (C.c_double * 16)()
+            n = L.ref_mccfr_get(self._c, key.encode(), legal, r, cu, 16)
+            if n < 0:
+                continue
+            out[key] = {"legal": list(legal[:n]), "regrets": list(r[:n]), "cum_policy": list(cu[:n])}
+        return out
+
+    def nash_conv(self):
+        return lib().ref_mccfr_nash_conv(self.game._g, self._c)
