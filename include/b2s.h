@@ -229,7 +229,8 @@ int b2s_mcts_nodes_used(void* roots_batch, int64_t* nodes);
  * the batched kernels, regret / average-policy tables live on the device, and every
  * EvaluateAndUpdatePolicy (cfr.cc:263-282) runs inside one persistent kernel.  FP64, reference operation
  * order: tables match the reference bit for bit. */
-enum { B2S_CFR_LINEAR_AVERAGING = 1, B2S_CFR_REGRET_MATCHING_PLUS = 2 };   /* both = CFRPlusSolver */
+enum { B2S_CFR_LINEAR_AVERAGING = 1, B2S_CFR_REGRET_MATCHING_PLUS = 2,   /* both = CFRPlusSolver */
+       B2S_CFR_MCCFR_TABLES = 4 };   /* tables start at kInitialTableValues = 1e-6 (external_sampling_mccfr.h:59) */
 typedef struct b2s_cfr_info {
   int32_t num_nodes, num_levels, num_infosets, num_entries;   /* entries = sum of legal actions over infosets */
   int32_t key_floats;                                         /* information-state tensor size */
@@ -270,6 +271,18 @@ int  b2s_cfr_traverse_shard(void* solver, int player, int iteration, int shard, 
 int  b2s_cfr_apply_deltas(void* solver, void* stream);
 int  b2s_cfr_delta_buffer(void* solver, double** delta_d);
 int  b2s_cfr_set_iteration(void* solver, int iteration);
+
+/* Replaces algorithms::ExternalSamplingMCCFRSolver (open_spiel/algorithms/external_sampling_mccfr.h:55-110,
+ * AverageType::kSimple) on a solver created with B2S_CFR_MCCFR_TABLES: `iters` x RunIteration
+ * (external_sampling_mccfr.cc:71-80).  Every (iteration, traverser) phase runs `traversals_per_update` independent
+ * UpdateRegrets traversals (:124-186) in parallel, one thread each, all reading the tables as they stand at the start
+ * of the phase; their regret / average-policy deltas are then added in traversal order (deterministic, FP64).  With
+ * traversals_per_update = 1 this is exactly the reference's algorithm.  The uniform variates come from a
+ * position-keyed Philox stream (seed, path hash, phase, traversal) instead of the reference's sequential
+ * std::mt19937; oracle/algorithms/mccfr.cc implements both streams and ties the two together.
+ * Synchronises `stream`; fails if a sampling step found sum(probabilities) <= z (the reference's
+ * SpielFatalError in SampleActionIndex, cfr.cc:617-628). */
+int  b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_update, uint64_t seed, void* stream);
 
 /* ---- pinned host memory helpers (for the *_host entry points) ----------------------------- */
 int  b2s_host_alloc(void** out, size_t bytes);

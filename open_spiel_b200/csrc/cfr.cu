@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../../include/b2s.h"
+#include "common.cuh"
 #include "errors.h"
 
 namespace b2s {
@@ -60,6 +61,7 @@ struct CfrDev {
   double* cum_policy;          // [E]
   double* cur_policy;          // [E]
   double* delta;               // [2E]: regret deltas then average-policy deltas of one sharded traversal
+  const int4* mc_node;         // [n] MCCFR traversal record: {first_child, table offset of the information state, kind | actor << 8 | nchild << 16, 0}
 };
 
 __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration0, int linear_averaging, int rm_plus) {
@@ -322,7 +324,141 @@ __global__ void __launch_bounds__(1024) k_cfr_nashconv(CfrDev d, int use_average
   }
 }
 
+// ---- external-sampling MCCFR (external_sampling_mccfr.cc) ----------------------------------------------------
+// One thread = one UpdateRegrets traversal (:124-186) of traverser p over the flattened tree, as an explicit-stack
+// DFS: chance and opponent nodes are sampled and followed (no frame), the traverser's decision nodes keep a frame
+// (policy, child values) until all actions are explored.  Tables are read-only here; each traversal owns row k of
+// `rows` ([K][2E]: regret deltas, then average-policy deltas), which k_mccfr_apply adds in traversal order.
+// z(node) = U53(Philox4x32-10(seed; path hash, phase, k)) — the stream oracle/algorithms/mccfr.cc (rng_mode 1) restates.
+constexpr int kMcMaxActions = 8;
+constexpr int kMcMaxDepth = 32;
+
+__device__ __forceinline__ double mc_uniform(u64 seed, u64 h, u32 phase, u32 k) {
+  u32 r[4];
+  philox4(seed, h, phase, k, r);
+  u64 bits = (((u64)r[1] << 32) | r[0]) >> 11;
+  return __dmul_rn((double)bits, 1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ u64 mc_child_hash(u64 h, int idx) { return h * 0x9E3779B97F4A7C15ull + (u64)(idx + 1); }
+
+__global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u64 seed, int K, double* __restrict__ rows, int* __restrict__ err) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int E = d.n_entries;
+  double* reg_row = rows + (size_t)k * 2 * E;
+  double* avg_row = reg_row + E;
+  struct Frame { int node, a, n, off; double v; u64 h; double cv[kMcMaxActions], sig[kMcMaxActions]; };
+  Frame st[kMcMaxDepth];
+  int sp = 0, node = 0;
+  u64 h = 0;
+  for (;;) {
+    // ---- descend until a value is produced ----
+    double r;
+    for (;;) {
+      const int4 rec = __ldg(d.mc_node + node);          // one 16-byte load per node instead of five dependent ones
+      const int kind = rec.z & 0xff, actor = (rec.z >> 8) & 0xff, n = rec.z >> 16, fc = rec.x;
+      if (kind == 0) { r = d.ret[2 * node + p]; break; }
+      if (kind == 1) {                                   // SampleAction(ChanceOutcomes(), z), spiel.cc:372-409
+        double z = mc_uniform(seed, h, phase, (u32)k);
+        int chosen = -1;
+        if (n == 1) chosen = 0;
+        else {
+          double sum = 0.0;
+          for (int c = 0; c < n; ++c) {
+            double prob = d.chance_prob[fc + c];
+            if (sum <= z && z < __dadd_rn(sum, prob)) { chosen = c; break; }
+            sum = __dadd_rn(sum, prob);
+          }
+        }
+        if (chosen < 0) { atomicAdd(err, 1); chosen = n - 1; }
+        h = mc_child_hash(h, chosen);
+        node = fc + chosen;
+        continue;
+      }
+      const int off = rec.y;
+      double sig[kMcMaxActions];
+      {                                                  // ApplyRegretMatching on a copy, cfr.cc:596-615
+        double sum_pos = 0.0;
+        for (int a = 0; a < n; ++a) { double rg = d.regrets[off + a]; if (rg > 0) sum_pos = __dadd_rn(sum_pos, rg); }
+        for (int a = 0; a < n; ++a) {
+          double rg = d.regrets[off + a];
+          sig[a] = sum_pos > 0 ? (rg > 0 ? __ddiv_rn(rg, sum_pos) : 0.0) : __ddiv_rn(1.0, (double)n);
+        }
+      }
+      if (actor != p) {                                  // opponent: SampleActionIndex(0, z), cfr.cc:617-628
+        double z = mc_uniform(seed, h, phase, (u32)k);
+        int aidx = -1;
+        double sum = 0.0;
+        for (int a = 0; a < n; ++a) {
+          if (z >= sum && z < __dadd_rn(sum, sig[a])) { aidx = a; break; }
+          sum = __dadd_rn(sum, sig[a]);
+        }
+        if (aidx < 0) { atomicAdd(err, 1); aidx = n - 1; }
+        if (actor == ((p + 1) & 1))                      // simple averaging at the next player's nodes (:176-183)
+          for (int a = 0; a < n; ++a) avg_row[off + a] = __dadd_rn(avg_row[off + a], sig[a]);
+        h = mc_child_hash(h, aidx);
+        node = fc + aidx;
+        continue;
+      }
+      Frame& f = st[sp++];                               // traverser: walk every action (:156-163)
+      f.node = node; f.a = 0; f.n = n; f.off = off; f.v = 0.0; f.h = h;
+      for (int a = 0; a < n; ++a) f.sig[a] = sig[a];
+      h = mc_child_hash(f.h, 0);
+      node = fc;
+    }
+    // ---- hand the value to the waiting frames ----
+    bool done = false;
+    for (;;) {
+      if (sp == 0) { done = true; break; }
+      Frame& f = st[sp - 1];
+      f.cv[f.a] = r;
+      f.v = __dadd_rn(f.v, __dmul_rn(f.sig[f.a], r));
+      ++f.a;
+      if (f.a < f.n) { node = d.first_child[f.node] + f.a; h = mc_child_hash(f.h, f.a); break; }
+      for (int a = 0; a < f.n; ++a)                      // regret += child value - node value (:168-172)
+        reg_row[f.off + a] = __dadd_rn(reg_row[f.off + a], __dsub_rn(f.cv[a], f.v));
+      r = f.v;
+      --sp;
+    }
+    if (done) return;
+  }
+}
+
+// tables += the sum of the K traversal rows, in a FIXED order so the result is reproducible (and restated by the
+// oracle): 32 partial sums, partial[q] = delta[q] + delta[q+32] + delta[q+64] + ... (sequential, from 0.0), combined by
+// the tree partial[q] += partial[q+s], s = 16, 8, 4, 2, 1; table += partial[0].  With K = 1 this is table += delta[0].
+// A block owns 32 consecutive table entries (x) and the 32 partial lanes (y): every row is read with 256-byte
+// coalesced segments.  Touched entries of the rows are re-zeroed for the next phase.
+__global__ void __launch_bounds__(1024) k_mccfr_apply(CfrDev d, int K, double* __restrict__ rows) {
+  __shared__ double part[32][33];
+  const int E2 = 2 * d.n_entries;
+  const int ex = threadIdx.x, q = threadIdx.y;
+  const int e = blockIdx.x * 32 + ex;
+  double acc = 0.0;
+  if (e < E2) {
+    for (int k = q; k < K; k += 32) {
+      double* cell = rows + (size_t)k * E2 + e;
+      double v = *cell;
+      if (v != 0.0) { acc = __dadd_rn(acc, v); *cell = 0.0; }
+    }
+  }
+  part[q][ex] = acc;
+  __syncthreads();
+  for (int s = 16; s >= 1; s >>= 1) {
+    if (q < s) part[q][ex] = __dadd_rn(part[q][ex], part[q + s][ex]);
+    __syncthreads();
+  }
+  if (q == 0 && e < E2) {
+    double* dst = e < d.n_entries ? d.regrets + e : d.cum_policy + (e - d.n_entries);
+    *dst = __dadd_rn(*dst, part[0][ex]);
+  }
+}
+
 struct CfrSolver {
+  int mccfr_tables = 0;
+  double* mc_rows = nullptr; int mc_rows_k = 0;
+  int* mc_err = nullptr;
+  int max_actions = 0;
   int device = 0;
   int game_id = 0;
   int iteration = 0;
@@ -333,7 +469,7 @@ struct CfrSolver {
   // host copies of the structure (export)
   std::vector<int> is_player, is_off, legal_actions, node_counts;    // node_counts = {chance, decision, terminal}
   std::vector<float> keys;                                           // [I][tensor_size] information-state tensors
-  ~CfrSolver() { for (void* p : allocs) cudaFree(p); }
+  ~CfrSolver() { for (void* p : allocs) cudaFree(p); if (mc_rows) cudaFree(mc_rows); if (mc_err) cudaFree(mc_err); }
 };
 
 template <typename T>
@@ -375,6 +511,7 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
   S->device = device; S->game_id = game_id; S->tensor_size = gi.information_state_tensor_size;
   S->linear_averaging = (flags & B2S_CFR_LINEAR_AVERAGING) ? 1 : 0;
   S->rm_plus = (flags & B2S_CFR_REGRET_MATCHING_PLUS) ? 1 : 0;
+  S->mccfr_tables = (flags & B2S_CFR_MCCFR_TABLES) ? 1 : 0;
   void* level = nullptr;
   void* next = nullptr;
   const int T = gi.information_state_tensor_size, MW = gi.mask_words;
@@ -518,6 +655,11 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
       if (kind[par] == 2) policy_index[v] = S->is_off[infoset[par]] + aidx[v];
       chance_reach[v] = kind[par] == 1 ? chance_reach[par] * chance_prob[v] : chance_reach[par];   // parents precede children
     }
+    std::vector<int4> mc(N);
+    for (int v = 0; v < N; ++v)
+      mc[v] = make_int4(first_child[v], kind[v] == 2 ? S->is_off[infoset[v]] : -1,
+                        (int)kind[v] | ((int)(actor[v] & 0xff) << 8) | ((int)nchild[v] << 16), 0);
+    CK(upload(S, mc, &d.mc_node));
     CK(upload(S, policy_index, &d.policy_index)); CK(upload(S, par_actor, &d.par_actor));
     CK(upload(S, chance_reach, &d.chance_reach));
   }
@@ -539,6 +681,12 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
   for (int i = 0; i < I; ++i)
     for (int k = S->is_off[i]; k < S->is_off[i + 1]; ++k) uni[k] = 1.0 / (double)(S->is_off[i + 1] - S->is_off[i]);
   B2S_CU(cudaMemcpy(d.cur_policy, uni.data(), sizeof(double) * E, cudaMemcpyHostToDevice));
+  for (int i = 0; i < I; ++i) S->max_actions = std::max(S->max_actions, S->is_off[i + 1] - S->is_off[i]);
+  if (S->mccfr_tables) {     // CFRInfoStateValues(legal_actions, kInitialTableValues), external_sampling_mccfr.cc:143
+    std::vector<double> init(E, 0.000001);
+    B2S_CU(cudaMemcpy(d.regrets, init.data(), sizeof(double) * E, cudaMemcpyHostToDevice));
+    B2S_CU(cudaMemcpy(d.cum_policy, init.data(), sizeof(double) * E, cudaMemcpyHostToDevice));
+  }
   *out_solver = S;
   return 0;
 }
@@ -561,6 +709,44 @@ int b2s_cfr_iterate(void* solver, int iters, void* stream) {
   S->iteration += iters;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_cfr launch");
+  return 0;
+}
+
+int b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_update, uint64_t seed, void* stream) {
+  if (!solver) return fail("mccfr: null solver");
+  CfrSolver* S = (CfrSolver*)solver;
+  if (!S->mccfr_tables) return fail("mccfr: the solver was not created with B2S_CFR_MCCFR_TABLES");
+  if (iters < 0 || traversals_per_update < 1) return fail("mccfr: iters >= 0 and traversals_per_update >= 1 required");
+  if (S->max_actions > kMcMaxActions || S->d.n_levels > kMcMaxDepth) return fail("mccfr: game tree too wide / deep for the device traversal");
+  B2S_CU(cudaSetDevice(S->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = traversals_per_update, E = S->d.n_entries;
+  if (S->mc_rows_k < K) {
+    if (S->mc_rows) cudaFree(S->mc_rows);
+    S->mc_rows = nullptr; S->mc_rows_k = 0;
+    B2S_CU(cudaMalloc((void**)&S->mc_rows, sizeof(double) * 2 * (size_t)E * (size_t)K));
+    B2S_CU(cudaMemset(S->mc_rows, 0, sizeof(double) * 2 * (size_t)E * (size_t)K));
+    S->mc_rows_k = K;
+  }
+  if (!S->mc_err) {
+    B2S_CU(cudaMalloc((void**)&S->mc_err, sizeof(int)));
+    B2S_CU(cudaMemset(S->mc_err, 0, sizeof(int)));
+  }
+  for (int it = 0; it < iters; ++it) {
+    for (int p = 0; p < 2; ++p) {
+      unsigned phase = (unsigned)(S->iteration * 2 + p);
+      k_mccfr_es<<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, S->mc_rows, S->mc_err);
+      k_mccfr_apply<<<(2 * E + 31) / 32, dim3(32, 32), 0, st>>>(S->d, K, S->mc_rows);
+      g_launches += 2;
+    }
+    ++S->iteration;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_mccfr launch");
+  int bad = 0;
+  B2S_CU(cudaMemcpyAsync(&bad, S->mc_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2S_CU(cudaStreamSynchronize(st));
+  if (bad) return fail("mccfr: a sampling step found sum of probabilities <= z (SampleActionIndex, cfr.cc:617-628)");
   return 0;
 }
 

@@ -514,13 +514,13 @@ class CFRSolver:
     """Mirror of pyspiel.CFRSolver(game) (python/pybind11/policy.cc:224-245; algorithms/cfr.h:312-328) with
     device-resident tables.  CFRPlusSolver = CFRSolver(game, linear_averaging=True, regret_matching_plus=True)."""
 
-    def __init__(self, game, linear_averaging=False, regret_matching_plus=False):
+    def __init__(self, game, linear_averaging=False, regret_matching_plus=False, _mccfr_tables=False):
         from ._lib import CfrInfo
         if not torch.cuda.is_available():
             raise B2SError("no CUDA device: open_spiel_b200 has no CPU fallback")
         self.game = game
         self._h = C.c_void_p()
-        flags = (1 if linear_averaging else 0) | (2 if regret_matching_plus else 0)
+        flags = (1 if linear_averaging else 0) | (2 if regret_matching_plus else 0) | (4 if _mccfr_tables else 0)
         check(lib().b2s_cfr_create(game._gid, C.byref(game._cparams), flags, game.device, C.byref(self._h)))
         self._info = CfrInfo()
         check(lib().b2s_cfr_info_get(self._h, C.byref(self._info)))
@@ -593,3 +593,22 @@ class CFRSolver:
             probs = [1.0 / (hi - lo)] * (hi - lo) if s == 0.0 else [v / s for v in cp]
             pol[t["keys"][k].tobytes()] = list(zip(t["legal_actions"][lo:hi].tolist(), probs))
         return pol
+
+
+class ExternalSamplingMCCFRSolver(CFRSolver):
+    """Mirror of pyspiel.ExternalSamplingMCCFRSolver(game, seed, avg_type=kSimple)
+    (algorithms/external_sampling_mccfr.h:55-110) with device-resident tables.  `traversals_per_update` independent
+    traversals run in parallel per (iteration, traverser) phase against frozen tables; 1 = the reference's algorithm."""
+
+    def __init__(self, game, seed=0, traversals_per_update=1):
+        super().__init__(game, _mccfr_tables=True)
+        self.seed, self.traversals_per_update = int(seed), int(traversals_per_update)
+
+    def run_iteration(self, iterations=1):
+        """ExternalSamplingMCCFRSolver::RunIteration (external_sampling_mccfr.cc:71-80), `iterations` times."""
+        st = C.c_void_p(torch.cuda.current_stream(torch.device("cuda", self.game.device)).cuda_stream)
+        check(lib().b2s_mccfr_external_iterate(self._h, int(iterations), self.traversals_per_update, self.seed, st))
+
+    def evaluate_and_update_policy(self, iterations=1):
+        raise B2SError("ExternalSamplingMCCFRSolver: use run_iteration()")
+

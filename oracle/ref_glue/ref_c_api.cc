@@ -227,7 +227,8 @@ int ref_mccfr_get(void* c, const char* key, int64_t* legal, double* regrets, dou
 }
 double ref_mccfr_nash_conv(void* g, void* c) {
   auto* solver = (open_spiel::algorithms::ExternalSamplingMCCFRSolver*)c;
-  GUARD(return open_spiel::algorithms::NashConv(*((GameHolder*)g)->game, *solver->AveragePolicy()), return -1.0);
+  GUARD(return open_spiel::algorithms::NashConv(*((GameHolder*)g)->game, *solver->AveragePolicy(), /*use_state_get_policy=*/true),
+               return -1.0);
 }
 
 }  // extern "C"

@@ -1,0 +1,66 @@
+"""GPU parity: device external-sampling MCCFR (b2s_mccfr_external_iterate) vs oracle/algorithms/mccfr.cc on the same
+position-keyed Philox stream — cumulative regrets and cumulative policy of every information state BIT FOR BIT, for one
+traversal per update (the reference's algorithm) and for batched updates.  The oracle itself is pinned bit-for-bit to the
+unmodified reference's ExternalSamplingMCCFRSolver on the reference's own mt19937 stream (tests/test_mccfr_oracle.py).
+Plus the reference test's known answers (external_sampling_mccfr_test.cc:104-106): NashConv after 1000 iterations."""
+import numpy as np
+import pytest
+
+import open_spiel_b200 as b2
+from oracle_lib import OracleGame, OracleMCCFR, infostate_tensors
+
+pytestmark = pytest.mark.gpu
+
+INIT = 0.000001
+
+
+def compare(dev_table, cpu_table, tensors):
+    by_key = {dev_table["keys"][k].tobytes(): k for k in range(len(dev_table["players"]))}
+    seen = set()
+    for key, v in cpu_table.items():
+        k = by_key[tensors[key]]
+        seen.add(k)
+        lo, hi = dev_table["offsets"][k], dev_table["offsets"][k + 1]
+        assert dev_table["legal_actions"][lo:hi].tolist() == v["legal"]
+        assert dev_table["players"][k] == v["player"]
+        for f in ("regrets", "cum_policy"):
+            assert np.array_equal(dev_table[f][lo:hi], np.array(v[f])), (key, f, dev_table[f][lo:hi], v[f])
+    # information states the reference has not created yet are still at their initial values on the device
+    for k in range(len(dev_table["players"])):
+        if k not in seen:
+            lo, hi = dev_table["offsets"][k], dev_table["offsets"][k + 1]
+            assert (dev_table["regrets"][lo:hi] == INIT).all() and (dev_table["cum_policy"][lo:hi] == INIT).all()
+
+
+@pytest.mark.parametrize("gs,K,steps", [("kuhn_poker", 1, [1, 5, 60, 400]), ("leduc_poker", 1, [1, 10, 150]),
+                                        ("kuhn_poker", 64, [1, 3, 20]), ("leduc_poker", 256, [1, 2, 8]),
+                                        ("leduc_poker", 4096, [2])])
+def test_device_mccfr_equals_oracle_bitwise(gs, K, steps):
+    game, og = b2.load_game(gs), OracleGame(gs)
+    seed = 0x5EED + K
+    dev = b2.ExternalSamplingMCCFRSolver(game, seed=seed, traversals_per_update=K)
+    cpu = OracleMCCFR(og, seed=seed, rng_mode=1, traversals_per_update=K)
+    tensors = infostate_tensors(og)
+    for n in steps:
+        dev.run_iteration(n)
+        cpu.iterate(n)
+        compare(dev.table(), cpu.table(), tensors)
+
+
+def test_reference_known_answers_nash_conv():
+    # external_sampling_mccfr_test.cc:104-106: 1000 iterations -> NashConv <= 0.05 (kuhn), <= 2.5 (leduc) on the
+    # reference's mt19937 stream.  The bounds are properties of that sample path: the unmodified reference itself, over
+    # seeds 0..7, gives kuhn 0.023-0.070 at 1000 iterations (0.004-0.035 at 10000) and leduc 2.25-2.76 at 1000
+    # (1.54-1.87 at 2000).  On the Philox stream we therefore ask the reference's bounds at the larger iteration counts
+    # and bounds just above the reference's own spread at 1000.
+    for gs, iters, bound in [("kuhn_poker", 1000, 0.15), ("kuhn_poker", 10000, 0.05), ("leduc_poker", 1000, 3.2),
+                             ("leduc_poker", 2000, 2.5)]:
+        s = b2.ExternalSamplingMCCFRSolver(b2.load_game(gs), seed=230398247)
+        s.run_iteration(iters)
+        assert s.nash_conv() <= bound, (gs, iters, s.nash_conv())
+
+
+def test_batched_updates_converge_faster_per_launch():
+    s = b2.ExternalSamplingMCCFRSolver(b2.load_game("leduc_poker"), seed=3, traversals_per_update=4096)
+    s.run_iteration(50)
+    assert s.nash_conv() < 1.0
