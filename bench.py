@@ -388,6 +388,34 @@ def run_gpu(args):
         torch.cuda.synchronize()
         dt = maxtime(time.perf_counter() - t0)
         loops["cfr_leduc_nccl_sharded"] = {"iters_per_s": 200 / dt, "world": world, "seconds": dt}
+    del solver
+    # external-sampling MCCFR: leduc_poker, 16384 traversals per update (replicated per rank, seeds differ)
+    mc = b2.ExternalSamplingMCCFRSolver(leduc, seed=11 + rank, traversals_per_update=16384)
+    mc.run_iteration(2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mc.run_iteration(50)
+    torch.cuda.synchronize()
+    dt = maxtime(time.perf_counter() - t0)
+    loops["mccfr_external_leduc"] = {"traversals_per_s": world * 2 * 16384 * 50 / dt, "traversals_per_update": 16384,
+                                     "iterations": 50, "seconds": dt, "nash_conv_rank0": mc.nash_conv()}
+    del mc
+    # self-play trajectory recorder: connect_four, 2^18 episodes per GPU with observations (42 x 2^18 x 126 floats)
+    c4 = b2.Game("connect_four", device=local)
+    eps = 1 << 18
+    tb = c4.new_batch(eps)
+    tb.record_trajectories(seed=1, lane_offset=rank * eps)
+    tb.reset()
+    barrier()
+    t0 = time.perf_counter()
+    tr = tb.record_trajectories(seed=2, lane_offset=rank * eps)
+    torch.cuda.synchronize()
+    dt = maxtime(time.perf_counter() - t0)
+    nbytes = sum(v.numel() * v.element_size() for v in tr.time_major.values() if v is not None)
+    dec = parallel.allreduce_stats(tr.lengths.sum().to(torch.int64).reshape(1))
+    loops["trajectories_connect_four"] = {"episodes_per_s": world * eps / dt, "decisions_per_s": float(dec.item()) / dt,
+                                          "episodes_per_gpu": eps, "output_gbs_per_gpu": nbytes / dt / 1e9, "seconds": dt}
+    del tb, tr
     barrier()
 
     if rank != 0:

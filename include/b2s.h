@@ -276,7 +276,7 @@ int  b2s_cfr_set_iteration(void* solver, int iteration);
  * AverageType::kSimple) on a solver created with B2S_CFR_MCCFR_TABLES: `iters` x RunIteration
  * (external_sampling_mccfr.cc:71-80).  Every (iteration, traverser) phase runs `traversals_per_update` independent
  * UpdateRegrets traversals (:124-186) in parallel, one thread each, all reading the tables as they stand at the start
- * of the phase; their regret / average-policy deltas are then added in traversal order (deterministic, FP64).  With
+ * of the phase; their regret / average-policy deltas are then added in a fixed, documented order (deterministic, FP64).  With
  * traversals_per_update = 1 this is exactly the reference's algorithm.  The uniform variates come from a
  * position-keyed Philox stream (seed, path hash, phase, traversal) instead of the reference's sequential
  * std::mt19937; oracle/algorithms/mccfr.cc implements both streams and ties the two together.

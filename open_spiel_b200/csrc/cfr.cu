@@ -61,6 +61,7 @@ struct CfrDev {
   double* cum_policy;          // [E]
   double* cur_policy;          // [E]
   double* delta;               // [2E]: regret deltas then average-policy deltas of one sharded traversal
+  const signed char* entry_player;   // [E] the player an entry's information state belongs to
   const int4* mc_node;         // [n] MCCFR traversal record: {first_child, table offset of the information state, kind | actor << 8 | nchild << 16, 0}
 };
 
@@ -328,7 +329,8 @@ __global__ void __launch_bounds__(1024) k_cfr_nashconv(CfrDev d, int use_average
 // One thread = one UpdateRegrets traversal (:124-186) of traverser p over the flattened tree, as an explicit-stack
 // DFS: chance and opponent nodes are sampled and followed (no frame), the traverser's decision nodes keep a frame
 // (policy, child values) until all actions are explored.  Tables are read-only here; each traversal owns row k of
-// `rows` ([K][2E]: regret deltas, then average-policy deltas), which k_mccfr_apply adds in traversal order.
+// `rows` ([K][E]: in phase p an entry of player p receives a regret delta, an entry of the other player an
+// average-policy delta, so one row serves both), which k_mccfr_apply adds in a fixed order.
 // z(node) = U53(Philox4x32-10(seed; path hash, phase, k)) — the stream oracle/algorithms/mccfr.cc (rng_mode 1) restates.
 constexpr int kMcMaxActions = 8;
 constexpr int kMcMaxDepth = 32;
@@ -345,8 +347,8 @@ __global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u6
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   const int E = d.n_entries;
-  double* reg_row = rows + (size_t)k * 2 * E;
-  double* avg_row = reg_row + E;
+  double* reg_row = rows + (size_t)k * E;
+  double* avg_row = reg_row;
   struct Frame { int node, a, n, off; double v; u64 h; double cv[kMcMaxActions], sig[kMcMaxActions]; };
   Frame st[kMcMaxDepth];
   int sp = 0, node = 0;
@@ -425,31 +427,43 @@ __global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u6
 }
 
 // tables += the sum of the K traversal rows, in a FIXED order so the result is reproducible (and restated by the
-// oracle): 32 partial sums, partial[q] = delta[q] + delta[q+32] + delta[q+64] + ... (sequential, from 0.0), combined by
-// the tree partial[q] += partial[q+s], s = 16, 8, 4, 2, 1; table += partial[0].  With K = 1 this is table += delta[0].
-// A block owns 32 consecutive table entries (x) and the 32 partial lanes (y): every row is read with 256-byte
-// coalesced segments.  Touched entries of the rows are re-zeroed for the next phase.
-__global__ void __launch_bounds__(1024) k_mccfr_apply(CfrDev d, int K, double* __restrict__ rows) {
-  __shared__ double part[32][33];
-  const int E2 = 2 * d.n_entries;
+// oracle): 64 partial sums, partial[q] = delta[q] + delta[q+64] + delta[q+128] + ... (sequential, from 0.0), combined
+// by the tree partial[q] += partial[q+s], s = 32, 16, 8, 4, 2, 1; table += partial[0].  With K = 1 this is
+// table += delta[0].  A block owns 16 consecutive table entries (x) and the 64 partial lanes (y): every row is read
+// in 128-byte coalesced segments, 8 independent loads in flight per thread.  Touched cells are re-zeroed for the
+// next phase.
+constexpr int kMcLanes = 64, kMcTile = 16;
+__global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_apply(CfrDev d, int p, int K, double* __restrict__ rows) {
+  __shared__ double part[kMcLanes][kMcTile + 1];
+  const int E = d.n_entries;
   const int ex = threadIdx.x, q = threadIdx.y;
-  const int e = blockIdx.x * 32 + ex;
+  const int e = blockIdx.x * kMcTile + ex;
   double acc = 0.0;
-  if (e < E2) {
-    for (int k = q; k < K; k += 32) {
-      double* cell = rows + (size_t)k * E2 + e;
+  if (e < E) {
+    constexpr int U = 8;
+    int k = q;
+    for (; k + kMcLanes * (U - 1) < K; k += kMcLanes * U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = rows[(size_t)(k + kMcLanes * u) * E + e];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (v[u] != 0.0) { acc = __dadd_rn(acc, v[u]); rows[(size_t)(k + kMcLanes * u) * E + e] = 0.0; }
+    }
+    for (; k < K; k += kMcLanes) {
+      double* cell = rows + (size_t)k * E + e;
       double v = *cell;
       if (v != 0.0) { acc = __dadd_rn(acc, v); *cell = 0.0; }
     }
   }
   part[q][ex] = acc;
   __syncthreads();
-  for (int s = 16; s >= 1; s >>= 1) {
+  for (int s = kMcLanes / 2; s >= 1; s >>= 1) {
     if (q < s) part[q][ex] = __dadd_rn(part[q][ex], part[q + s][ex]);
     __syncthreads();
   }
-  if (q == 0 && e < E2) {
-    double* dst = e < d.n_entries ? d.regrets + e : d.cum_policy + (e - d.n_entries);
+  if (q == 0 && e < E) {
+    double* dst = d.entry_player[e] == p ? d.regrets + e : d.cum_policy + e;
     *dst = __dadd_rn(*dst, part[0][ex]);
   }
 }
@@ -660,6 +674,10 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
       mc[v] = make_int4(first_child[v], kind[v] == 2 ? S->is_off[infoset[v]] : -1,
                         (int)kind[v] | ((int)(actor[v] & 0xff) << 8) | ((int)nchild[v] << 16), 0);
     CK(upload(S, mc, &d.mc_node));
+    std::vector<signed char> entry_player(S->legal_actions.size(), 0);
+    for (int i = 0; i < I; ++i)
+      for (int k = S->is_off[i]; k < S->is_off[i + 1]; ++k) entry_player[k] = (signed char)S->is_player[i];
+    CK(upload(S, entry_player, &d.entry_player));
     CK(upload(S, policy_index, &d.policy_index)); CK(upload(S, par_actor, &d.par_actor));
     CK(upload(S, chance_reach, &d.chance_reach));
   }
@@ -724,8 +742,8 @@ int b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_updat
   if (S->mc_rows_k < K) {
     if (S->mc_rows) cudaFree(S->mc_rows);
     S->mc_rows = nullptr; S->mc_rows_k = 0;
-    B2S_CU(cudaMalloc((void**)&S->mc_rows, sizeof(double) * 2 * (size_t)E * (size_t)K));
-    B2S_CU(cudaMemset(S->mc_rows, 0, sizeof(double) * 2 * (size_t)E * (size_t)K));
+    B2S_CU(cudaMalloc((void**)&S->mc_rows, sizeof(double) * (size_t)E * (size_t)K));
+    B2S_CU(cudaMemset(S->mc_rows, 0, sizeof(double) * (size_t)E * (size_t)K));
     S->mc_rows_k = K;
   }
   if (!S->mc_err) {
@@ -736,7 +754,7 @@ int b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_updat
     for (int p = 0; p < 2; ++p) {
       unsigned phase = (unsigned)(S->iteration * 2 + p);
       k_mccfr_es<<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, S->mc_rows, S->mc_err);
-      k_mccfr_apply<<<(2 * E + 31) / 32, dim3(32, 32), 0, st>>>(S->d, K, S->mc_rows);
+      k_mccfr_apply<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, p, K, S->mc_rows);
       g_launches += 2;
     }
     ++S->iteration;

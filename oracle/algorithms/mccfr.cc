@@ -15,8 +15,8 @@
 //               traverser, U53 = top 53 bits of (r1:r0) * 2^-53.  Keyed by position, not by consumption order.
 // traversals_per_update = K: the K traversals of one (iteration, traverser) phase all read the tables as they were at
 // the start of the phase; afterwards every table entry receives the sum of its K deltas, formed in the fixed order the
-// device kernel k_mccfr_apply uses: 32 partial sums partial[q] = delta[q] + delta[q+32] + ... (sequential, from 0.0),
-// the tree partial[q] += partial[q+s] for s = 16, 8, 4, 2, 1, then table += partial[0].
+// device kernel k_mccfr_apply uses: 64 partial sums partial[q] = delta[q] + delta[q+64] + ... (sequential, from 0.0),
+// the tree partial[q] += partial[q+s] for s = 32, 16, 8, 4, 2, 1, then table += partial[0].
 // K = 1 is exactly the reference's algorithm (a traversal never revisits an information state it has updated).
 #include <cstdint>
 #include <cstring>
@@ -145,17 +145,17 @@ struct EsMccfr {
         auto root = game->NewInitialState();
         Update(*root, p, 0, phase, (uint32_t)k, &deltas[k]);
       }
-      // (key, average?) -> 32 partial sums per action
+      // (key, average?) -> 64 partial sums per action
       std::map<std::pair<std::string, bool>, std::vector<std::vector<double>>> partial;
       for (int k = 0; k < K; ++k)
         for (const Delta& d : deltas[k]) {
           auto& ps = partial[{d.key, d.average}];
-          if (ps.empty()) ps.assign(32, std::vector<double>(d.d.size(), 0.0));
-          for (size_t a = 0; a < d.d.size(); ++a) if (d.d[a] != 0.0) ps[k % 32][a] += d.d[a];
+          if (ps.empty()) ps.assign(64, std::vector<double>(d.d.size(), 0.0));
+          for (size_t a = 0; a < d.d.size(); ++a) if (d.d[a] != 0.0) ps[k % 64][a] += d.d[a];
         }
       for (auto& kv : partial) {
         auto& ps = kv.second;
-        for (int s = 16; s >= 1; s >>= 1)
+        for (int s = 32; s >= 1; s >>= 1)
           for (int q = 0; q < s; ++q)
             for (size_t a = 0; a < ps[q].size(); ++a) ps[q][a] += ps[q + s][a];
         McValues& v = table[kv.first.first];
