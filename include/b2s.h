@@ -283,6 +283,14 @@ int  b2s_cfr_set_iteration(void* solver, int iteration);
  * Synchronises `stream`; fails if a sampling step found sum(probabilities) <= z (the reference's
  * SpielFatalError in SampleActionIndex, cfr.cc:617-628). */
 int  b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_update, uint64_t seed, void* stream);
+/* The same phase split over GPUs, bit-identical to the single-GPU call: the 64 lanes of the fixed-order reduction are
+ * the unit of sharding.  Every rank runs the traversals k with k mod 64 in [lane_begin, lane_end) of phase
+ * (current iteration, player) and writes those lanes of partials_d [64][num_entries]; after the lanes of all ranks have
+ * been gathered (NCCL all-gather) every rank calls b2s_mccfr_apply_partials, which runs the reduction tree, updates the
+ * (replicated) tables and, after player 1, advances the iteration counter. */
+int  b2s_mccfr_traverse_lanes(void* solver, int player, int traversals_per_update, uint64_t seed, int lane_begin, int lane_end,
+                              double* partials_d, void* stream);
+int  b2s_mccfr_apply_partials(void* solver, int player, const double* partials_d, void* stream);
 
 /* ---- pinned host memory helpers (for the *_host entry points) ----------------------------- */
 int  b2s_host_alloc(void** out, size_t bytes);

@@ -96,6 +96,8 @@ SIGNATURES = {
     "b2s_cfr_apply_deltas": (C.c_int, [_VP, _VP]),
     "b2s_cfr_delta_buffer": (C.c_int, [_VP, C.POINTER(_VP)]),
     "b2s_mccfr_external_iterate": (C.c_int, [_VP, C.c_int, C.c_int, _U64, _VP]),
+    "b2s_mccfr_traverse_lanes": (C.c_int, [_VP, C.c_int, C.c_int, _U64, C.c_int, C.c_int, _VP, _VP]),
+    "b2s_mccfr_apply_partials": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "b2s_cfr_set_iteration": (C.c_int, [_VP, C.c_int]),
     "b2s_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_size_t]),
     "b2s_host_free": (None, [_VP]),

@@ -343,11 +343,16 @@ __device__ __forceinline__ double mc_uniform(u64 seed, u64 h, u32 phase, u32 k) 
 }
 __device__ __forceinline__ u64 mc_child_hash(u64 h, int idx) { return h * 0x9E3779B97F4A7C15ull + (u64)(idx + 1); }
 
-__global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u64 seed, int K, double* __restrict__ rows, int* __restrict__ err) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
+// Sharding: the rank that owns reduction lanes [lane_begin, lane_begin + L) runs the traversals k with k mod 64 in
+// that range; thread t is traversal k = lane_begin + t mod L + 64 (t div L) and owns row t.  One GPU: L = 64, k = t.
+__global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u64 seed, int K, int lane_begin, int L, int n_threads,
+                                                   double* __restrict__ rows, int* __restrict__ err) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_threads) return;
+  int k = lane_begin + t % L + 64 * (t / L);
   if (k >= K) return;
   const int E = d.n_entries;
-  double* reg_row = rows + (size_t)k * E;
+  double* reg_row = rows + (size_t)t * E;
   double* avg_row = reg_row;
   struct Frame { int node, a, n, off; double v; u64 h; double cv[kMcMaxActions], sig[kMcMaxActions]; };
   Frame st[kMcMaxDepth];
@@ -457,6 +462,38 @@ __global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_apply(CfrDev d, in
     }
   }
   part[q][ex] = acc;
+  __syncthreads();
+  for (int s = kMcLanes / 2; s >= 1; s >>= 1) {
+    if (q < s) part[q][ex] = __dadd_rn(part[q][ex], part[q + s][ex]);
+    __syncthreads();
+  }
+  if (q == 0 && e < E) {
+    double* dst = d.entry_player[e] == p ? d.regrets + e : d.cum_policy + e;
+    *dst = __dadd_rn(*dst, part[0][ex]);
+  }
+}
+
+// Sharded form of k_mccfr_apply, step 1: the partial sums of lanes [lane_begin, lane_begin + L) from this rank's rows
+// (row t holds traversal k = lane_begin + t mod L + 64 (t div L)) into partials[64][E].
+__global__ void __launch_bounds__(1024) k_mccfr_partial(CfrDev d, int K, int lane_begin, int L, double* __restrict__ rows, double* __restrict__ partials) {
+  const int E = d.n_entries;
+  const int e = blockIdx.x * kMcTile + threadIdx.x, ql = threadIdx.y;
+  if (e >= E || ql >= L) return;
+  double acc = 0.0;
+  for (int j = 0; lane_begin + ql + 64 * j < K; ++j) {
+    double* cell = rows + (size_t)(ql + L * j) * E + e;
+    double v = *cell;
+    if (v != 0.0) { acc = __dadd_rn(acc, v); *cell = 0.0; }
+  }
+  partials[(size_t)(lane_begin + ql) * E + e] = acc;
+}
+// step 2 (after the lanes of all ranks have been gathered): the tree over the 64 lanes, then table += partial[0].
+__global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_combine(CfrDev d, int p, const double* __restrict__ partials) {
+  __shared__ double part[kMcLanes][kMcTile + 1];
+  const int E = d.n_entries;
+  const int ex = threadIdx.x, q = threadIdx.y;
+  const int e = blockIdx.x * kMcTile + ex;
+  part[q][ex] = e < E ? partials[(size_t)q * E + e] : 0.0;
   __syncthreads();
   for (int s = kMcLanes / 2; s >= 1; s >>= 1) {
     if (q < s) part[q][ex] = __dadd_rn(part[q][ex], part[q + s][ex]);
@@ -730,30 +767,72 @@ int b2s_cfr_iterate(void* solver, int iters, void* stream) {
   return 0;
 }
 
-int b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_update, uint64_t seed, void* stream) {
-  if (!solver) return fail("mccfr: null solver");
-  CfrSolver* S = (CfrSolver*)solver;
+static int mccfr_prepare(CfrSolver* S, int rows_needed) {
   if (!S->mccfr_tables) return fail("mccfr: the solver was not created with B2S_CFR_MCCFR_TABLES");
-  if (iters < 0 || traversals_per_update < 1) return fail("mccfr: iters >= 0 and traversals_per_update >= 1 required");
   if (S->max_actions > kMcMaxActions || S->d.n_levels > kMcMaxDepth) return fail("mccfr: game tree too wide / deep for the device traversal");
   B2S_CU(cudaSetDevice(S->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  const int K = traversals_per_update, E = S->d.n_entries;
-  if (S->mc_rows_k < K) {
+  const int E = S->d.n_entries;
+  if (S->mc_rows_k < rows_needed) {
     if (S->mc_rows) cudaFree(S->mc_rows);
     S->mc_rows = nullptr; S->mc_rows_k = 0;
-    B2S_CU(cudaMalloc((void**)&S->mc_rows, sizeof(double) * (size_t)E * (size_t)K));
-    B2S_CU(cudaMemset(S->mc_rows, 0, sizeof(double) * (size_t)E * (size_t)K));
-    S->mc_rows_k = K;
+    B2S_CU(cudaMalloc((void**)&S->mc_rows, sizeof(double) * (size_t)E * (size_t)rows_needed));
+    B2S_CU(cudaMemset(S->mc_rows, 0, sizeof(double) * (size_t)E * (size_t)rows_needed));
+    S->mc_rows_k = rows_needed;
   }
   if (!S->mc_err) {
     B2S_CU(cudaMalloc((void**)&S->mc_err, sizeof(int)));
     B2S_CU(cudaMemset(S->mc_err, 0, sizeof(int)));
   }
+  return 0;
+}
+
+int b2s_mccfr_traverse_lanes(void* solver, int player, int traversals_per_update, uint64_t seed, int lane_begin, int lane_end,
+                             double* partials_d, void* stream) {
+  if (!solver || !partials_d) return fail("mccfr: null argument");
+  CfrSolver* S = (CfrSolver*)solver;
+  if (player < 0 || player > 1 || traversals_per_update < 1) return fail("mccfr: bad player / traversals_per_update");
+  if (lane_begin < 0 || lane_end > kMcLanes || lane_begin >= lane_end) return fail("mccfr: lane range must lie within [0, 64)");
+  const int K = traversals_per_update, L = lane_end - lane_begin, E = S->d.n_entries;
+  const int n_threads = L * ((K + 63) / 64);
+  if (int r = mccfr_prepare(S, n_threads)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned phase = (unsigned)(S->iteration * 2 + player);
+  k_mccfr_es<<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, S->mc_rows, S->mc_err);
+  k_mccfr_partial<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, K, lane_begin, L, S->mc_rows, partials_d);
+  g_launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "k_mccfr launch");
+  return 0;
+}
+
+int b2s_mccfr_apply_partials(void* solver, int player, const double* partials_d, void* stream) {
+  if (!solver || !partials_d) return fail("mccfr: null argument");
+  CfrSolver* S = (CfrSolver*)solver;
+  if (player < 0 || player > 1) return fail("mccfr: bad player");
+  if (int r = mccfr_prepare(S, 1)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int E = S->d.n_entries;
+  k_mccfr_combine<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, player, partials_d);
+  ++g_launches;
+  if (player == 1) ++S->iteration;
+  int bad = 0;
+  B2S_CU(cudaMemcpyAsync(&bad, S->mc_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2S_CU(cudaStreamSynchronize(st));
+  if (bad) return fail("mccfr: a sampling step found sum of probabilities <= z (SampleActionIndex, cfr.cc:617-628)");
+  return 0;
+}
+
+int b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_update, uint64_t seed, void* stream) {
+  if (!solver) return fail("mccfr: null solver");
+  CfrSolver* S = (CfrSolver*)solver;
+  if (iters < 0 || traversals_per_update < 1) return fail("mccfr: iters >= 0 and traversals_per_update >= 1 required");
+  if (int r = mccfr_prepare(S, traversals_per_update)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = traversals_per_update, E = S->d.n_entries;
   for (int it = 0; it < iters; ++it) {
     for (int p = 0; p < 2; ++p) {
       unsigned phase = (unsigned)(S->iteration * 2 + p);
-      k_mccfr_es<<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, S->mc_rows, S->mc_err);
+      k_mccfr_es<<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, 0, kMcLanes, K, S->mc_rows, S->mc_err);
       k_mccfr_apply<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, p, K, S->mc_rows);
       g_launches += 2;
     }

@@ -80,3 +80,41 @@ class DistributedCFRSolver:
 
     def table(self):
         return self.solver.table()
+
+
+class DistributedExternalSamplingMCCFRSolver:
+    """ExternalSamplingMCCFRSolver whose traversals are split over the ranks, BIT-IDENTICAL to the single-GPU solver:
+    the 64 lanes of the fixed-order delta reduction are dealt out to the ranks (world size must divide 64), every rank
+    runs the traversals of its lanes and reduces them to per-lane partial sums, the lanes are all-gathered (NCCL), and
+    every rank finishes the same reduction tree on the same numbers — tables stay replicated and identical."""
+
+    LANES = 64
+
+    def __init__(self, game, seed=0, traversals_per_update=1):
+        from .spiel import ExternalSamplingMCCFRSolver
+        self.solver = ExternalSamplingMCCFRSolver(game, seed, traversals_per_update)
+        self.rank, self.world = world()
+        if self.LANES % self.world:
+            raise ValueError("world size must divide %d" % self.LANES)
+        self.lanes_per_rank = self.LANES // self.world
+        dev = torch.device("cuda", game.device)
+        self.partials = torch.zeros((self.LANES, self.solver._info.num_entries), dtype=torch.float64, device=dev)
+
+    def run_iteration(self, iterations=1):
+        import torch.distributed as dist
+        L, h, s = lib(), self.solver._h, self.solver
+        st = C.c_void_p(torch.cuda.current_stream(self.partials.device).cuda_stream)
+        lo = self.rank * self.lanes_per_rank
+        for _ in range(int(iterations)):
+            for player in (0, 1):
+                check(L.b2s_mccfr_traverse_lanes(h, player, s.traversals_per_update, s.seed, lo, lo + self.lanes_per_rank,
+                                                 self.partials.data_ptr(), st))
+                if self.world > 1:
+                    dist.all_gather_into_tensor(self.partials, self.partials[lo:lo + self.lanes_per_rank].clone())
+                check(L.b2s_mccfr_apply_partials(h, player, self.partials.data_ptr(), st))
+
+    def table(self):
+        return self.solver.table()
+
+    def nash_conv(self):
+        return self.solver.nash_conv()

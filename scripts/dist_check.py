@@ -28,6 +28,20 @@ td, ts = d.table(), single.table()
 err = max(float(np.abs(td[f] - ts[f]).max()) for f in ("regrets", "cum_policy", "cur_policy"))
 assert err <= 1e-6, err
 
+# 1b. external-sampling MCCFR: reduction lanes dealt out to the ranks, NCCL all-gather -> bit-identical tables
+import time  # noqa: E402
+K = 16384
+dm = parallel.DistributedExternalSamplingMCCFRSolver(game, seed=5, traversals_per_update=K)
+sm = b2.ExternalSamplingMCCFRSolver(game, seed=5, traversals_per_update=K)
+dm.run_iteration(6)
+sm.run_iteration(6)
+tdm, tsm = dm.table(), sm.table()
+assert all(np.array_equal(tdm[f], tsm[f]) for f in ("regrets", "cum_policy")), "sharded MCCFR tables differ"
+torch.cuda.synchronize(); dist.barrier()
+t0 = time.perf_counter(); dm.run_iteration(40); torch.cuda.synchronize(); dist.barrier(); t_d = time.perf_counter() - t0
+t0 = time.perf_counter(); sm.run_iteration(40); torch.cuda.synchronize(); t_s = time.perf_counter() - t0
+mccfr_note = "mccfr K=%d bit-identical; %d-GPU %.3e trav/s vs 1-GPU %.3e" % (K, world, 2 * K * 40 / t_d, 2 * K * 40 / t_s)
+
 # 2. MCTS: trees sharded by root index; per-tree results must not depend on the number of GPUs
 g2 = b2.Game("connect_four", device=local)
 total = 4096
@@ -50,6 +64,6 @@ if rank == 0:
     r0 = r2[:, 0]
     want = [int((r0 > 0).sum()), int((r0 < 0).sum()), int((r0 == 0).sum()), int(p2.sum()), n]
     assert stats.tolist() == want, (stats.tolist(), want)
-    print("dist_check ok: world=%d cfr_max_abs_diff=%.3e rollout_stats=%s" % (world, err, stats.tolist()))
+    print("dist_check ok: world=%d cfr_max_abs_diff=%.3e rollout_stats=%s; %s" % (world, err, stats.tolist(), mccfr_note))
 dist.barrier()
 dist.destroy_process_group()

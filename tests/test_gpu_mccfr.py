@@ -64,3 +64,27 @@ def test_batched_updates_converge_faster_per_launch():
     s = b2.ExternalSamplingMCCFRSolver(b2.load_game("leduc_poker"), seed=3, traversals_per_update=4096)
     s.run_iteration(50)
     assert s.nash_conv() < 1.0
+
+
+@pytest.mark.parametrize("gs,K,world", [("leduc_poker", 1000, 2), ("leduc_poker", 4096, 8), ("kuhn_poker", 37, 4)])
+def test_lane_sharded_path_is_bit_identical_to_single_gpu(gs, K, world):
+    """The multi-GPU code path (b2s_mccfr_traverse_lanes per rank -> all-gather of the lanes -> b2s_mccfr_apply_partials)
+    run on one GPU, the ranks evaluated one after the other into the same lane buffer (what the all-gather assembles)."""
+    import ctypes as C
+    import torch
+    from open_spiel_b200._lib import check, lib
+    game = b2.load_game(gs)
+    single = b2.ExternalSamplingMCCFRSolver(game, seed=21, traversals_per_update=K)
+    sharded = b2.ExternalSamplingMCCFRSolver(game, seed=21, traversals_per_update=K)
+    partials = torch.zeros((64, sharded._info.num_entries), dtype=torch.float64, device="cuda")
+    per = 64 // world
+    for _ in range(3):
+        single.run_iteration(1)
+        for player in (0, 1):
+            for r in range(world):
+                check(lib().b2s_mccfr_traverse_lanes(sharded._h, player, K, 21, r * per, (r + 1) * per, partials.data_ptr(), None))
+            check(lib().b2s_mccfr_apply_partials(sharded._h, player, partials.data_ptr(), None))
+        a, b = single.table(), sharded.table()
+        for f in ("regrets", "cum_policy"):
+            assert np.array_equal(a[f], b[f]), (gs, K, world, f)
+    assert sharded.info().iteration == 3
