@@ -134,6 +134,11 @@ class Game:
     def new_initial_state(self):
         return State(self)
 
+    def deserialize_state(self, text):
+        """Game::DeserializeState (spiel.cc:757-791): replay a State::Serialize action list from the initial state."""
+        from .serialization import deserialize_state
+        return deserialize_state(self, text)
+
     def new_batch(self, n, device=None):
         return BatchedState(self, n, self.device if device is None else device)
 
@@ -521,6 +526,7 @@ class CFRSolver:
         self.game = game
         self._h = C.c_void_p()
         flags = (1 if linear_averaging else 0) | (2 if regret_matching_plus else 0) | (4 if _mccfr_tables else 0)
+        self._plus = bool(linear_averaging and regret_matching_plus)
         check(lib().b2s_cfr_create(game._gid, C.byref(game._cparams), flags, game.device, C.byref(self._h)))
         self._info = CfrInfo()
         check(lib().b2s_cfr_info_get(self._h, C.byref(self._info)))
@@ -567,6 +573,24 @@ class CFRSolver:
         r, c, u = C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(lib().b2s_cfr_tables(self._h, C.byref(r), C.byref(c), C.byref(u)))
         return r.value, c.value, u.value
+
+    def serialize(self, delimiter="<~>"):
+        """CFRSolverBase::Serialize (cfr.cc:284-307) with double_precision = -1: text the reference's DeserializeCFRSolver /
+        DeserializeCFRPlusSolver loads (information states keyed by their strings, doubles as lossless hex floats)."""
+        from . import serialization as ser
+        t = self.table()
+        i = self.info()
+        kind = "CFRPlusSolver" if getattr(self, "_plus", False) else "CFRSolver"
+        return ser.serialize_cfr_solver(str(self.game), kind, i.iteration, ser.table_keys(self.game._name, t), t, delimiter)
+
+    def load_serialized(self, text, delimiter="<~>"):
+        """Load tables and iteration counter from a CFRSolverBase::Serialize text (ours or the reference's)."""
+        from . import serialization as ser
+        parsed = ser.deserialize_cfr_solver(text, delimiter)
+        t = self.table()
+        r, c, p = ser.table_arrays_from(parsed["table"], ser.table_keys(self.game._name, t), t)
+        self.load_table(r, c, p, iteration=parsed["iteration"])
+        return parsed
 
     def nash_conv(self, average=True):
         """algorithms::NashConv (tabular_exploitability.cc) of the average (default) or current policy, on the device."""

@@ -430,10 +430,14 @@ struct from_chars_result { const char* ptr; std::errc ec; };
 inline from_chars_result from_chars(const char* first, const char* last, double& value, chars_format fmt = chars_format::general) {
   std::chars_format f = fmt == chars_format::hex ? std::chars_format::hex : fmt == chars_format::fixed ? std::chars_format::fixed
                         : fmt == chars_format::scientific ? std::chars_format::scientific : std::chars_format::general;
-  // absl accepts a leading "0x" for hex floats, std::from_chars does not; hex-float text here comes from "%a".
+  // absl::from_chars parses a "0x"-prefixed number as a hex float in general mode too (that is how the reference
+  // reads back its "%a" serialisation, cfr.cc:546-560); std::from_chars never accepts the prefix.
   bool neg = false;
   const char* p = first;
-  if (fmt == chars_format::hex) {
+  const char* q = (p < last && *p == '-') ? p + 1 : p;
+  const bool prefixed = last - q >= 2 && q[0] == '0' && (q[1] == 'x' || q[1] == 'X');
+  if (fmt == chars_format::hex || prefixed) {
+    f = std::chars_format::hex;
     if (p < last && *p == '-') { neg = true; ++p; }
     if (last - p >= 2 && p[0] == '0' && (p[1] == 'x' || p[1] == 'X')) p += 2;
     double v = 0;

@@ -231,4 +231,17 @@ double ref_mccfr_nash_conv(void* g, void* c) {
                return -1.0);
 }
 
+// ---- text formats (Game::ToString spiel.cc:802-806, CFRSolverBase::Serialize cfr.cc:284-307, DeserializeCFRSolver :704-715) ----
+int ref_game_to_string(void* g, char* buf, int cap) { GUARD(return CopyStr(((GameHolder*)g)->game->ToString(), buf, cap), return -1); }
+int ref_cfr_serialize(void* c, char* buf, int cap) {
+  GUARD(return CopyStr(((open_spiel::algorithms::CFRSolver*)c)->Serialize(), buf, cap), return -1);
+}
+void* ref_cfr_deserialize(const char* text) {
+  GUARD(return open_spiel::algorithms::DeserializeCFRSolver(text).release(), return nullptr);
+}
+int ref_state_serialize(void* s, char* buf, int cap) { GUARD(return CopyStr(((State*)s)->Serialize(), buf, cap), return -1); }
+void* ref_deserialize_state(void* g, const char* text) {
+  GUARD(return ((GameHolder*)g)->game->DeserializeState(text).release(), return nullptr);
+}
+
 }  // extern "C"

@@ -271,3 +271,49 @@ class RefMCCFR:
 
     def nash_conv(self):
         return lib().ref_mccfr_nash_conv(self.game._g, self._c)
+
+
+def _text(fn, *args, cap=1 << 22):
+    buf = C.create_string_buffer(cap)
+    n = fn(*args, buf, cap)
+    assert 0 <= n < cap, lib().ref_last_error()
+    return buf.value.decode()
+
+
+def game_to_string(game):
+    L = lib()
+    L.ref_game_to_string.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    return _text(L.ref_game_to_string, game._g)
+
+
+def cfr_serialize(ref_cfr):
+    L = lib()
+    L.ref_cfr_serialize.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    return _text(L.ref_cfr_serialize, ref_cfr._c)
+
+
+def cfr_deserialize(game, text):
+    """DeserializeCFRSolver(text) of the unmodified reference, wrapped as a RefCFR."""
+    L = lib()
+    L.ref_cfr_deserialize.restype = C.c_void_p
+    L.ref_cfr_deserialize.argtypes = [C.c_char_p]
+    ptr = L.ref_cfr_deserialize(text.encode())
+    assert ptr, L.ref_last_error()
+    r = RefCFR.__new__(RefCFR)
+    r.game, r._c = game, ptr
+    return r
+
+
+def state_serialize(state):
+    L = lib()
+    L.ref_state_serialize.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    return _text(L.ref_state_serialize, state._s, cap=1 << 16)
+
+
+def deserialize_state(game, text):
+    L = lib()
+    L.ref_deserialize_state.restype = C.c_void_p
+    L.ref_deserialize_state.argtypes = [C.c_void_p, C.c_char_p]
+    ptr = L.ref_deserialize_state(game._g, text.encode())
+    assert ptr, L.ref_last_error()
+    return RefState(game, ptr)
