@@ -341,7 +341,7 @@ def run_gpu(args):
     from open_spiel_b200 import parallel
     # MCTS: go 9x9, RandomRolloutEvaluator(1), uct_c=2, solve; independent roots sharded over GPUs
     go = b2.Game("go", {"board_size": 9}, device=local)
-    trees, sims = 16384, 128
+    trees, sims = 65536, 128                  # throughput grows with resident trees until ~14 warps/SM
     roots = go.new_batch(trees)
     b2.mcts_search(roots, 8, seed=1, tree_index_offset=rank * trees)          # warm-up: allocations, table upload
     barrier()

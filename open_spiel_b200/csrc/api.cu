@@ -22,6 +22,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 #define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e, #x); } while (0)
 
+constexpr int kHostChunks = 8;
+
 struct Batch {
   GameOps* ops = nullptr;
   b2s_game_info info;
@@ -32,7 +34,8 @@ struct Batch {
   ErrBuf* err = nullptr;
   // staging for the *_host entry points
   int* act_d = nullptr; u32* mask_d = nullptr; unsigned char* term_d = nullptr; float* rets_d = nullptr;
-  cudaStream_t hs = nullptr;
+  cudaStream_t hs = nullptr, hs2 = nullptr;      // b2s_step_fused_host: upload + kernel stream, download stream
+  cudaEvent_t host_ev[8] = {};
   // MCTS scratch (b2s_mcts_search): work lanes, log table, node arena
   void* mcts_work = nullptr; u64* mcts_hist = nullptr; long long mcts_work_cap = 0;
   double* mcts_log = nullptr; int mcts_log_n = 0;
@@ -47,6 +50,8 @@ struct Batch {
     if (term_d) cudaFree(term_d);
     if (rets_d) cudaFree(rets_d);
     if (hs) cudaStreamDestroy(hs);
+    if (hs2) cudaStreamDestroy(hs2);
+    for (cudaEvent_t e : host_ev) if (e) cudaEventDestroy(e);
     if (mcts_work) cudaFree(mcts_work);
     if (mcts_hist) cudaFree(mcts_hist);
     if (mcts_log) cudaFree(mcts_log);
@@ -247,20 +252,38 @@ int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h,
   Batch* B = (Batch*)batch;
   if (!B->hs) {
     CU(cudaStreamCreateWithFlags(&B->hs, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&B->hs2, cudaStreamNonBlocking));
+    for (int i = 0; i < kHostChunks; ++i) CU(cudaEventCreateWithFlags(&B->host_ev[i], cudaEventDisableTiming));
     CU(cudaMalloc((void**)&B->act_d, sizeof(int) * B->cap));
     CU(cudaMalloc((void**)&B->mask_d, sizeof(u32) * (size_t)B->info.mask_words * B->cap));
     CU(cudaMalloc((void**)&B->term_d, B->cap));
     CU(cudaMalloc((void**)&B->rets_d, sizeof(float) * (size_t)B->info.num_players * B->cap));
   }
-  cudaStream_t st = B->hs;
-  CU(cudaMemcpyAsync(B->act_d, actions_h, sizeof(int) * n, cudaMemcpyHostToDevice, st));
-  B->ops->step_fused(B->ctx(), B->act_d, mask_h ? B->mask_d : nullptr, term_h ? B->term_d : nullptr,
-                     rets_h ? B->rets_d : nullptr, n, st);
-  if (int r = post()) return r;
-  if (mask_h) CU(cudaMemcpyAsync(mask_h, B->mask_d, sizeof(u32) * (size_t)B->info.mask_words * n, cudaMemcpyDeviceToHost, st));
-  if (term_h) CU(cudaMemcpyAsync(term_h, B->term_d, n, cudaMemcpyDeviceToHost, st));
-  if (rets_h) CU(cudaMemcpyAsync(rets_h, B->rets_d, sizeof(float) * (size_t)B->info.num_players * n, cudaMemcpyDeviceToHost, st));
+  // Chunked and double-streamed: the upload + kernel of chunk c+1 (stream hs) overlaps the download of chunk c
+  // (stream hs2) — PCIe is full duplex, so the call costs about max(H2D, D2H) instead of their sum.
+  cudaStream_t st = B->hs, st2 = B->hs2;
+  const size_t W = (size_t)B->info.mask_words, P = (size_t)B->info.num_players, cb = B->ops->chunk_bytes();
+  const int64_t chunk = n >= (1 << 18) ? ((n + kHostChunks - 1) / kHostChunks + 1023) / 1024 * 1024 : n;
+  int c = 0;
+  for (int64_t lo = 0; lo < n; lo += chunk, ++c) {
+    const int64_t len = n - lo < chunk ? n - lo : chunk;
+    Ctx v = B->ctx();
+    v.planes = (char*)v.planes + (size_t)lo * cb;
+    if (v.hist) v.hist += lo;
+    v.lane0 = lo;
+    CU(cudaMemcpyAsync(B->act_d + lo, actions_h + lo, sizeof(int) * len, cudaMemcpyHostToDevice, st));
+    B->ops->step_fused(v, B->act_d + lo, mask_h ? B->mask_d + lo * W : nullptr, term_h ? B->term_d + lo : nullptr,
+                       rets_h ? B->rets_d + lo * P : nullptr, len, st);
+    if (int r = post()) return r;
+    cudaEvent_t ev = B->host_ev[c % kHostChunks];
+    CU(cudaEventRecord(ev, st));
+    CU(cudaStreamWaitEvent(st2, ev, 0));
+    if (mask_h) CU(cudaMemcpyAsync(mask_h + lo * W, B->mask_d + lo * W, sizeof(u32) * W * len, cudaMemcpyDeviceToHost, st2));
+    if (term_h) CU(cudaMemcpyAsync(term_h + lo, B->term_d + lo, len, cudaMemcpyDeviceToHost, st2));
+    if (rets_h) CU(cudaMemcpyAsync(rets_h + lo * P, B->rets_d + lo * P, sizeof(float) * P * len, cudaMemcpyDeviceToHost, st2));
+  }
   CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(st2));
   return 0;
 }
 

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kBlock, R::kMinBlocks) k_apply(Ctx ctx, typena
   for (int j = 0; j < ILP; ++j) {
     long long i = base + (long long)j * kBlock;
     if (a[j] == -1) continue;
-    if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) { flag_error(ctx.err, i); continue; }
+    if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) { flag_error(ctx.err, ctx.lane0 + i); continue; }
     R::store(s[j], ctx, i);
   }
 }
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kBlock) k_step_fused(Ctx ctx, typename R::Cfg 
     long long i = base + (long long)j * kBlock;
     if (i >= n) continue;
     if (a[j] != -1) {
-      if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) flag_error(ctx.err, i);
+      if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) flag_error(ctx.err, ctx.lane0 + i);
       else R::store(s[j], ctx, i);
     }
     bool t = R::terminal(s[j], cfg);

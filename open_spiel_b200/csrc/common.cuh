@@ -31,6 +31,7 @@ struct Ctx {
   long long cap;
   u64* hist;          // go: [max_len+1][cap] zobrist history, else nullptr
   ErrBuf* err;
+  long long lane0 = 0;   // batch lane of this view's lane 0 (sub-range views: planes / hist are pre-offset, errors report lane0 + i)
 };
 
 // ---- Philox4x32-10 counter RNG (Salmon et al. 2011), key = seed, counter = (lane, ply) ----------

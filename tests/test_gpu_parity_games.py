@@ -189,3 +189,33 @@ def test_full_size_properties_connect_four():
     # observation planes partition the board: exactly one plane set per cell
     obs = b.observation_tensor(0, n=65536).reshape(-1, 3, 42)
     assert bool((obs.sum(dim=1) == 1).all())
+
+
+def test_host_buffer_step_equals_device_step_across_chunks():
+    """b2s_step_fused_host uploads / steps / downloads in overlapping chunks: outputs must equal the device-buffer call on
+    an identical batch, and a rejected action must be reported with its batch lane (not its lane within a chunk)."""
+    n = (1 << 19) + 777                                       # > 2^18: chunked path, ragged last chunk
+    game = b2.load_game("connect_four")
+    a, b = game.new_batch(n), game.new_batch(n)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    mask_h = torch.empty((n, 1), dtype=torch.int32).pin_memory()
+    term_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    rets_h = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+    for ply in range(12):
+        acts = torch.randint(0, 7, (n,), generator=g, dtype=torch.int32)    # early plies: every column is legal
+        acts_h = acts.pin_memory()
+        m, t, r = a.step_fused(acts.to(a._dev))
+        b.step_host(acts_h, mask_h, term_h, rets_h)
+        if ply < 6:
+            assert a.error_count()[0] == 0 and b.error_count()[0] == 0
+        assert torch.equal(m.cpu().reshape(-1), mask_h.reshape(-1))
+        assert torch.equal(t.cpu(), term_h) and torch.equal(r.cpu(), rets_h)
+    # one illegal action far from lane 0: column 0 six more times fills it, the seventh drop is rejected
+    c = game.new_batch(n)
+    bad_lane = 3 * (1 << 17) + 12345
+    acts_h = torch.full((n,), -1, dtype=torch.int32).pin_memory()
+    acts_h[bad_lane] = 0
+    for _ in range(7):
+        c.step_host(acts_h, mask_h, term_h, rets_h)
+    cnt, first = c.error_count()
+    assert cnt >= 1 and first == bad_lane
