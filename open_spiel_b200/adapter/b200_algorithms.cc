@@ -1,0 +1,164 @@
+#include "b200_algorithms.h"
+
+#include <cstring>
+#include <functional>
+
+namespace open_spiel {
+namespace b200 {
+namespace {
+
+void Check(int rc) {
+  if (rc != 0) SpielFatalError(std::string("b2s: ") + b2s_last_error());
+}
+
+}  // namespace
+
+int GameIdAndParams(const Game& game, b2s_params* p) {
+  const std::string name = game.GetType().short_name;
+  const GameParameters params = game.GetParameters();
+  b2s_params_default(p);
+  auto geti = [&](const char* k, int32_t* out) {
+    auto it = params.find(k);
+    if (it == params.end()) return;
+    if (it->second.has_int_value()) *out = it->second.int_value();
+    else if (it->second.has_bool_value()) *out = it->second.bool_value() ? 1 : 0;
+  };
+  auto getd = [&](const char* k, double* out) {
+    auto it = params.find(k);
+    if (it != params.end() && it->second.has_double_value()) *out = it->second.double_value();
+  };
+  geti("rows", &p->rows); geti("columns", &p->columns); geti("x_in_row", &p->x_in_row);
+  geti("egocentric_obs_tensor", &p->egocentric_obs_tensor);
+  geti("board_size", &p->board_size); geti("swap", &p->swap); geti("plain_obs_tensor", &p->plain_obs_tensor);
+  geti("num_rows", &p->rows); geti("num_cols", &p->columns);
+  geti("handicap", &p->handicap); geti("max_game_length", &p->max_game_length); getd("komi", &p->komi);
+  geti("players", &p->players); geti("starting_player", &p->starting_player);
+  int gid = b2s_game_id(name.c_str());
+  if (gid < 0) SpielFatalError("b200: unsupported game " + name);
+  return gid;
+}
+
+// ---- MCTS ------------------------------------------------------------------------------------------------------
+B200MCTSBot::B200MCTSBot(const Game& game, int n_rollouts, double uct_c, int max_simulations, int64_t max_memory_mb,
+                         bool solve, int seed, bool verbose, algorithms::ChildSelectionPolicy policy) {
+  gid_ = GameIdAndParams(game, &params_);
+  num_actions_ = game.NumDistinctActions();
+  memset(&cfg_, 0, sizeof cfg_);
+  cfg_.max_simulations = max_simulations;
+  cfg_.n_rollouts = n_rollouts;
+  cfg_.solve = solve ? 1 : 0;
+  cfg_.child_selection_policy = policy == algorithms::ChildSelectionPolicy::PUCT ? B2S_MCTS_PUCT : B2S_MCTS_UCT;
+  cfg_.uct_c = uct_c;
+  cfg_.seed = (uint64_t)seed;
+  cfg_.max_nodes_total = max_memory_mb > 0 ? (max_memory_mb << 20) / 32 : 0;     // arena nodes are 32 bytes
+  Check(b2s_batch_create(gid_, &params_, 1, 0, &batch_));
+  Check(b2s_device_alloc(0, &dev_, 64 + (sizeof(int32_t) + sizeof(double)) * (size_t)num_actions_));
+  visits_.assign(num_actions_, 0);
+}
+
+B200MCTSBot::~B200MCTSBot() {
+  if (batch_) b2s_batch_destroy(batch_);
+  if (dev_) b2s_device_free(0, dev_);
+}
+
+Action B200MCTSBot::Step(const State& state) {
+  // the search root = the reference state's action history replayed on a one-lane device batch
+  char* d = (char*)dev_;
+  int32_t* act_d = (int32_t*)d;
+  int32_t* best_d = (int32_t*)(d + 16);
+  int32_t* visits_d = (int32_t*)(d + 64);
+  double* reward_d = (double*)(d + 64 + sizeof(int32_t) * (size_t)((num_actions_ + 1) & ~1));
+  Check(b2s_reset(batch_, 1, nullptr));
+  for (Action a : state.History()) {
+    int32_t a32 = (int32_t)a;
+    Check(b2s_memcpy_h2d(0, act_d, &a32, sizeof a32, nullptr));
+    Check(b2s_apply_actions(batch_, act_d, 1, nullptr));
+  }
+  int64_t bad = 0;
+  Check(b2s_error_count(batch_, &bad, nullptr, nullptr));
+  if (bad) SpielFatalError("b200: the state's history is not playable on the device");
+  cfg_.tree_index_offset = (int64_t)steps_++;            // a fresh random stream per move, like the bot's advancing rng_
+  Check(b2s_mcts_search(batch_, 1, &cfg_, visits_d, reward_d, nullptr, best_d, nullptr, nullptr));
+  int32_t best = -1;
+  Check(b2s_memcpy_d2h(0, &best, best_d, sizeof best, nullptr));
+  Check(b2s_memcpy_d2h(0, visits_.data(), visits_d, sizeof(int32_t) * (size_t)num_actions_, nullptr));
+  Check(b2s_stream_synchronize(0, nullptr));
+  if (best < 0) SpielFatalError("b200: MCTS called on a terminal state");
+  return best;
+}
+
+// ---- CFR -------------------------------------------------------------------------------------------------------
+B200CFRSolver::B200CFRSolver(const Game& game, bool cfr_plus) : game_(game.shared_from_this()) {
+  b2s_params p;
+  int gid = GameIdAndParams(game, &p);
+  Check(b2s_cfr_create(gid, &p, cfr_plus ? (B2S_CFR_LINEAR_AVERAGING | B2S_CFR_REGRET_MATCHING_PLUS) : 0, 0, &solver_));
+  Check(b2s_cfr_info_get(solver_, &info_));
+  const int I = info_.num_infosets, E = info_.num_entries, T = info_.key_floats;
+  offsets_.resize(I + 1); legal_.resize(E);
+  std::vector<float> keys((size_t)I * T);
+  Check(b2s_cfr_export(solver_, nullptr, nullptr, nullptr, offsets_.data(), legal_.data(), nullptr, keys.data(), nullptr));
+  // The device keys its rows by information-state TENSOR, the reference's policies by information-state STRING: walk the
+  // stock game tree once on the host and pair the two for every decision node.
+  std::unordered_map<std::string, std::string> tensor_to_string;
+  std::function<void(const State&)> walk = [&](const State& s) {
+    if (s.IsTerminal()) return;
+    if (!s.IsChanceNode()) {
+      Player pl = s.CurrentPlayer();
+      std::vector<float> t = s.InformationStateTensor(pl);
+      tensor_to_string.emplace(std::string((const char*)t.data(), sizeof(float) * t.size()), s.InformationStateString(pl));
+    }
+    for (Action a : s.LegalActions()) walk(*s.Child(a));
+  };
+  walk(*game.NewInitialState());
+  keys_.resize(I);
+  for (int i = 0; i < I; ++i) {
+    auto it = tensor_to_string.find(std::string((const char*)&keys[(size_t)i * T], sizeof(float) * T));
+    if (it == tensor_to_string.end()) SpielFatalError("b200: device information state without a host counterpart");
+    keys_[i] = it->second;
+  }
+}
+
+B200CFRSolver::~B200CFRSolver() { if (solver_) b2s_cfr_destroy(solver_); }
+
+void B200CFRSolver::EvaluateAndUpdatePolicy() { EvaluateAndUpdatePolicy(1); }
+void B200CFRSolver::EvaluateAndUpdatePolicy(int iterations) {
+  Check(b2s_cfr_iterate(solver_, iterations, nullptr));
+  Check(b2s_stream_synchronize(0, nullptr));
+}
+
+TabularPolicy B200CFRSolver::PolicyFrom(const std::vector<double>& v, bool normalise) const {
+  std::unordered_map<std::string, ActionsAndProbs> table;
+  for (int i = 0; i < info_.num_infosets; ++i) {
+    const int lo = offsets_[i], hi = offsets_[i + 1];
+    double sum = 0.0;
+    for (int k = lo; k < hi; ++k) sum += v[k];
+    ActionsAndProbs ap;
+    for (int k = lo; k < hi; ++k) {
+      double p = !normalise ? v[k] : (sum > 0 ? v[k] / sum : 1.0 / (hi - lo));   // GetStatePolicyFromInformationStateValues, cfr.cc:104-125
+      ap.push_back({legal_[k], p});
+    }
+    table.emplace(keys_[i], ap);
+  }
+  return TabularPolicy(table);
+}
+
+TabularPolicy B200CFRSolver::AveragePolicy() const {
+  std::vector<double> cum(info_.num_entries);
+  Check(b2s_cfr_export(solver_, nullptr, cum.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+  return PolicyFrom(cum, true);
+}
+
+TabularPolicy B200CFRSolver::CurrentPolicy() const {
+  std::vector<double> cur(info_.num_entries);
+  Check(b2s_cfr_export(solver_, nullptr, nullptr, cur.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
+  return PolicyFrom(cur, false);
+}
+
+double B200CFRSolver::NashConv() const {
+  double nc = 0, vals[4];
+  Check(b2s_cfr_nash_conv(solver_, 1, &nc, vals, nullptr));
+  return nc;
+}
+
+}  // namespace b200
+}  // namespace open_spiel

@@ -1,0 +1,76 @@
+// C++ host adapters for the two search / solving loops, with the reference's own constructor signatures, so existing
+// OpenSpiel code switches by changing a type name:
+//   B200MCTSBot   : open_spiel::Bot           <- algorithms::MCTSBot (mcts.h:149-230) with a RandomRolloutEvaluator
+//   B200CFRSolver                             <- algorithms::CFRSolver / CFRPlusSolver (cfr.h:312-357)
+// Every computation is a call into the b2s C ABI (libb2s.so); these classes only translate between the reference's
+// host objects (State history, TabularPolicy keyed by information-state strings) and device batches / tables.
+#ifndef OPEN_SPIEL_B200_ADAPTER_B200_ALGORITHMS_H_
+#define OPEN_SPIEL_B200_ADAPTER_B200_ALGORITHMS_H_
+
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "open_spiel/algorithms/mcts.h"
+#include "open_spiel/policy.h"
+#include "open_spiel/spiel.h"
+#include "open_spiel/spiel_bots.h"
+
+extern "C" {
+#include "b2s.h"
+}
+
+namespace open_spiel {
+namespace b200 {
+
+// b2s game id + parameters for a reference Game object (by short name and GetParameters()).
+int GameIdAndParams(const Game& game, b2s_params* params);
+
+class B200MCTSBot : public Bot {
+ public:
+  // Argument order of MCTSBot's constructor (mcts.h:161-169); the evaluator is RandomRolloutEvaluator(n_rollouts, seed).
+  B200MCTSBot(const Game& game, int n_rollouts, double uct_c, int max_simulations, int64_t max_memory_mb, bool solve,
+              int seed, bool verbose,
+              algorithms::ChildSelectionPolicy child_selection_policy = algorithms::ChildSelectionPolicy::UCT);
+  ~B200MCTSBot() override;
+  Action Step(const State& state) override;
+  void Restart() override {}
+  void RestartAt(const State& state) override {}
+  // Root statistics of the last Step: visit count per action id (0 for illegal actions).
+  const std::vector<int>& LastVisitCounts() const { return visits_; }
+
+ private:
+  b2s_params params_;
+  b2s_mcts_config cfg_;
+  int gid_ = -1;
+  int num_actions_ = 0;
+  void* batch_ = nullptr;      // one lane: the search root
+  void* dev_ = nullptr;        // device scratch: action, visits, rewards, best
+  std::vector<int> visits_;
+  uint64_t steps_ = 0;
+};
+
+class B200CFRSolver {
+ public:
+  explicit B200CFRSolver(const Game& game, bool cfr_plus = false);
+  ~B200CFRSolver();
+  void EvaluateAndUpdatePolicy();                       // CFRSolverBase::EvaluateAndUpdatePolicy (cfr.cc:263-282)
+  void EvaluateAndUpdatePolicy(int iterations);         // ... `iterations` times inside one kernel launch
+  TabularPolicy AveragePolicy() const;                  // CFRAveragePolicy (cfr.cc:104-125) as a TabularPolicy
+  TabularPolicy CurrentPolicy() const;
+  double NashConv() const;                              // on the device (b2s_cfr_nash_conv)
+  int NumInfoStates() const { return info_.num_infosets; }
+
+ private:
+  TabularPolicy PolicyFrom(const std::vector<double>& per_entry, bool normalise) const;
+  std::shared_ptr<const Game> game_;
+  void* solver_ = nullptr;
+  b2s_cfr_info info_;
+  std::vector<std::string> keys_;                       // information-state string of every device table row
+  std::vector<int32_t> offsets_, legal_;
+};
+
+}  // namespace b200
+}  // namespace open_spiel
+#endif
