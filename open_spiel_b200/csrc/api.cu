@@ -22,7 +22,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 #define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e, #x); } while (0)
 
-constexpr int kHostChunks = 8;
+constexpr int kHostChunks = 8, kHostChunksDefault = 2;   // measured on B200 + PCIe gen5: 1: 0.364 ms, 2: 0.343, 4: 0.358, 8: 0.395 (1M lanes)
 
 struct Batch {
   GameOps* ops = nullptr;
@@ -263,7 +263,12 @@ int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h,
   // (stream hs2) — PCIe is full duplex, so the call costs about max(H2D, D2H) instead of their sum.
   cudaStream_t st = B->hs, st2 = B->hs2;
   const size_t W = (size_t)B->info.mask_words, P = (size_t)B->info.num_players, cb = B->ops->chunk_bytes();
-  const int64_t chunk = n >= (1 << 18) ? ((n + kHostChunks - 1) / kHostChunks + 1023) / 1024 * 1024 : n;
+  static const int n_chunks = [] {                 // B2S_HOST_CHUNKS=1..8 overrides the default (tuning knob)
+    const char* e = getenv("B2S_HOST_CHUNKS");
+    int v = e ? atoi(e) : kHostChunksDefault;
+    return v < 1 ? 1 : (v > kHostChunks ? kHostChunks : v);
+  }();
+  const int64_t chunk = (n >= (1 << 18) && n_chunks > 1) ? ((n + n_chunks - 1) / n_chunks + 1023) / 1024 * 1024 : n;
   int c = 0;
   for (int64_t lo = 0; lo < n; lo += chunk, ++c) {
     const int64_t len = n - lo < chunk ? n - lo : chunk;

@@ -204,7 +204,7 @@ def test_host_buffer_step_equals_device_step_across_chunks():
     for ply in range(12):
         acts = torch.randint(0, 7, (n,), generator=g, dtype=torch.int32)    # early plies: every column is legal
         acts_h = acts.pin_memory()
-        m, t, r = a.step_fused(acts.to(a._dev))
+        m, t, r = a.step(acts.to(a._dev))
         b.step_host(acts_h, mask_h, term_h, rets_h)
         if ply < 6:
             assert a.error_count()[0] == 0 and b.error_count()[0] == 0
