@@ -45,6 +45,32 @@ def rollout_stats(returns, plies):
     return allreduce_stats(s.to(torch.int64))
 
 
+def lane_range(rank=None, world_size=None, lanes=64):
+    """The reduction lanes [lo, hi) a rank owns in the lane-sharded MCCFR (world size must divide `lanes`)."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    if lanes % world_size:
+        raise ValueError("world size must divide %d" % lanes)
+    per = lanes // world_size
+    return rank * per, (rank + 1) * per
+
+
+def gather_lanes(partials, lo, hi):
+    """All-gather along dim 0 in place: every rank contributes rows [lo, hi) of `partials` ([lanes, E]) and ends up with
+    all rows.  NCCL: one all_gather_into_tensor; gloo (CPU tests): list all_gather."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return partials
+    mine = partials[lo:hi].clone()
+    if partials.is_cuda:
+        dist.all_gather_into_tensor(partials, mine)
+    else:
+        pieces = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(pieces, mine)
+        partials.copy_(torch.cat(pieces, dim=0))
+    return partials
+
+
 class _DevArray:
     """__cuda_array_interface__ view of library-owned device memory, so torch / NCCL can operate on it in place."""
 
@@ -94,23 +120,18 @@ class DistributedExternalSamplingMCCFRSolver:
         from .spiel import ExternalSamplingMCCFRSolver
         self.solver = ExternalSamplingMCCFRSolver(game, seed, traversals_per_update)
         self.rank, self.world = world()
-        if self.LANES % self.world:
-            raise ValueError("world size must divide %d" % self.LANES)
-        self.lanes_per_rank = self.LANES // self.world
+        self.lo, self.hi = lane_range(self.rank, self.world, self.LANES)
         dev = torch.device("cuda", game.device)
         self.partials = torch.zeros((self.LANES, self.solver._info.num_entries), dtype=torch.float64, device=dev)
 
     def run_iteration(self, iterations=1):
-        import torch.distributed as dist
         L, h, s = lib(), self.solver._h, self.solver
         st = C.c_void_p(torch.cuda.current_stream(self.partials.device).cuda_stream)
-        lo = self.rank * self.lanes_per_rank
         for _ in range(int(iterations)):
             for player in (0, 1):
-                check(L.b2s_mccfr_traverse_lanes(h, player, s.traversals_per_update, s.seed, lo, lo + self.lanes_per_rank,
+                check(L.b2s_mccfr_traverse_lanes(h, player, s.traversals_per_update, s.seed, self.lo, self.hi,
                                                  self.partials.data_ptr(), st))
-                if self.world > 1:
-                    dist.all_gather_into_tensor(self.partials, self.partials[lo:lo + self.lanes_per_rank].clone())
+                gather_lanes(self.partials, self.lo, self.hi)
                 check(L.b2s_mccfr_apply_partials(h, player, self.partials.data_ptr(), st))
 
     def table(self):

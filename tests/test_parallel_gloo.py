@@ -49,6 +49,16 @@ def _worker(rank, world, port, q):
     dist.all_gather(both, local.to(torch.int64))
     assert torch.equal(stats, both[0] + both[1])
     assert int(stats[4]) == total and int(stats[:3].sum()) == total
+    # lane-sharded MCCFR exchange: every rank owns 64 / world reduction lanes; after the gather all ranks hold the same
+    # [64, E] partial sums, so the fixed-order tree gives every rank the same bits
+    llo, lhi = parallel.lane_range()
+    assert (llo, lhi) == (rank * 32, rank * 32 + 32)
+    E = 37
+    full = torch.arange(64 * E, dtype=torch.float64).reshape(64, E) * 0.1 + 1.0 / 3.0
+    partials = torch.zeros(64, E, dtype=torch.float64)
+    partials[llo:lhi] = full[llo:lhi]
+    parallel.gather_lanes(partials, llo, lhi)
+    assert torch.equal(partials, full)
     q.put((rank, edges, stats.tolist()))
     dist.destroy_process_group()
 
@@ -66,6 +76,16 @@ def test_world_size_2_gloo_sharding_and_stats():
         assert p.exitcode == 0
     results = [q.get(timeout=5) for _ in range(world)]
     assert results[0][1] == results[1][1] and results[0][2] == results[1][2]     # all ranks agree
+
+
+def test_lane_range_properties():
+    sys.path.insert(0, ROOT)
+    from open_spiel_b200.parallel import lane_range
+    for world in (1, 2, 4, 8, 16, 32, 64):
+        pieces = [lane_range(r, world) for r in range(world)]
+        assert pieces[0][0] == 0 and pieces[-1][1] == 64 and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+    with pytest.raises(ValueError):
+        lane_range(0, 3)
 
 
 def test_shard_range_properties():
