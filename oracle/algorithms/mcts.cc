@@ -14,7 +14,9 @@
 //       legal candidate is played — a uniform draw over the legal actions    (replaces absl::Uniform, mcts.cc:54)
 //   key = seed + tree_index * 0x9E3779B97F4A7C15.
 #include <cmath>
+#include <algorithm>
 #include <limits>
+#include <random>
 
 #include "../oracle.h"
 #include "philox.h"
@@ -62,7 +64,31 @@ int64_t SampleRolloutAction(const State& s, Draw draw, uint32_t ply) {
   }
 }
 
+// absl::Uniform(rng, 0u, n) as the reference calls it at mcts.cc:54 (common type of unsigned and size_t = a 64-bit
+// unsigned): abseil's published uniform_int_distribution algorithm — a 64-bit word assembled from two mt19937 draws
+// (first draw in the high half), a mask when n is a power of two, else Lemire's multiply-shift with rejection of the
+// low products below (2^64 - n) mod n.  oracle/absl_shim implements the same published algorithm for the reference
+// build; seeded parity with stock abseil binaries stays unpinned.
+uint64_t AbslUniformBelow(std::mt19937& g, uint64_t n) {
+  auto bits64 = [&]() { uint64_t hi = g(); return (hi << 32) + (uint64_t)g(); };
+  uint64_t bits = bits64();
+  const uint64_t r = n - 1;
+  if ((r & n) == 0) return bits & r;
+  unsigned __int128 product = (unsigned __int128)bits * n;
+  if ((uint64_t)product < n) {
+    const uint64_t threshold = (0 - n) % n;
+    while ((uint64_t)product < threshold) { bits = bits64(); product = (unsigned __int128)bits * n; }
+  }
+  return (uint64_t)(product >> 64);
+}
+
 struct Search {
+  // rng_mode 0: the position-keyed Philox stream shared with the device kernel (default).
+  // rng_mode 1: the reference's own streams — MCTSBot::rng_ (std::mt19937(seed), std::shuffle of new children,
+  //             mcts.cc:294) and RandomRolloutEvaluator::rng_ (std::mt19937(seed), absl::Uniform over LegalActions(),
+  //             mcts.cc:54) — so that results can be compared with the unmodified reference bit for bit.
+  int rng_mode = 0;
+  std::mt19937 bot_rng, eval_rng;
   uint64_t key;
   double uct_c, max_utility;
   bool puct = false;               // ChildSelectionPolicy (mcts.h:148)
@@ -77,7 +103,12 @@ struct Search {
       auto ws = state.Clone();
       uint32_t ply = 0;
       while (!ws->IsTerminal()) {
-        ws->ApplyAction(SampleRolloutAction(*ws, [&](uint32_t b, uint32_t n) { return RngUniform(key, sim, b, 2 + r, n); }, ply));
+        if (rng_mode == 1) {
+          auto actions = ws->LegalActions();
+          ws->ApplyAction(actions[AbslUniformBelow(eval_rng, actions.size())]);
+        } else {
+          ws->ApplyAction(SampleRolloutAction(*ws, [&](uint32_t b, uint32_t n) { return RngUniform(key, sim, b, 2 + r, n); }, ply));
+        }
         ++ply;
       }
       auto returns = ws->Returns();
@@ -96,7 +127,8 @@ struct Search {
       if (cur->children.empty()) {
         auto legal = ws->LegalActions();             // uniform prior over LegalActions (mcts.cc:74-87)
         uint32_t e = expansions++;
-        for (int i = (int)legal.size() - 1; i >= 1; --i) std::swap(legal[i], legal[RngUniform(key, e, i, 1, i + 1)]);
+        if (rng_mode == 1) std::shuffle(legal.begin(), legal.end(), bot_rng);
+        else for (int i = (int)legal.size() - 1; i >= 1; --i) std::swap(legal[i], legal[RngUniform(key, e, i, 1, i + 1)]);
         int player = ws->CurrentPlayer();
         cur->children.reserve(legal.size());
         for (auto a : legal) { Node c; c.action = a; c.player = player; cur->children.push_back(c); }
@@ -168,7 +200,7 @@ int orc_mcts_search(void* game, void* state, double uct_c, int max_simulations, 
                     uint64_t seed, uint64_t tree_index, int64_t* child_actions, int* child_visits,
                     double* child_rewards, double* child_outcome_p0, int cap, int64_t* best_action,
                     int* root_visits, double* root_outcome_p0, long* nodes_out, int* sims_run,
-                    int child_selection_policy) {
+                    int child_selection_policy, int rng_mode) {
   using namespace oracle;
   Game* g = (Game*)game;
   State* s = (State*)state;
@@ -179,6 +211,8 @@ int orc_mcts_search(void* game, void* state, double uct_c, int max_simulations, 
   srch.n_rollouts = n_rollouts;
   srch.solve = solve != 0;
   srch.puct = child_selection_policy == 1;
+  srch.rng_mode = rng_mode;
+  if (rng_mode == 1) { srch.bot_rng.seed((uint32_t)seed); srch.eval_rng.seed((uint32_t)seed); }
   Node root;
   root.player = s->CurrentPlayer();
   int ran = srch.Run(&root, *s, max_simulations);

@@ -8,7 +8,9 @@
 // board scans, linked-list chains, recursion) so that it is independent of the bitboard kernels it
 // checks.  Pinned against: tests/golden/playthroughs/*.json (reference playthrough traces), the
 // known-answer cases of the reference's *_test.cc files (tests/test_oracle_known_answers.py), and,
-// when built, the unmodified reference compiled against an abseil shim (oracle/_ref, tests/test_ref_vs_oracle.py).
+// when built, the unmodified reference compiled against an abseil shim (oracle/_ref): tests/test_ref_vs_oracle.py (State
+// functions, CFR tables), test_mcts_oracle_vs_reference.py (MCTSBot searches bit for bit on the reference's RNG streams),
+// test_mccfr_oracle.py (ExternalSamplingMCCFRSolver tables bit for bit), test_trajectories_oracle.py (RecordBatchedTrajectory).
 #ifndef B2S_ORACLE_H_
 #define B2S_ORACLE_H_
 

@@ -1,0 +1,49 @@
+"""CPU: pins the oracle's MCTS (oracle/algorithms/mcts.cc) to the UNMODIFIED reference's MCTSBot (algorithms/mcts.cc, built by
+oracle/ref_build.mk).  Fed the reference's own random streams — std::mt19937(seed) for the bot (std::shuffle of new
+children) and for the RandomRolloutEvaluator (absl::Uniform over the legal actions) — the restatement must reproduce the
+search BIT FOR BIT: the root's children in the same (shuffled) order, their visit counts, their total rewards as exact
+doubles, and BestChild.  The device kernel is then compared with the same oracle code on the Philox stream
+(tests/test_gpu_mcts.py): the two modes differ only in where the random integers come from."""
+import random
+
+import pytest
+
+from oracle_lib import OracleGame, oracle_mcts
+import ref_lib
+
+pytestmark = pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not built")
+
+CASES = [
+    # game, prefix plies, simulations, n_rollouts, solve, seed
+    ("tic_tac_toe", 0, 500, 1, True, 1),
+    ("tic_tac_toe", 3, 300, 4, True, 7),
+    ("tic_tac_toe", 2, 400, 1, False, 3),
+    ("connect_four", 0, 600, 1, True, 42),
+    ("connect_four", 9, 400, 2, True, 5),
+    ("breakthrough(rows=6,columns=6)", 4, 200, 1, True, 11),
+    ("hex(board_size=5)", 3, 300, 1, True, 2),
+    ("go(board_size=5)", 6, 150, 1, True, 9),
+    ("go(board_size=9)", 10, 60, 1, True, 13),
+]
+
+
+@pytest.mark.parametrize("gs,prefix,sims,nroll,solve,seed", CASES, ids=["%s-%d" % (c[0], c[2]) for c in CASES])
+def test_oracle_mcts_equals_reference_mctsbot_bitwise(gs, prefix, sims, nroll, solve, seed):
+    rng = random.Random(seed)
+    rg, og = ref_lib.RefGame(gs), OracleGame(gs)
+    rs, os_ = rg.new_initial_state(), og.new_initial_state()
+    for _ in range(prefix):
+        a = rng.choice(rs.legal_actions())
+        nxt = rs.clone()
+        nxt.apply_action(a)
+        if nxt.is_terminal():
+            break
+        rs.apply_action(a)
+        os_.apply_action(a)
+    ref = ref_lib.ref_mcts(rg, rs, 2.0, sims, nroll, solve, seed)
+    mine = oracle_mcts(os_, 2.0, sims, nroll, solve, seed, reference_rng=True)
+    assert [c[0] for c in mine["children"]] == [c[0] for c in ref["children"]]          # same shuffled child order
+    assert [c[1] for c in mine["children"]] == [c[1] for c in ref["children"]]          # visit counts
+    assert [c[2] for c in mine["children"]] == [c[2] for c in ref["children"]]          # total rewards, exact doubles
+    assert mine["best_action"] == ref["best_action"]
+    assert mine["root_visits"] == ref["root_visits"]
