@@ -388,6 +388,23 @@ class State:
             player = max(self.current_player(), 0)
         return self._b.information_state_tensor(player)[0].cpu().numpy()
 
+    def information_state_string(self, player=None):
+        """State::InformationStateString (kuhn_poker.cc:109-166, leduc_poker.cc:198-239), rebuilt on the host from the
+        device's information-state tensor (open_spiel_b200/serialization.py)."""
+        from .serialization import INFORMATION_STATE_STRING
+        f = INFORMATION_STATE_STRING.get(self._game._name)
+        if f is None:
+            raise B2SError("%s provides no information state string" % self._game._name)
+        return f(self.information_state_tensor(player))
+
+    def chance_outcomes(self):
+        """State::ChanceOutcomes: kuhn / leduc deal uniformly over the remaining cards (kuhn_poker.cc:329-337,
+        leduc_poker.cc:546-571)."""
+        if not self.is_chance_node():
+            raise B2SError("chance_outcomes() at a non-chance node")
+        la = self.legal_actions()
+        return [(a, 1.0 / len(la)) for a in la]
+
     def history(self):
         return [a for _, a in self._history]
 
@@ -603,6 +620,14 @@ class CFRSolver:
     def exploitability(self, average=True):
         """algorithms::Exploitability = NashConv / num_players."""
         return self.nash_conv(average) / 2.0
+
+    def tabular_average_policy(self):
+        """pyspiel CFRSolver.tabular_average_policy (python/pybind11/policy.cc:224-245): {information state string:
+        [(action, prob)]} — the keys the reference's TabularPolicy uses."""
+        from . import serialization as ser
+        t = self.table()
+        keys = ser.table_keys(self.game._name, t)
+        return {keys[k]: v for k, v in enumerate(self.average_policy().values())}
 
     def average_policy(self):
         """CFRAveragePolicy (cfr.cc:104-125): {key bytes: [(action, prob)]}, uniform where nothing accumulated."""

@@ -58,3 +58,33 @@ def test_state_serialize_round_trip_through_the_reference():
         back = game.deserialize_state(ref_lib.state_serialize(rs))   # and we load the reference's
         assert back.history() == st.history() and back.legal_actions() == st.legal_actions()
         assert np.array_equal(np.asarray(back.observation_tensor(0)), np.asarray(st.observation_tensor(0)))
+
+
+def test_information_state_strings_and_tabular_policy_match_the_reference():
+    rng = np.random.RandomState(11)
+    for name in ("kuhn_poker", "leduc_poker"):
+        game, rg = b2.load_game(name), ref_lib.RefGame(name)
+        for _ in range(6):
+            st, rs = game.new_initial_state(), rg.new_initial_state()
+            while not rs.is_terminal():
+                if rs.current_player() >= 0:
+                    p = rs.current_player()
+                    assert st.information_state_string(p) == rs.information_state_string(p)
+                else:
+                    assert [a for a, _ in st.chance_outcomes()] == [a for a, _ in rs.chance_outcomes()]
+                    assert [pr for _, pr in st.chance_outcomes()] == [pr for _, pr in rs.chance_outcomes()]
+                la = rs.legal_actions()
+                a = int(la[rng.randint(len(la))])
+                st.apply_action(a)
+                rs.apply_action(a)
+        dev = b2.CFRSolver(game)
+        ref = ref_lib.RefCFR(rg)
+        dev.evaluate_and_update_policy(9)
+        ref.iterate(9)
+        pol = dev.tabular_average_policy()
+        table = ref.table()
+        assert set(pol) == set(table)
+        for key, v in table.items():
+            total = sum(v["cum_policy"])
+            want = [c / total if total > 0 else 1.0 / len(v["legal"]) for c in v["cum_policy"]]
+            assert [a for a, _ in pol[key]] == v["legal"] and [p for _, p in pol[key]] == want
