@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,13 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 #define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_fail(_e, #x); } while (0)
 
+constexpr int kMaxDevices = 64;
+struct HostPipe {                 // per device: b2s_step_fused_host's upload+kernel stream, download stream, chunk events
+  std::mutex mu;
+  cudaStream_t hs = nullptr, hs2 = nullptr;
+  cudaEvent_t ev[8] = {};
+};
+static HostPipe g_host_pipe[kMaxDevices];
 constexpr int kHostChunks = 8, kHostChunksDefault = 2;   // measured on B200 + PCIe gen5: 1: 0.364 ms, 2: 0.343, 4: 0.358, 8: 0.395 (1M lanes)
 
 struct Batch {
@@ -34,8 +42,7 @@ struct Batch {
   ErrBuf* err = nullptr;
   // staging for the *_host entry points
   int* act_d = nullptr; u32* mask_d = nullptr; unsigned char* term_d = nullptr; float* rets_d = nullptr;
-  cudaStream_t hs = nullptr, hs2 = nullptr;      // b2s_step_fused_host: upload + kernel stream, download stream
-  cudaEvent_t host_ev[8] = {};
+  bool host_ready = false;                       // b2s_step_fused_host staging buffers allocated
   // MCTS scratch (b2s_mcts_search): work lanes, log table, node arena
   void* mcts_work = nullptr; u64* mcts_hist = nullptr; long long mcts_work_cap = 0;
   double* mcts_log = nullptr; int mcts_log_n = 0;
@@ -49,9 +56,6 @@ struct Batch {
     if (mask_d) cudaFree(mask_d);
     if (term_d) cudaFree(term_d);
     if (rets_d) cudaFree(rets_d);
-    if (hs) cudaStreamDestroy(hs);
-    if (hs2) cudaStreamDestroy(hs2);
-    for (cudaEvent_t e : host_ev) if (e) cudaEventDestroy(e);
     if (mcts_work) cudaFree(mcts_work);
     if (mcts_hist) cudaFree(mcts_hist);
     if (mcts_log) cudaFree(mcts_log);
@@ -250,10 +254,19 @@ int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h,
   if (int r = check(batch, n)) return r;
   if (!actions_h) return fail("null actions");
   Batch* B = (Batch*)batch;
-  if (!B->hs) {
-    CU(cudaStreamCreateWithFlags(&B->hs, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&B->hs2, cudaStreamNonBlocking));
-    for (int i = 0; i < kHostChunks; ++i) CU(cudaEventCreateWithFlags(&B->host_ev[i], cudaEventDisableTiming));
+  // The two streams and the chunk events are shared by all batches of a device (a fresh stream / event costs tens of
+  // microseconds on first use, which a per-batch pair would pay inside the first call on every batch); calls on one
+  // device are serialised by the pipe's mutex — they are PCIe-bound anyway.
+  if (B->device < 0 || B->device >= kMaxDevices) return fail("device index out of range");
+  HostPipe& pipe = g_host_pipe[B->device];
+  std::lock_guard<std::mutex> lock(pipe.mu);
+  if (!pipe.hs) {
+    CU(cudaStreamCreateWithFlags(&pipe.hs, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&pipe.hs2, cudaStreamNonBlocking));
+    for (int i = 0; i < kHostChunks; ++i) CU(cudaEventCreateWithFlags(&pipe.ev[i], cudaEventDisableTiming));
+  }
+  if (!B->host_ready) {
+    B->host_ready = true;
     CU(cudaMalloc((void**)&B->act_d, sizeof(int) * B->cap));
     CU(cudaMalloc((void**)&B->mask_d, sizeof(u32) * (size_t)B->info.mask_words * B->cap));
     CU(cudaMalloc((void**)&B->term_d, B->cap));
@@ -261,7 +274,7 @@ int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h,
   }
   // Chunked and double-streamed: the upload + kernel of chunk c+1 (stream hs) overlaps the download of chunk c
   // (stream hs2) — PCIe is full duplex, so the call costs about max(H2D, D2H) instead of their sum.
-  cudaStream_t st = B->hs, st2 = B->hs2;
+  cudaStream_t st = pipe.hs, st2 = pipe.hs2;
   const size_t W = (size_t)B->info.mask_words, P = (size_t)B->info.num_players, cb = B->ops->chunk_bytes();
   static const int n_chunks = [] {                 // B2S_HOST_CHUNKS=1..8 overrides the default (tuning knob)
     const char* e = getenv("B2S_HOST_CHUNKS");
@@ -280,7 +293,7 @@ int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h,
     B->ops->step_fused(v, B->act_d + lo, mask_h ? B->mask_d + lo * W : nullptr, term_h ? B->term_d + lo : nullptr,
                        rets_h ? B->rets_d + lo * P : nullptr, len, st);
     if (int r = post()) return r;
-    cudaEvent_t ev = B->host_ev[c % kHostChunks];
+    cudaEvent_t ev = pipe.ev[c % kHostChunks];
     CU(cudaEventRecord(ev, st));
     CU(cudaStreamWaitEvent(st2, ev, 0));
     if (mask_h) CU(cudaMemcpyAsync(mask_h + lo * W, B->mask_d + lo * W, sizeof(u32) * W * len, cudaMemcpyDeviceToHost, st2));

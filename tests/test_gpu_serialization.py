@@ -85,6 +85,8 @@ def test_information_state_strings_and_tabular_policy_match_the_reference():
         table = ref.table()
         assert set(pol) == set(table)
         for key, v in table.items():
-            total = sum(v["cum_policy"])
+            total = 0.0
+            for c in v["cum_policy"]:          # sequential sum as CFRAveragePolicy does (Python 3.12's sum() is compensated)
+                total += c
             want = [c / total if total > 0 else 1.0 / len(v["legal"]) for c in v["cum_policy"]]
             assert [a for a, _ in pol[key]] == v["legal"] and [p for _, p in pol[key]] == want
