@@ -77,3 +77,33 @@ def test_oracle_recorder_is_a_legal_uniform_random_episode():
             assert (tr["legal_actions"][n:] == 1).all() and not tr["observations"][n:].any()
             for t in range(n):
                 assert tr["legal_actions"][t, tr["actions"][t]] == 1
+
+
+def test_batched_trajectory_host_views_on_cpu_tensors():
+    """Host logic of open_spiel_b200.BatchedTrajectory (bit-mask expansion, [B, T] views of time-major buffers, uniform
+    player_policies) exercised on CPU tensors filled from oracle episodes."""
+    import torch
+    from open_spiel_b200.spiel import BatchedTrajectory
+    og = OracleGame("connect_four")
+    B, T, A = 16, 42, 7
+    eps = [oracle_record_trajectory(og.new_initial_state(), seed=3, lane=i, T=T) for i in range(B)]
+    legal = np.stack([e["legal_actions"] for e in eps])                       # [B, T, A]
+    words = (legal.astype(np.int64) << np.arange(A)).sum(-1).astype(np.int32)  # bit a of word 0
+    tm = {
+        "observations": None,
+        "legal_mask": torch.from_numpy(words.T.copy()).reshape(T, B, 1),
+        "actions": torch.from_numpy(np.stack([e["actions"] for e in eps]).T.astype(np.int32).copy()),
+        "player_ids": torch.from_numpy(np.stack([e["player_ids"] for e in eps]).T.astype(np.int8).copy()),
+        "valid": torch.from_numpy(np.stack([e["valid"] for e in eps]).T.astype(np.uint8).copy()),
+        "next_is_terminal": torch.from_numpy(np.stack([e["next_is_terminal"] for e in eps]).T.astype(np.uint8).copy()),
+        "rewards": torch.from_numpy(np.stack([e["rewards"] for e in eps]).astype(np.float32)),
+        "lengths": torch.tensor([e["length"] for e in eps], dtype=torch.int32),
+    }
+    tr = BatchedTrajectory(B, T, A, tm)
+    assert tr.actions.shape == (B, T) and tr.legal_mask.shape == (B, T, 1)
+    assert np.array_equal(tr.legal_actions().numpy(), legal)
+    valid = np.stack([e["valid"] for e in eps])
+    la = legal.astype(np.float64)
+    want = np.where(valid[:, :, None] == 1, la / la.sum(-1, keepdims=True), 1.0)
+    assert np.array_equal(tr.player_policies().numpy(), want)
+    assert int(tr.valid.sum()) == int(tr.lengths.sum())
