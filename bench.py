@@ -84,7 +84,11 @@ def cpu_loops():
     out = {}
     for key, argv in (("mcts_go9x9_1thread", ["mcts", "go(board_size=9)", "2000", "1", "1"]),
                       ("mcts_go9x9_16threads", ["mcts", "go(board_size=9)", "2000", "1", "16"]),
-                      ("cfr_leduc", ["cfr", "leduc_poker", "20"])):
+                      ("cfr_leduc", ["cfr", "leduc_poker", "20"]),
+                      ("mccfr_external_leduc_1thread", ["mccfr", "leduc_poker", "10000", "1"]),
+                      ("rollouts_breakthrough_1thread", ["rollout", "breakthrough", "5000", "1", "1"]),
+                      ("rollouts_breakthrough_16threads", ["rollout", "breakthrough", "5000", "1", "16"]),
+                      ("rollouts_tic_tac_toe_1thread", ["rollout", "tic_tac_toe", "100000", "1", "1"])):
         try:
             r = subprocess.run([ref] + argv, capture_output=True, text=True, timeout=300)
             out[key] = json.loads(r.stdout.strip().splitlines()[-1])

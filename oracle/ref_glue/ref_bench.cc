@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "open_spiel/algorithms/cfr.h"
+#include "open_spiel/algorithms/external_sampling_mccfr.h"
 #include "open_spiel/algorithms/mcts.h"
 #include "open_spiel/spiel.h"
 
@@ -106,7 +107,58 @@ static int BenchCfr(const std::string& game_str, int iters) {
   return 0;
 }
 
+// ref_bench rollout <game> <games> <seed> <threads>: uniform-random playouts to the end, the loop of
+// examples/benchmark_game.cc:32-115 (LegalActions + ApplyAction per ply; no observation tensor), <games> per thread.
+static int BenchRollout(const std::string& game_str, long games, int seed, int threads) {
+  auto game = open_spiel::LoadGame(game_str);
+  std::vector<double> secs(threads, 0.0);
+  std::vector<long> plies(threads, 0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t) {
+    pool.emplace_back([&, t]() {
+      std::mt19937 rng(seed + t);
+      auto t0 = std::chrono::steady_clock::now();
+      long moves = 0;
+      for (long g = 0; g < games; ++g) {
+        auto s = game->NewInitialState();
+        while (!s->IsTerminal()) {
+          auto la = s->LegalActions();
+          std::uniform_int_distribution<int> pick(0, (int)la.size() - 1);
+          s->ApplyAction(la[pick(rng)]);
+          ++moves;
+        }
+      }
+      auto t1 = std::chrono::steady_clock::now();
+      secs[t] = std::chrono::duration<double>(t1 - t0).count();
+      plies[t] = moves;
+    });
+  }
+  for (auto& th : pool) th.join();
+  double mx = 0;
+  long total_plies = 0;
+  for (int t = 0; t < threads; ++t) { mx = secs[t] > mx ? secs[t] : mx; total_plies += plies[t]; }
+  printf("{\"games_per_s\": %.6g, \"plies_per_s\": %.6g, \"seconds\": %.9g, \"threads\": %d, \"games\": %ld}\n",
+         mx > 0 ? (double)games * threads / mx : 0.0, mx > 0 ? total_plies / mx : 0.0, mx, threads, games * threads);
+  return 0;
+}
+
+// ref_bench mccfr <game> <iters> <seed>: ExternalSamplingMCCFRSolver::RunIteration, one thread (the algorithm is sequential).
+static int BenchMccfr(const std::string& game_str, int iters, int seed) {
+  auto game = open_spiel::LoadGame(game_str);
+  open_spiel::algorithms::ExternalSamplingMCCFRSolver solver(*game, seed);
+  for (int i = 0; i < 50; ++i) solver.RunIteration();
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < iters; ++i) solver.RunIteration();
+  auto t1 = std::chrono::steady_clock::now();
+  double s = std::chrono::duration<double>(t1 - t0).count();
+  printf("{\"traversals_per_s\": %.6g, \"iters_per_s\": %.6g, \"seconds\": %.9g, \"iters\": %d}\n",
+         s > 0 ? 2.0 * iters / s : 0.0, s > 0 ? iters / s : 0.0, s, iters);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 6 && !strcmp(argv[1], "rollout")) return BenchRollout(argv[2], atol(argv[3]), atoi(argv[4]), atoi(argv[5]));
+  if (argc >= 5 && !strcmp(argv[1], "mccfr")) return BenchMccfr(argv[2], atoi(argv[3]), atoi(argv[4]));
   if (argc >= 8 && !strcmp(argv[1], "apply"))
     return BenchApply(argv[2], atol(argv[3]), atoi(argv[4]), strtoul(argv[5], nullptr, 10), atoi(argv[6]), atoi(argv[7]));
   if (argc >= 6 && !strcmp(argv[1], "mcts")) return BenchMcts(argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
