@@ -170,14 +170,14 @@ int main(int argc, char** argv) {
     auto run = [&](int mode, ulonglong2* dst) {
       CK(cudaMemsetAsync(dst, 0, nb * 16, s)); CK(cudaMemsetAsync(flags, 0, 4 * grid, s)); CK(cudaStreamSynchronize(s));
       CK(cudaEventRecord(e0, s));
-      for (int e = 0; e < steps; ++e) {
+      for (int ep = 0; ep < steps; ++ep) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         if (mode == 0) CK(cudaLaunchKernelEx(&cfg, k_apply<4, 256, true>, dst, (const int*)bact, nb, err));
-        else CK(cudaLaunchKernelEx(&cfg, k_apply_tileflags<4, 256>, dst, (const int*)bact, nb, err, flags, (unsigned)e));
+        else CK(cudaLaunchKernelEx(&cfg, k_apply_tileflags<4, 256>, dst, (const int*)bact, nb, err, flags, (unsigned)ep));
       }
       CK(cudaEventRecord(e1, s)); CK(cudaStreamSynchronize(s));
       float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
