@@ -33,7 +33,7 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "playthroughs")
 TRACES = [
     "tic_tac_toe", "connect_four", "breakthrough", "hex(board_size=5)", "go",
     "kuhn_poker_2p", "leduc_poker_1540482260", "leduc_poker_3977671846",
-    "leduc_poker_773740114",
+    "leduc_poker_773740114", "kuhn_poker_3p", "leduc_poker_3p",
 ]
 
 CIRCLES = {"◯": 0.0, "◉": 1.0}
