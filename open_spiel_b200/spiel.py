@@ -621,6 +621,20 @@ class CFRSolver:
         """algorithms::Exploitability = NashConv / num_players."""
         return self.nash_conv(average) / 2.0
 
+    def current_policy(self):
+        """CFRCurrentPolicy (cfr.cc:139-165): {key bytes: [(action, prob)]} from the current-policy table."""
+        t = self.table()
+        return {t["keys"][k].tobytes(): list(zip(t["legal_actions"][t["offsets"][k]:t["offsets"][k + 1]].tolist(),
+                                                 t["cur_policy"][t["offsets"][k]:t["offsets"][k + 1]].tolist()))
+                for k in range(len(t["players"]))}
+
+    def tabular_current_policy(self):
+        """{information state string: [(action, prob)]} of the current policy."""
+        from . import serialization as ser
+        t = self.table()
+        keys = ser.table_keys(self.game._name, t)
+        return {keys[k]: v for k, v in enumerate(self.current_policy().values())}
+
     def tabular_average_policy(self):
         """pyspiel CFRSolver.tabular_average_policy (python/pybind11/policy.cc:224-245): {information state string:
         [(action, prob)]} — the keys the reference's TabularPolicy uses."""
