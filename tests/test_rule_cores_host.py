@@ -1,0 +1,248 @@
+"""CPU: the PRODUCT's rule cores (open_spiel_b200/csrc/rules_*.cuh), compiled for the host by tests/host_emul (test
+infrastructure: the library itself has no CPU path), played lock-step against the oracle: current player, terminal flag,
+returns (sign of zero included), legal-action mask, observation and information-state tensors after every move of
+random games, for every game and parameter variant the device supports.  This checks the bit-twiddling the CUDA kernels
+are built from without a GPU; launch geometry and memory staging are covered by the -m gpu tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import open_spiel_b200 as b2
+from open_spiel_b200._lib import GameInfo
+from oracle_lib import OracleGame
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul")
+
+
+def _lib():
+    so = os.path.join(HERE, "libemul.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-C", HERE], capture_output=True)
+    if not os.path.exists(so):
+        pytest.skip("host emulation library not built (needs g++ and the CUDA headers)")
+    L = C.CDLL(so)
+    L.emu_create.restype = C.c_void_p
+    L.emu_create.argtypes = [C.c_int, C.c_void_p, C.c_longlong]
+    L.emu_last_error.restype = C.c_char_p
+    for name, args in (("emu_destroy", [C.c_void_p]), ("emu_info", [C.c_void_p, C.c_void_p]),
+                       ("emu_reset", [C.c_void_p, C.c_longlong]), ("emu_apply", [C.c_void_p, C.c_void_p, C.c_longlong]),
+                       ("emu_legal_mask", [C.c_void_p, C.c_void_p, C.c_longlong]),
+                       ("emu_status", [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]),
+                       ("emu_observation", [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong])):
+        getattr(L, name).argtypes = args
+    L.emu_error_count.restype = C.c_longlong
+    L.emu_error_count.argtypes = [C.c_void_p]
+    L.emu_rollout.argtypes = [C.c_void_p, C.c_ulonglong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong]
+    L.emu_mcts.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p] + [C.c_void_p] * 5
+    return L
+
+
+class Emu:
+    def __init__(self, game_string, n):
+        self.L = _lib()
+        g = b2.load_game(game_string)                       # parameter parsing only; no device is touched
+        self.h = self.L.emu_create(g._gid, C.byref(g._cparams), n)
+        assert self.h, self.L.emu_last_error()
+        self.info = GameInfo()
+        self.L.emu_info(self.h, C.byref(self.info))
+        self.n = n
+        self.L.emu_reset(self.h, n)
+
+    def __del__(self):
+        try:
+            self.L.emu_destroy(self.h)
+        except Exception:
+            pass
+
+    def apply(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        self.L.emu_apply(self.h, a.ctypes.data, self.n)
+
+    def legal(self):
+        W = self.info.mask_words
+        out = np.zeros((self.n, W), dtype=np.uint32)
+        self.L.emu_legal_mask(self.h, out.ctypes.data, self.n)
+        width = max(self.info.num_distinct_actions, self.info.max_chance_outcomes)
+        bits = ((out[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(self.n, -1)[:, :width]
+        return [np.nonzero(r)[0].tolist() for r in bits]
+
+    def status(self):
+        cur = np.zeros(self.n, dtype=np.int8)
+        term = np.zeros(self.n, dtype=np.uint8)
+        rets = np.zeros((self.n, self.info.num_players), dtype=np.float32)
+        self.L.emu_status(self.h, cur.ctypes.data, term.ctypes.data, rets.ctypes.data, self.n)
+        return cur, term, rets
+
+    def tensor(self, player, which):
+        size = self.info.observation_tensor_size if which == 0 else self.info.information_state_tensor_size
+        out = np.zeros((self.n, size), dtype=np.float32)
+        assert self.L.emu_observation(self.h, player, which, out.ctypes.data, self.n) == 0
+        return out
+
+    def errors(self):
+        return self.L.emu_error_count(self.h)
+
+    def rollout(self, seed, lane_offset=0):
+        rets = np.zeros((self.n, self.info.num_players), dtype=np.float32)
+        plies = np.zeros(self.n, dtype=np.int32)
+        self.L.emu_rollout(self.h, seed, lane_offset, rets.ctypes.data, plies.ctypes.data, self.n)
+        return rets, plies
+
+    def mcts(self, sims, uct_c=2.0, n_rollouts=1, solve=True, seed=0, offset=0, puct=False, max_nodes=0):
+        from open_spiel_b200._lib import MctsConfig
+        A = self.info.num_distinct_actions
+        cfg = MctsConfig(sims, n_rollouts, int(solve), int(puct), uct_c, seed, offset, max_nodes or self.n * (sims * A + 2))
+        visits = np.zeros((self.n, A), dtype=np.int32)
+        reward = np.zeros((self.n, A), dtype=np.float64)
+        outcome = np.zeros((self.n, A), dtype=np.float32)
+        best = np.zeros(self.n, dtype=np.int32)
+        ran = np.zeros(self.n, dtype=np.int32)
+        rc = self.L.emu_mcts(self.h, self.n, C.byref(cfg), visits.ctypes.data, reward.ctypes.data, outcome.ctypes.data,
+                             best.ctypes.data, ran.ctypes.data)
+        assert rc == 0
+        return visits, reward, outcome, best, ran
+
+
+GAMES = [
+    ("tic_tac_toe", 64), ("connect_four", 64), ("connect_four(rows=4,columns=5,x_in_row=3)", 48),
+    ("connect_four(rows=7,columns=8,x_in_row=5)", 32), ("connect_four(egocentric_obs_tensor=True)", 32),
+    ("breakthrough", 24), ("breakthrough(rows=6,columns=6)", 32), ("breakthrough(rows=5,columns=4)", 32),
+    ("hex", 16), ("hex(board_size=5)", 48), ("hex(num_cols=3,num_rows=5)", 32), ("hex(board_size=4,swap=True)", 48),
+    ("hex(board_size=5,plain_obs_tensor=True)", 24),
+    ("go(board_size=9)", 12), ("go(board_size=5)", 32), ("go(board_size=3,komi=0.5)", 48), ("go(board_size=7,komi=4.5)", 16),
+    ("go(board_size=5,max_game_length=30)", 24),
+    ("kuhn_poker", 128), ("leduc_poker", 128), ("leduc_poker(starting_player=1)", 64),
+]
+
+
+@pytest.mark.parametrize("gs,n", GAMES, ids=[g for g, _ in GAMES])
+def test_rule_core_lockstep_vs_oracle(gs, n):
+    rng = np.random.RandomState(sum(map(ord, gs)) % 997)
+    og = OracleGame(gs)
+    emu = Emu(gs, n)
+    info = emu.info
+    assert (info.num_distinct_actions, info.max_game_length, info.num_players) == (og.num_distinct_actions, og.max_game_length,
+                                                                                  og.num_players)
+    assert info.observation_tensor_size == og.observation_tensor_size
+    has_info = og.information_state_tensor_size > 0
+    states = [og.new_initial_state() for _ in range(n)]
+    P = og.num_players
+    for ply in range(og.max_game_length + 8):
+        cur, term, rets = emu.status()
+        legal = emu.legal()
+        obs = [emu.tensor(p, 0) for p in range(P)]
+        ist = [emu.tensor(p, 1) for p in range(P)] if has_info else None
+        actions = np.full(n, -1, dtype=np.int32)
+        alive = 0
+        for i, st in enumerate(states):
+            assert int(cur[i]) == st.current_player(), (gs, i, ply)
+            assert bool(term[i]) == st.is_terminal(), (gs, i, ply)
+            ola = st.legal_actions()
+            assert legal[i] == ola, (gs, i, ply, legal[i], ola, st.to_string())
+            want = np.array(st.returns())
+            assert rets[i].tolist() == want.tolist() and np.array_equal(np.signbit(rets[i]), np.signbit(want)), (gs, i, ply)
+            for p in range(P):
+                np.testing.assert_array_equal(obs[p][i], st.observation_tensor(p), err_msg="%s lane %d ply %d" % (gs, i, ply))
+                if has_info:
+                    np.testing.assert_array_equal(ist[p][i], st.information_state_tensor(p))
+            if not st.is_terminal():
+                a = ola[rng.randint(len(ola))]
+                actions[i] = a
+                st.apply_action(a)
+                alive += 1
+        if alive == 0:
+            break
+        emu.apply(actions)
+        assert emu.errors() == 0
+    else:
+        raise AssertionError("games did not end")
+
+
+def test_rule_core_rejects_illegal_and_post_terminal_actions():
+    emu = Emu("connect_four", 4)
+    for _ in range(6):
+        emu.apply([0, -1, -1, -1])                   # fill column 0 of lane 0
+    assert emu.errors() == 0
+    before = emu.legal()
+    emu.apply([0, 9, -2, -1])                        # full column, out of range, negative: three rejected lanes
+    assert emu.errors() == 3 and emu.legal() == before
+    ttt = Emu("tic_tac_toe", 1)
+    for a in (0, 3, 1, 4, 2):                        # x wins on the top row
+        ttt.apply([a])
+    assert ttt.status()[1][0] == 1 and ttt.errors() == 0
+    ttt.apply([5])                                   # acting on a terminal state is rejected, state unchanged
+    assert ttt.errors() == 1 and ttt.status()[2][0].tolist() == [1.0, -1.0]
+
+
+@pytest.mark.parametrize("gs", ["connect_four", "tic_tac_toe", "breakthrough", "breakthrough(rows=6,columns=6)", "hex(board_size=5)",
+                                "go(board_size=5)", "go(board_size=9)", "kuhn_poker", "leduc_poker"])
+def test_playout_step_matches_oracle_given_same_random_stream(gs):
+    """common.cuh playout_step (legal-mask draw; candidate rejection sampling for go and breakthrough) on the host vs the
+    oracle replaying the same Philox words — the CPU twin of the GPU test of b2s_rollout."""
+    from philox_ref import philox_uniform
+    n = 24 if "9" in gs else 64
+    emu = Emu(gs, n)
+    rets, plies = emu.rollout(0x5EED, 1000)
+    og = OracleGame(gs)
+    for i in range(n):
+        st = og.new_initial_state()
+        ply = 0
+        while not st.is_terminal():
+            la, cand = st.legal_actions(), st.rollout_candidates()
+            retry = 0
+            while True:
+                a = cand[philox_uniform(0x5EED, 1000 + i, ply + 4096 * retry, len(cand))]
+                if a in la:
+                    break
+                retry += 1
+            st.apply_action(a)
+            ply += 1
+        assert ply == plies[i] and st.returns() == rets[i].tolist(), (gs, i)
+    assert emu.status()[1].all()
+
+
+MCTS_CASES = [("tic_tac_toe", 16, 3, 300, 2, True, False), ("connect_four", 12, 8, 200, 1, True, False),
+              ("connect_four(rows=4,columns=5,x_in_row=3)", 12, 5, 300, 1, True, True),
+              ("breakthrough(rows=6,columns=6)", 8, 8, 100, 1, True, False), ("hex(board_size=5)", 12, 6, 150, 1, True, False),
+              ("hex(board_size=4,swap=True)", 8, 2, 150, 1, True, True), ("go(board_size=5)", 12, 8, 100, 1, True, False),
+              ("go(board_size=9)", 6, 20, 30, 1, True, False)]
+
+
+@pytest.mark.parametrize("gs,n,prefix,sims,nroll,solve,puct", MCTS_CASES, ids=["%s-%d" % (c[0], c[3]) for c in MCTS_CASES])
+def test_mcts_kernel_body_on_host_equals_oracle(gs, n, prefix, sims, nroll, solve, puct):
+    """The body of the k_mcts kernel (mcts.cuh), executed on the host one tree at a time, vs the oracle's MCTS on the same
+    Philox stream: visit counts, total rewards (exact doubles), proven outcomes, BestChild, simulations run."""
+    import math
+    from oracle_lib import oracle_mcts
+    rng = np.random.RandomState(len(gs) + sims)
+    og = OracleGame(gs)
+    emu = Emu(gs, n)
+    states = [og.new_initial_state() for _ in range(n)]
+    ks = rng.randint(0, prefix + 1, size=n)
+    for t in range(prefix):
+        acts = np.full(n, -1, dtype=np.int32)
+        for i, st in enumerate(states):
+            if t < ks[i] and not st.is_terminal():
+                la = st.legal_actions()
+                a = la[rng.randint(len(la))]
+                nxt = st.clone()
+                nxt.apply_action(a)
+                if nxt.is_terminal():
+                    continue
+                states[i] = nxt
+                acts[i] = a
+        emu.apply(acts)
+    assert emu.errors() == 0
+    visits, reward, outcome, best, ran = emu.mcts(sims, 2.0, nroll, solve, seed=0xC0FFEE, offset=17, puct=puct)
+    assert emu.errors() == 0
+    for i, st in enumerate(states):
+        o = oracle_mcts(st, 2.0, sims, nroll, solve, 0xC0FFEE, tree_index=i + 17, puct=puct)
+        assert ran[i] == o["sims_run"], (gs, i)
+        for a, v, r, oc in o["children"]:
+            assert visits[i, a] == v and reward[i, a] == r, (gs, i, a)
+            assert (math.isnan(oc) and math.isnan(outcome[i, a])) or outcome[i, a] == oc, (gs, i, a)
+        assert int(visits[i].sum()) == sum(v for _, v, _, _ in o["children"])
+        assert best[i] == o["best_action"], (gs, i)
