@@ -184,6 +184,15 @@ struct EmuT : Emu {
     std::vector<u64> whist(info.history_bytes ? (size_t)info.history_bytes / sizeof(u64) * (size_t)n : 0, 0);
     Ctx work;
     work.planes = wplanes.data(); work.cap = n; work.hist = whist.empty() ? nullptr : whist.data(); work.err = &err;
+    {                                                       // api.cu: B->ops->copy(work, 0, roots, 0, n) — k_copy
+      Ctx src = ctx();
+      for (long long i = 0; i < n; ++i) {
+        typename R::S s;
+        R::load(s, src, i);
+        R::store(s, work, i);
+        R::copy_history(work, i, src, i, s, cfg);
+      }
+    }
     std::vector<double> logt((size_t)mc.max_simulations + 2, 0.0);
     for (size_t k = 1; k < logt.size(); ++k) logt[k] = std::log((double)k);
     unsigned long long cap_nodes = mc.max_nodes_total > 0 ? (unsigned long long)mc.max_nodes_total

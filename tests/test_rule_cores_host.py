@@ -208,7 +208,10 @@ MCTS_CASES = [("tic_tac_toe", 16, 3, 300, 2, True, False), ("connect_four", 12, 
               ("connect_four(rows=4,columns=5,x_in_row=3)", 12, 5, 300, 1, True, True),
               ("breakthrough(rows=6,columns=6)", 8, 8, 100, 1, True, False), ("hex(board_size=5)", 12, 6, 150, 1, True, False),
               ("hex(board_size=4,swap=True)", 8, 2, 150, 1, True, True), ("go(board_size=5)", 12, 8, 100, 1, True, False),
-              ("go(board_size=9)", 6, 20, 30, 1, True, False)]
+              ("go(board_size=9)", 6, 20, 30, 1, True, False),
+              # tiny boards: positional superko decides playouts, so the root's hash history must reach the work lanes
+              ("go(board_size=2)", 6, 5, 80, 2, False, True), ("go(board_size=3)", 6, 5, 80, 2, False, True),
+              ("go(board_size=2)", 6, 12, 60, 1, True, True)]
 
 
 @pytest.mark.parametrize("gs,n,prefix,sims,nroll,solve,puct", MCTS_CASES, ids=["%s-%d" % (c[0], c[3]) for c in MCTS_CASES])
