@@ -37,6 +37,8 @@ struct HexRules {
     if (c.cols < 2 || c.rows < 1) return "hex: board too small";
     if (c.cols * c.rows > 121 || c.cols > 63) return "hex: at most 121 cells on the device path";
     if (c.plain && c.cols < c.rows) return "hex: plain_obs_tensor with num_cols < num_rows is not supported (the reference indexes out of its plane)";
+    if (c.swap && c.cols > c.rows)
+      return "hex: swap with num_cols > num_rows is not supported (the reference mirrors the first stone outside the board, hex.cc:238)";
     c.cells = c.cols * c.rows;
     B128 z = {0, 0};
     c.board = c.not_west = c.not_east = c.row_first = c.row_last = c.col_first = c.col_last = z;

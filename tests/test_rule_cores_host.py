@@ -277,6 +277,9 @@ def test_hex_swap_on_wide_boards_is_reference_undefined_behaviour():
     """hex.cc:238 mirrors the first stone to cell c * num_cols + r without a bounds check: with more columns than rows that
     index can lie outside the board (undefined behaviour in the reference).  The oracle reports it as an error instead of
     writing out of bounds; parity is only defined — and checked above — for swap with rows >= cols."""
+    with pytest.raises(b2.SpielError):                  # the device path refuses the configuration outright
+        b2.load_game("hex(num_rows=2,num_cols=3,swap=True)")
+    b2.load_game("hex(num_rows=3,num_cols=2,swap=True)")  # rows >= cols is well defined and supported
     st = OracleGame("hex(num_rows=2,num_cols=3,swap=True)").new_initial_state()
     st.apply_action(5)                                   # r = 1, c = 2 -> mirrored cell 2 * 3 + 1 = 7 >= 6
     with pytest.raises(RuntimeError):
