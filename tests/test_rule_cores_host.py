@@ -120,8 +120,22 @@ GAMES = [
 
 @pytest.mark.parametrize("gs,n", GAMES, ids=[g for g, _ in GAMES])
 def test_rule_core_lockstep_vs_oracle(gs, n):
+    _lockstep(gs, n, OracleGame)
+
+
+@pytest.mark.parametrize("gs,n", [(g, max(8, k // 3)) for g, k in GAMES], ids=[g for g, _ in GAMES])
+def test_rule_core_lockstep_vs_unmodified_reference(gs, n):
+    """The same lock-step play with the UNMODIFIED reference (oracle/_ref) as the checker: the code the CUDA kernels are
+    built from against open_spiel's own State classes, in the CPU suite."""
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not built")
+    _lockstep(gs, n, ref_lib.RefGame)
+
+
+def _lockstep(gs, n, checker):
     rng = np.random.RandomState(sum(map(ord, gs)) % 997)
-    og = OracleGame(gs)
+    og = checker(gs)
     emu = Emu(gs, n)
     info = emu.info
     assert (info.num_distinct_actions, info.max_game_length, info.num_players) == (og.num_distinct_actions, og.max_game_length,
