@@ -133,6 +133,20 @@ int b2s_step_fused(void* batch, const int32_t* actions_d, uint32_t* mask_words_d
  * loop such as python/rl_environment.py:337-431) uses. */
 int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_words_h, uint8_t* terminal_h,
                         float* returns_h, int64_t n);
+/* The same env step with byte-wide I/O, for host-driven loops where PCIe bytes per lane are the cost (win / loss / draw
+ * games: tic_tac_toe, connect_four, breakthrough, hex, go).  actions_h: action_bytes = 1 -> uint8 per lane, 0xFF = leave
+ * the lane untouched; action_bytes = 4 -> int32, -1 = untouched.  status_h: one byte per lane,
+ *   bit 7      IsTerminal (spiel.h:447)
+ *   terminal:  bits 0-1 = outcome: 0 draw (Returns {0,0}), 1 player 0 won ({+1,-1}), 2 player 1 won ({-1,+1})
+ *   otherwise: bits 0-6 = the next LegalActionsMask when num_distinct_actions <= 7 (connect_four up to 7 columns), else 0
+ * mask_words_h (nullable): the full mask words as b2s_step_fused_host writes them, for games with more actions.
+ * Same information as b2s_step_fused_host (the sign of a zero return is not carried), 2 B instead of 17 B per
+ * connect_four lane.  Ordering of both *_host entry points: they run on library-owned BLOCKING streams, i.e. after work
+ * already enqueued on the legacy default stream (stream = NULL) for this device and before later NULL-stream work; work the
+ * caller has in flight on other streams must be synchronised by the caller first.  Both return after the results are in
+ * the host buffers. */
+int b2s_step_fused_host_compact(void* batch, const void* actions_h, int action_bytes, uint8_t* status_h,
+                                uint32_t* mask_words_h, int64_t n);
 
 /* Number of lanes whose action was rejected since the last b2s_reset (synchronises the stream);
  * first_bad_lane (nullable) receives the lowest-numbered such lane seen first, or -1. */
@@ -301,6 +315,10 @@ int  b2s_memcpy_h2d(int device, void* dst_d, const void* src_h, size_t bytes, vo
 int  b2s_memcpy_d2h(int device, void* dst_h, const void* src_d, size_t bytes, void* stream);
 int  b2s_stream_synchronize(int device, void* stream);
 int  b2s_device_count(void);
+/* Pins the calling thread to the CPUs local to `device` (sysfs local_cpulist of its PCI function), so that pinned
+ * buffers it allocates afterwards (b2s_host_alloc, first touch) and its copy submissions stay on the GPU's NUMA node.
+ * n_cpus (nullable) receives the size of that CPU set. */
+int  b2s_bind_host_to_device(int device, int* n_cpus);
 
 /* Launch accounting: number of kernels this library has launched in this process. */
 int64_t b2s_launch_count(void);

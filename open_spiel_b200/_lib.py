@@ -74,6 +74,8 @@ SIGNATURES = {
     "b2s_information_state": (C.c_int, [_VP, C.c_int, _VP, _I64, _VP]),
     "b2s_step_fused": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _VP]),
     "b2s_step_fused_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64]),
+    "b2s_step_fused_host_compact": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP, _I64]),
+    "b2s_bind_host_to_device": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "b2s_error_count": (C.c_int, [_VP, C.POINTER(_I64), C.POINTER(_I64), _VP]),
     "b2s_state_get": (C.c_int, [_VP, _I64, _VP, C.c_size_t]),
     "b2s_state_set": (C.c_int, [_VP, _I64, _VP, C.c_size_t]),

@@ -1,6 +1,9 @@
 // extern "C" layer (include/b2s.h) over the per-game kernel tables.  Host logic only: argument checks,
 // buffer ownership, stream plumbing.  No CPU fallback anywhere: without a CUDA device every call fails.
+#include <ctype.h>
 #include <math.h>
+#include <sched.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -129,6 +132,34 @@ int b2s_game_info_get(int game_id, const b2s_params* params, b2s_game_info* out)
   return 0;
 }
 
+// Pin the calling thread (and, by first touch, the pinned buffers it allocates afterwards) to the CPUs of the NUMA node
+// the GPU hangs off: /sys/bus/pci/devices/<bus id>/local_cpulist.  Returns 0 and the number of CPUs in *n_cpus.
+int b2s_bind_host_to_device(int device, int* n_cpus) {
+  char bus[32] = {0};
+  CU(cudaDeviceGetPCIBusId(bus, sizeof bus, device));
+  for (char* q = bus; *q; ++q) *q = (char)tolower(*q);
+  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return fail("bind: cannot read " + path);
+  char line[4096] = {0};
+  if (!fgets(line, sizeof line, f)) { fclose(f); return fail("bind: empty " + path); }
+  fclose(f);
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int count = 0;
+  for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k == 1) b = a;
+    if (k < 1) continue;
+    for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; ++cpu) { CPU_SET(cpu, &set); ++count; }
+  }
+  if (count == 0) return fail("bind: no CPUs listed in " + path);
+  if (sched_setaffinity(0, sizeof set, &set) != 0) return fail("bind: sched_setaffinity failed");
+  if (n_cpus) *n_cpus = count;
+  return 0;
+}
+
 int b2s_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -226,6 +257,7 @@ int b2s_observation(void* batch, int player, float* obs_d, int64_t n, void* stre
   if (int r = check(batch, n)) return r;
   Batch* B = (Batch*)batch;
   if (!obs_d) return fail("null obs");
+  if ((uintptr_t)obs_d & 3u) return fail("observation: output pointer must be 4-byte aligned");
   if (player >= B->info.num_players) return fail("player out of range");
   const char* e = B->ops->obs(B->ctx(), player, 0, 0, obs_d, n, (cudaStream_t)stream);
   if (e) return fail(e);
@@ -236,6 +268,7 @@ int b2s_information_state(void* batch, int player, float* out_d, int64_t n, void
   if (int r = check(batch, n)) return r;
   Batch* B = (Batch*)batch;
   if (!out_d) return fail("null out");
+  if ((uintptr_t)out_d & 3u) return fail("information_state: output pointer must be 4-byte aligned");
   if (player >= B->info.num_players) return fail("player out of range");
   const char* e = B->ops->obs(B->ctx(), player, 1, 0, out_d, n, (cudaStream_t)stream);
   if (e) return fail(e);
@@ -250,10 +283,10 @@ int b2s_step_fused(void* batch, const int32_t* actions_d, uint32_t* mask_d, uint
   return post();
 }
 
-int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h, uint8_t* term_h, float* rets_h, int64_t n) {
-  if (int r = check(batch, n)) return r;
-  if (!actions_h) return fail("null actions");
-  Batch* B = (Batch*)batch;
+// Shared body of the *_host step entry points.  compact = 0: int32 actions in, mask words / terminal / float returns out
+// (b2s_step_fused_host); compact = 1: `action_bytes`-wide actions in, one status byte (+ optional mask words) out.
+static int step_host_impl(Batch* B, const void* actions_h, int action_bytes, uint32_t* mask_h, uint8_t* term_or_status_h,
+                          float* rets_h, int64_t n, int compact) {
   // The two streams and the chunk events are shared by all batches of a device (a fresh stream / event costs tens of
   // microseconds on first use, which a per-batch pair would pay inside the first call on every batch); calls on one
   // device are serialised by the pipe's mutex — they are PCIe-bound anyway.
@@ -261,16 +294,19 @@ int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h,
   HostPipe& pipe = g_host_pipe[B->device];
   std::lock_guard<std::mutex> lock(pipe.mu);
   if (!pipe.hs) {
-    CU(cudaStreamCreateWithFlags(&pipe.hs, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&pipe.hs2, cudaStreamNonBlocking));
+    // BLOCKING streams (cudaStreamDefault): they are implicitly ordered after work already enqueued on the legacy default
+    // stream (NULL) — e.g. a b2s_reset / b2s_apply_actions(…, NULL) issued just before — and later NULL-stream work is
+    // ordered after them.  Work the caller enqueued on OTHER streams must be synchronised by the caller (b2s.h).
+    CU(cudaStreamCreateWithFlags(&pipe.hs, cudaStreamDefault));
+    CU(cudaStreamCreateWithFlags(&pipe.hs2, cudaStreamDefault));
     for (int i = 0; i < kHostChunks; ++i) CU(cudaEventCreateWithFlags(&pipe.ev[i], cudaEventDisableTiming));
   }
   if (!B->host_ready) {
-    B->host_ready = true;
     CU(cudaMalloc((void**)&B->act_d, sizeof(int) * B->cap));
     CU(cudaMalloc((void**)&B->mask_d, sizeof(u32) * (size_t)B->info.mask_words * B->cap));
     CU(cudaMalloc((void**)&B->term_d, B->cap));
     CU(cudaMalloc((void**)&B->rets_d, sizeof(float) * (size_t)B->info.num_players * B->cap));
+    B->host_ready = true;                        // only once every staging buffer exists
   }
   // Chunked and double-streamed: the upload + kernel of chunk c+1 (stream hs) overlaps the download of chunk c
   // (stream hs2) — PCIe is full duplex, so the call costs about max(H2D, D2H) instead of their sum.
@@ -282,27 +318,52 @@ int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h,
     return v < 1 ? 1 : (v > kHostChunks ? kHostChunks : v);
   }();
   const int64_t chunk = (n >= (1 << 18) && n_chunks > 1) ? ((n + n_chunks - 1) / n_chunks + 1023) / 1024 * 1024 : n;
-  int c = 0;
-  for (int64_t lo = 0; lo < n; lo += chunk, ++c) {
+  const size_t ab = (size_t)action_bytes;
+  int c = 0, rc = 0;
+  for (int64_t lo = 0; lo < n && !rc; lo += chunk, ++c) {
     const int64_t len = n - lo < chunk ? n - lo : chunk;
     Ctx v = B->ctx();
     v.planes = (char*)v.planes + (size_t)lo * cb;
     if (v.hist) v.hist += lo;
     v.lane0 = lo;
-    CU(cudaMemcpyAsync(B->act_d + lo, actions_h + lo, sizeof(int) * len, cudaMemcpyHostToDevice, st));
-    B->ops->step_fused(v, B->act_d + lo, mask_h ? B->mask_d + lo * W : nullptr, term_h ? B->term_d + lo : nullptr,
-                       rets_h ? B->rets_d + lo * P : nullptr, len, st);
-    if (int r = post()) return r;
+    char* act_d = (char*)B->act_d + (size_t)lo * ab;
+    cudaError_t e = cudaMemcpyAsync(act_d, (const char*)actions_h + (size_t)lo * ab, ab * len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "step_host: upload"); break; }
+    if (compact)
+      B->ops->step_compact(v, act_d, action_bytes, B->term_d + lo, mask_h ? B->mask_d + lo * W : nullptr, len, st);
+    else
+      B->ops->step_fused(v, (const int*)act_d, mask_h ? B->mask_d + lo * W : nullptr, term_or_status_h ? B->term_d + lo : nullptr,
+                         rets_h ? B->rets_d + lo * P : nullptr, len, st);
+    if ((rc = post())) break;
     cudaEvent_t ev = pipe.ev[c % kHostChunks];
-    CU(cudaEventRecord(ev, st));
-    CU(cudaStreamWaitEvent(st2, ev, 0));
-    if (mask_h) CU(cudaMemcpyAsync(mask_h + lo * W, B->mask_d + lo * W, sizeof(u32) * W * len, cudaMemcpyDeviceToHost, st2));
-    if (term_h) CU(cudaMemcpyAsync(term_h + lo, B->term_d + lo, len, cudaMemcpyDeviceToHost, st2));
-    if (rets_h) CU(cudaMemcpyAsync(rets_h + lo * P, B->rets_d + lo * P, sizeof(float) * P * len, cudaMemcpyDeviceToHost, st2));
+    if ((e = cudaEventRecord(ev, st)) != cudaSuccess || (e = cudaStreamWaitEvent(st2, ev, 0)) != cudaSuccess) { rc = cuda_fail(e, "step_host: event"); break; }
+    if (mask_h && (e = cudaMemcpyAsync(mask_h + lo * W, B->mask_d + lo * W, sizeof(u32) * W * len, cudaMemcpyDeviceToHost, st2)) != cudaSuccess) { rc = cuda_fail(e, "step_host: download"); break; }
+    if (term_or_status_h && (e = cudaMemcpyAsync(term_or_status_h + lo, B->term_d + lo, len, cudaMemcpyDeviceToHost, st2)) != cudaSuccess) { rc = cuda_fail(e, "step_host: download"); break; }
+    if (rets_h && (e = cudaMemcpyAsync(rets_h + lo * P, B->rets_d + lo * P, sizeof(float) * P * len, cudaMemcpyDeviceToHost, st2)) != cudaSuccess) { rc = cuda_fail(e, "step_host: download"); break; }
   }
-  CU(cudaStreamSynchronize(st));
-  CU(cudaStreamSynchronize(st2));
+  // always drain both streams, error or not: no copy into a caller's host buffer may stay in flight after the call
+  cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(st2);
+  if (rc) return rc;
+  if (e1 != cudaSuccess) return cuda_fail(e1, "step_host: synchronize");
+  if (e2 != cudaSuccess) return cuda_fail(e2, "step_host: synchronize");
   return 0;
+}
+
+int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_h, uint8_t* term_h, float* rets_h, int64_t n) {
+  if (int r = check(batch, n)) return r;
+  if (!actions_h) return fail("null actions");
+  return step_host_impl((Batch*)batch, actions_h, 4, mask_h, term_h, rets_h, n, 0);
+}
+
+int b2s_step_fused_host_compact(void* batch, const void* actions_h, int action_bytes, uint8_t* status_h, uint32_t* mask_h, int64_t n) {
+  if (int r = check(batch, n)) return r;
+  if (!actions_h || !status_h) return fail("null actions / status");
+  Batch* B = (Batch*)batch;
+  if (action_bytes != 1 && action_bytes != 4) return fail("step_compact: action_bytes must be 1 (uint8, 0xFF = skip) or 4 (int32, -1 = skip)");
+  if (action_bytes == 1 && B->info.num_distinct_actions > 255) return fail("step_compact: uint8 actions need num_distinct_actions <= 255");
+  if (B->info.min_utility != -1.0 || B->info.max_utility != 1.0 || B->info.max_chance_outcomes > 0)
+    return fail("step_compact: the 2-bit outcome code needs a win / loss / draw game (use b2s_step_fused_host)");
+  return step_host_impl(B, actions_h, action_bytes, mask_h, status_h, nullptr, n, 1);
 }
 
 int b2s_error_count(void* batch, int64_t* count, int64_t* first_bad_lane, void* stream) {

@@ -180,6 +180,59 @@ __global__ void __launch_bounds__(kBlock) k_step_fused(Ctx ctx, typename R::Cfg 
   }
 }
 
+// Compact env step for host-driven loops (b2s_step_fused_host_compact): the same apply -> terminal -> returns -> next legal
+// mask pass as k_step_fused with byte-wide I/O, because through PCIe the bytes per lane ARE the cost.  Actions are AT
+// (unsigned char: 0xFF = leave the lane untouched; int: -1).  One status byte per lane:
+//   bit 7      IsTerminal
+//   terminal:  bits 0-1 = outcome (0 draw / no winner, 1 player 0 won, 2 player 1 won) — win/loss/draw games only
+//   otherwise: bits 0-6 = LegalActionsMask when the game has <= 7 distinct actions (connect_four <= 7 columns), else 0
+// Games with more actions get their mask words through `mask` (nullable), exactly as k_step_fused writes them.
+template <class R, int ILP, class AT>
+__global__ void __launch_bounds__(kBlock) k_step_compact(Ctx ctx, typename R::Cfg cfg, const AT* __restrict__ actions, unsigned char* __restrict__ status,
+                                                         u32* __restrict__ mask, int mask_words, int small_mask, long long n) {
+  pdl_wait();
+  long long base = (long long)blockIdx.x * (kBlock * ILP) + threadIdx.x;
+  int a[ILP];
+  typename R::S s[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    a[j] = -1;
+    if (i < n) {
+      AT raw = __ldg(actions + i);
+      a[j] = (sizeof(AT) == 1 && (unsigned char)raw == 0xFFu) ? -1 : (int)raw;
+      R::load(s[j], ctx, i);
+    }
+  }
+  pdl_launch_dependents();
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    if (i >= n) continue;
+    if (a[j] != -1) {
+      if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) flag_error(ctx.err, ctx.lane0 + i);
+      else R::store(s[j], ctx, i);
+    }
+    bool t = R::terminal(s[j], cfg);
+    u32 m[R::kMaskWords];
+    unsigned st = 0;
+    if (t) {
+      float r[R::kPlayers];
+      R::returns(s[j], cfg, r);
+      st = 0x80u | (r[0] > 0.f ? 1u : (r[0] < 0.f ? 2u : 0u));
+      for (int w = 0; w < R::kMaskWords; ++w) m[w] = 0;
+    } else if (small_mask || mask) {
+      R::legal_nonterminal(s[j], cfg, m);
+      if (small_mask) st = m[0] & 0x7Fu;
+    }
+    status[i] = (unsigned char)st;
+    if (mask) {
+      if (R::kMaskWords == 1) mask[i] = m[0];
+      else for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+    }
+  }
+}
+
 // R::kObsBitPacked (optional): ObsPack is the tensor as a flat little-endian bit string in output order
 template <class R> constexpr auto obs_bitpacked(int) -> decltype(R::kObsBitPacked) { return R::kObsBitPacked; }
 template <class R> constexpr bool obs_bitpacked(long) { return false; }
@@ -206,12 +259,22 @@ __global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, in
   if (tile0 >= n) return;
   int lanes_here = (int)((n - tile0) < 32 ? (n - tile0) : 32);
   int total = lanes_here * size;                                       // floats in this tile
-  float* base = out + tile0 * size;                                    // 16B aligned: 32*size*4 % 16 == 0
+  float* base = out + tile0 * size;
+  // The tile is emitted as 16-byte stores, so the vector part must start on a 16-byte boundary.  tile0 * size * 4 is a
+  // multiple of 16 (tile0 is a multiple of 32), but `out` itself need not be (a caller pointer, or row t of the
+  // trajectory recorder at offset t*n*F floats): the first `peel` floats of the tile are written as scalars.
+  const int peel = (int)(((16u - (unsigned)((unsigned long long)base & 15ull)) & 15u) >> 2);
   const typename R::ObsPack* wp = packs + warp * 32;
   const unsigned char* dead = dead_flags + warp * 32;
-  int nvec = total >> 2;
+  const int head = peel < total ? peel : total;
+  if (lane < head) {
+    int st = (int)(((u64)lane * magic) >> 32);
+    base[lane] = (zero_terminal && dead[st]) ? 0.f : R::obs_elem(wp[st], cfg, lane - st * size);
+  }
+  int nvec = (total - head) >> 2;
+  float4* vbase = reinterpret_cast<float4*>(base + head);
   for (int q = lane; q < nvec; q += 32) {
-    int e0 = q << 2;
+    int e0 = head + (q << 2);
     int st = (int)(((u64)e0 * magic) >> 32);         // e0 / size (magic verified on the host for the range)
     int within = e0 - st * size;
     float v[4];
@@ -230,9 +293,9 @@ __global__ void __launch_bounds__(kBlock) k_obs(Ctx ctx, typename R::Cfg cfg, in
         if (++within == size) { within = 0; ++st; }     // a float4 may straddle two lanes' tensors
       }
     }
-    reinterpret_cast<float4*>(base)[q] = make_float4(v[0], v[1], v[2], v[3]);
+    vbase[q] = make_float4(v[0], v[1], v[2], v[3]);
   }
-  for (int e = (nvec << 2) + lane; e < total; e += 32) {               // ragged tail of the last tile
+  for (int e = head + (nvec << 2) + lane; e < total; e += 32) {        // ragged tail of the last tile
     int st = (int)(((u64)e * magic) >> 32);
     base[e] = (zero_terminal && dead[st]) ? 0.f : R::obs_elem(wp[st], cfg, e - st * size);
   }
@@ -415,6 +478,7 @@ struct GameOps {
   virtual void status(const Ctx&, signed char* cur, unsigned char* term, float* rets, long long n, cudaStream_t) = 0;
   virtual const char* obs(const Ctx&, int player, int which, int zero_terminal, float* out, long long n, cudaStream_t) = 0;
   virtual void step_fused(const Ctx&, const int* a, u32* m, unsigned char* term, float* rets, long long n, cudaStream_t) = 0;
+  virtual void step_compact(const Ctx&, const void* a, int action_bytes, unsigned char* status, u32* m, long long n, cudaStream_t) = 0;
   virtual void rollout(const Ctx&, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t) = 0;
   virtual void broadcast(const Ctx& dst, long long dst0, long long count, const Ctx& src, long long srclane, cudaStream_t) = 0;
   virtual void copy(const Ctx& dst, long long dst0, const Ctx& src, long long src0, long long count, cudaStream_t) = 0;
@@ -489,6 +553,15 @@ struct GameOpsT : GameOps {
   void step_fused(const Ctx& c, const int* a, u32* m, unsigned char* term, float* rets, long long n, cudaStream_t st) override {
     if (n <= 0) return;
     launch_pdl(k_step_fused<R, R::kIlp>, grid_for(n, R::kIlp), st, c, cfg, a, m, info.mask_words, term, rets, n); ++g_launches;
+  }
+  void step_compact(const Ctx& c, const void* a, int action_bytes, unsigned char* status, u32* m, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    const int small_mask = info.num_distinct_actions <= 7 ? 1 : 0;
+    if (action_bytes == 1)
+      launch_pdl(k_step_compact<R, R::kIlp, unsigned char>, grid_for(n, R::kIlp), st, c, cfg, (const unsigned char*)a, status, m, info.mask_words, small_mask, n);
+    else
+      launch_pdl(k_step_compact<R, R::kIlp, int>, grid_for(n, R::kIlp), st, c, cfg, (const int*)a, status, m, info.mask_words, small_mask, n);
+    ++g_launches;
   }
   void rollout(const Ctx& c, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t st) override {
     if (n <= 0) return;

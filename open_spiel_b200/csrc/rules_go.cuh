@@ -68,7 +68,8 @@ struct GoRules {
     gi.max_game_length = c.max_len;
     gi.observation_tensor_size = 4 * c.cells;                    // go.h:175-179
     gi.obs_shape[0] = 4; gi.obs_shape[1] = c.n; gi.obs_shape[2] = c.n;
-    gi.history_bytes = 8 * (c.max_len + 1);
+    // a game is never terminal before ply 2 (go.cc:225-230), so max_game_length 0 / 1 still plays two moves
+    gi.history_bytes = 8 * ((c.max_len > 2 ? c.max_len : 2) + 1);
     gi.min_utility = -1; gi.max_utility = 1;
     return nullptr;
   }

@@ -18,36 +18,9 @@
 #include <type_traits>
 #include <vector>
 
-static inline int __popc(unsigned x) { return __builtin_popcount(x); }
-static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
-static inline int __ffs(int x) { return __builtin_ffs(x); }
-static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
-// __fns(mask, base, offset > 0): position of the offset-th set bit of mask counting upwards from bit `base`
-static inline unsigned __fns(unsigned mask, unsigned base, int offset) {
-  for (unsigned b = base; b < 32; ++b)
-    if ((mask >> b) & 1u) { if (--offset == 0) return b; }
-  return 0xffffffffu;
-}
-static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
-  unsigned long long v = ((unsigned long long)hi << 32) | lo;
-  return (unsigned)(v >> (sh & 31));
-}
-template <typename T> static inline T __ldg(const T* p) { return *p; }
-static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
-static inline long long atomicMin(long long* p, long long v) { long long o = *p; if (v < o) *p = v; return o; }
-// explicitly rounded FP64 operations (x86-64 g++ does not contract a*b+c into an FMA at -O2 without -ffast-math / -march flags)
-static inline double __dadd_rn(double a, double b) { return a + b; }
-static inline double __dsub_rn(double a, double b) { return a - b; }
-static inline double __dmul_rn(double a, double b) { return a * b; }
-static inline double __ddiv_rn(double a, double b) { return a / b; }
-static inline double __dsqrt_rn(double a) { return __builtin_sqrt(a); }
-static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
-static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
-#define __launch_bounds__(...)
+#include "../../open_spiel_b200/csrc/host_compat.h"   // host definitions of the device intrinsics (product header)
 // one "thread" at a time: the kernels index with blockIdx.x * blockDim.x + threadIdx.x
 static struct { unsigned x, y, z; } blockIdx, blockDim = {1, 1, 1}, threadIdx;
-// GoRules::device_init uploads its Zobrist table with cudaMemcpyToSymbol; on the host the "symbol" is a plain array
-#define cudaMemcpyToSymbol(sym, src, size) (memcpy((void*)&(sym), (src), (size)), cudaSuccess)
 
 #include "../../open_spiel_b200/csrc/common.cuh"
 #include "../../open_spiel_b200/csrc/rules_tic_tac_toe.cuh"
