@@ -1,6 +1,7 @@
-// Runs the REFERENCE'S OWN test harness (open_spiel/tests/basic_tests.cc: RandomSimTest — legal actions sorted,
-// clone equality, serialization round trip, tensor sizes, returns bounds, game length, ...) on the B200 adapter
-// games obtained through open_spiel::LoadGame, then plays the stock C++ game and the adapter in lock-step.
+// GPU half of the adapter tests (the CPU half — the reference's RandomSimTest harness and lock-step against the stock
+// games — is adapter_host_test.cc): the device MCTS / CFR behind the reference's Bot / solver interfaces, driven by the
+// reference's own EvaluateBots / Exploitability, and the packed-lane bridge between scalar states and device batches.
+#include <cstring>
 #include <iostream>
 #include <random>
 
@@ -16,28 +17,6 @@
 #include "open_spiel/tests/basic_tests.h"
 
 using namespace open_spiel;
-
-static void LockStep(const Game& ours, const Game& stock, int games, std::mt19937* rng) {
-  for (int g = 0; g < games; ++g) {
-    auto a = ours.NewInitialState();
-    auto b = stock.NewInitialState();
-    while (true) {
-      SPIEL_CHECK_EQ(a->IsTerminal(), b->IsTerminal());
-      SPIEL_CHECK_EQ(a->CurrentPlayer(), b->CurrentPlayer());
-      SPIEL_CHECK_TRUE(a->LegalActions() == b->LegalActions());
-      SPIEL_CHECK_TRUE(a->Returns() == b->Returns());
-      SPIEL_CHECK_EQ(a->ToString(), b->ToString());
-      for (Player p = 0; p < 2; ++p) SPIEL_CHECK_TRUE(a->ObservationTensor(p) == b->ObservationTensor(p));
-      if (a->IsTerminal()) break;
-      auto la = b->LegalActions();
-      Action act = la[(*rng)() % la.size()];
-      SPIEL_CHECK_EQ(a->ActionToString(act), b->ActionToString(act));
-      a->ApplyAction(act);
-      b->ApplyAction(act);
-    }
-    SPIEL_CHECK_TRUE(a->History() == b->History());
-  }
-}
 
 // The reference's own self-play driver (algorithms/evaluate_bots.cc:28-66) with the device MCTS plugged in as a Bot.
 static void BotTests(const Game& stock_c4, const Game& stock_ttt) {
@@ -100,29 +79,116 @@ static void CfrTests() {
   }
 }
 
+// A scalar B200State and a device lane are the same packed bytes: host state -> lane -> device kernels must agree with
+// the host rule core on every observable, and one device ApplyAction must produce the blob the host produces.
+static void LaneBridgeTests(std::mt19937* rng) {
+  for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex(board_size=7,swap=true)", "go(board_size=9)",
+                           "go(board_size=5)", "kuhn_poker", "leduc_poker"}) {
+    std::shared_ptr<const Game> game = LoadGame(name);
+    const auto* bg = dynamic_cast<const b200::B200Game*>(game.get());
+    SPIEL_CHECK_TRUE(bg != nullptr);
+    const b2s_game_info& gi = bg->info();
+    const int kLanes = 64;
+    void* batch = bg->NewBatch(kLanes);
+    std::vector<std::unique_ptr<State>> states;
+    for (int i = 0; i < kLanes; ++i) {               // random positions of random depth
+      auto s = game->NewInitialState();
+      int plies = (int)((*rng)() % (unsigned)(gi.max_game_length + 1));
+      for (int k = 0; k < plies && !s->IsTerminal(); ++k) {
+        auto la = s->LegalActions();
+        s->ApplyAction(la[(*rng)() % la.size()]);
+      }
+      static_cast<const b200::B200State&>(*s).ToBatchLane(batch, i);
+      states.push_back(std::move(s));
+    }
+    void* dev = nullptr;
+    const size_t W = gi.mask_words, P = gi.num_players, F = gi.observation_tensor_size;
+    size_t bytes = kLanes * (4 * W + 1 + 1 + 4 * P + 4 * F + 4) + 256;
+    SPIEL_CHECK_EQ(b2s_device_alloc(0, &dev, bytes), 0);
+    char* d = (char*)dev;
+    uint32_t* mask_d = (uint32_t*)d; d += kLanes * 4 * W;
+    float* rets_d = (float*)d; d += kLanes * 4 * P;
+    float* obs_d = (float*)d; d += kLanes * 4 * F;
+    int32_t* act_d = (int32_t*)d; d += kLanes * 4;
+    int8_t* cur_d = (int8_t*)d; d += kLanes;
+    uint8_t* term_d = (uint8_t*)d;
+    SPIEL_CHECK_EQ(b2s_legal_mask(batch, mask_d, kLanes, nullptr), 0);
+    SPIEL_CHECK_EQ(b2s_status(batch, cur_d, term_d, rets_d, kLanes, nullptr), 0);
+    SPIEL_CHECK_EQ(b2s_observation(batch, 0, obs_d, kLanes, nullptr), 0);
+    std::vector<uint32_t> mask(kLanes * W);
+    std::vector<float> rets(kLanes * P), obs(kLanes * F);
+    std::vector<int8_t> cur(kLanes);
+    std::vector<uint8_t> term(kLanes);
+    b2s_memcpy_d2h(0, mask.data(), mask_d, mask.size() * 4, nullptr);
+    b2s_memcpy_d2h(0, rets.data(), rets_d, rets.size() * 4, nullptr);
+    b2s_memcpy_d2h(0, obs.data(), obs_d, obs.size() * 4, nullptr);
+    b2s_memcpy_d2h(0, cur.data(), cur_d, kLanes, nullptr);
+    b2s_memcpy_d2h(0, term.data(), term_d, kLanes, nullptr);
+    SPIEL_CHECK_EQ(b2s_stream_synchronize(0, nullptr), 0);
+    std::vector<int32_t> acts(kLanes, -1);
+    for (int i = 0; i < kLanes; ++i) {
+      const State& s = *states[i];
+      SPIEL_CHECK_EQ((int)cur[i], (int)s.CurrentPlayer());
+      SPIEL_CHECK_EQ((bool)term[i], s.IsTerminal());
+      std::vector<Action> legal;
+      for (size_t w = 0; w < W; ++w)
+        for (int b = 0; b < 32; ++b) if ((mask[i * W + w] >> b) & 1u) legal.push_back(w * 32 + b);
+      SPIEL_CHECK_TRUE(legal == s.LegalActions());
+      std::vector<double> r = s.Returns();
+      for (size_t p = 0; p < P; ++p) SPIEL_CHECK_EQ((double)rets[i * P + p], r[p]);
+      std::vector<float> o = s.ObservationTensor(0);
+      for (size_t f = 0; f < F; ++f) SPIEL_CHECK_EQ(obs[i * F + f], o[f]);
+      if (!legal.empty()) acts[i] = (int32_t)legal[(*rng)() % legal.size()];
+    }
+    b2s_memcpy_h2d(0, act_d, acts.data(), kLanes * 4, nullptr);
+    SPIEL_CHECK_EQ(b2s_apply_actions(batch, act_d, kLanes, nullptr), 0);
+    int64_t bad = -1;
+    SPIEL_CHECK_EQ(b2s_error_count(batch, &bad, nullptr, nullptr), 0);
+    SPIEL_CHECK_EQ(bad, 0);
+    for (int i = 0; i < kLanes; ++i) {
+      if (acts[i] < 0) continue;
+      states[i]->ApplyAction(acts[i]);                           // host rule core
+      auto probe = game->NewInitialState();
+      auto& lane = static_cast<b200::B200State&>(*probe);
+      lane.FromBatchLane(batch, i);                              // device kernel
+      const auto& host = static_cast<const b200::B200State&>(*states[i]);
+      SPIEL_CHECK_EQ(memcmp(lane.blob(), host.blob(), bg->rules().state_bytes()), 0);
+      SPIEL_CHECK_EQ(lane.ToString().substr(lane.ToString().find('\n') + 1),
+                     host.ToString().substr(host.ToString().find('\n') + 1));   // (go prints history_.size() on line 1)
+    }
+    b2s_device_free(0, dev);
+    b2s_batch_destroy(batch);
+    std::cout << "lane bridge ok " << name << std::endl;
+  }
+}
+
 int main() {
-  // stock game objects, built directly from their classes before the names are taken over
+  // stock game objects, built by the stock factories before the names are taken over
   std::shared_ptr<const Game> stock_c4 = LoadGame("connect_four");
   std::shared_ptr<const Game> stock_ttt = LoadGame("tic_tac_toe");
-  std::shared_ptr<const Game> stock_c4_small = LoadGame("connect_four(rows=4,columns=5,x_in_row=3)");
   BotTests(*stock_c4, *stock_ttt);
   CfrTests();
   b200::RegisterB200Games();
   std::shared_ptr<const Game> c4 = LoadGame("connect_four");
-  std::shared_ptr<const Game> ttt = LoadGame("tic_tac_toe");
-  std::shared_ptr<const Game> c4_small = LoadGame("connect_four(rows=4,columns=5,x_in_row=3)");
   SPIEL_CHECK_TRUE(dynamic_cast<const b200::B200Game*>(c4.get()) != nullptr);     // LoadGame now returns the adapter
-  SPIEL_CHECK_TRUE(dynamic_cast<const b200::B200Game*>(ttt.get()) != nullptr);
-  SPIEL_CHECK_TRUE(dynamic_cast<const b200::B200Game*>(stock_c4.get()) == nullptr);
-  SPIEL_CHECK_EQ(c4->NumDistinctActions(), 7);
-  SPIEL_CHECK_EQ(c4->MaxGameLength(), 42);
   std::mt19937 rng(7);
-  LockStep(*c4, *stock_c4, 40, &rng);
-  LockStep(*ttt, *stock_ttt, 40, &rng);
-  LockStep(*c4_small, *stock_c4_small, 20, &rng);
-  testing::RandomSimTest(*c4, 15);        // the reference's own harness on the drop-in
-  testing::RandomSimTest(*ttt, 15);
-  testing::RandomSimTest(*c4_small, 10);
+  LaneBridgeTests(&rng);
+  // the algorithm adapters on the drop-in games as well (roots copied to the device as packed lanes)
+  BotTests(*c4, *LoadGame("tic_tac_toe"));
+  CfrTests();
+  {
+    // MCTSearch returns the reference's SearchNode: children = legal actions, visits sum to simulations - 1
+    std::shared_ptr<const Game> go = LoadGame("go(board_size=9)");
+    b200::B200MCTSBot bot(*go, 1, 2.0, 500, 100, true, 3, false);
+    auto st = go->NewInitialState();
+    st->ApplyAction(40);
+    auto root = bot.MCTSearch(*st);
+    SPIEL_CHECK_EQ(root->children.size(), st->LegalActions().size());
+    int total = 0;
+    for (const auto& ch : root->children) total += ch.explore_count;
+    SPIEL_CHECK_EQ(total, 499);
+    SPIEL_CHECK_EQ(root->BestChild().action, bot.Step(*st) >= 0 ? root->BestChild().action : -1);
+  }
   std::cout << "adapter_test ok" << std::endl;
   return 0;
 }

@@ -1,5 +1,6 @@
 #include "b200_algorithms.h"
 
+#include <algorithm>
 #include <cstring>
 #include <functional>
 
@@ -51,8 +52,10 @@ B200MCTSBot::B200MCTSBot(const Game& game, int n_rollouts, double uct_c, int max
   cfg_.uct_c = uct_c;
   cfg_.seed = (uint64_t)seed;
   cfg_.max_nodes_total = max_memory_mb > 0 ? (max_memory_mb << 20) / 32 : 0;     // arena nodes are 32 bytes
+  b200_game_ = B200Game::Create(game.GetType(), game.GetParameters());
+  if (!b200_game_) SpielFatalError("b200: " + game.ToString() + " does not fit the packed device layouts");
   Check(b2s_batch_create(gid_, &params_, 1, 0, &batch_));
-  Check(b2s_device_alloc(0, &dev_, 64 + (sizeof(int32_t) + sizeof(double)) * (size_t)num_actions_));
+  Check(b2s_device_alloc(0, &dev_, 64 + (2 * sizeof(int32_t) + sizeof(double) + sizeof(float)) * (size_t)(num_actions_ + 2)));
   visits_.assign(num_actions_, 0);
 }
 
@@ -61,34 +64,66 @@ B200MCTSBot::~B200MCTSBot() {
   if (dev_) b2s_device_free(0, dev_);
 }
 
-Action B200MCTSBot::Step(const State& state) {
-  // the search root = the reference state's action history replayed on a one-lane device batch
+// The search root: the reference state as a packed lane.  A B200State is copied as it is; any other State of the same
+// game (e.g. the stock C++ state) is rebuilt from its action history on the host rule core first.
+void B200MCTSBot::RootToDevice(const State& state) {
+  const B200State* packed = dynamic_cast<const B200State*>(&state);
+  std::unique_ptr<State> rebuilt;
+  if (!packed) {
+    rebuilt = b200_game_->NewInitialState();
+    for (Action a : state.History()) rebuilt->ApplyAction(a);
+    packed = static_cast<const B200State*>(rebuilt.get());
+  }
+  packed->ToBatchLane(batch_, 0);
+}
+
+std::unique_ptr<algorithms::SearchNode> B200MCTSBot::MCTSearch(const State& state) {
+  if (state.IsTerminal()) SpielFatalError("b200: MCTS called on a terminal state");
   char* d = (char*)dev_;
-  int32_t* act_d = (int32_t*)d;
   int32_t* best_d = (int32_t*)(d + 16);
   int32_t* visits_d = (int32_t*)(d + 64);
-  double* reward_d = (double*)(d + 64 + sizeof(int32_t) * (size_t)((num_actions_ + 1) & ~1));
-  Check(b2s_reset(batch_, 1, nullptr));
-  for (Action a : state.History()) {
-    int32_t a32 = (int32_t)a;
-    Check(b2s_memcpy_h2d(0, act_d, &a32, sizeof a32, nullptr));
-    Check(b2s_apply_actions(batch_, act_d, 1, nullptr));
-  }
-  int64_t bad = 0;
-  Check(b2s_error_count(batch_, &bad, nullptr, nullptr));
-  if (bad) SpielFatalError("b200: the state's history is not playable on the device");
+  const size_t A = (size_t)num_actions_, A2 = (A + 1) & ~(size_t)1;
+  double* reward_d = (double*)(d + 64 + sizeof(int32_t) * A2);
+  float* outcome_d = (float*)(d + 64 + sizeof(int32_t) * A2 + sizeof(double) * A);
+  RootToDevice(state);
   cfg_.tree_index_offset = (int64_t)steps_++;            // a fresh random stream per move, like the bot's advancing rng_
-  Check(b2s_mcts_search(batch_, 1, &cfg_, visits_d, reward_d, nullptr, best_d, nullptr, nullptr));
+  Check(b2s_mcts_search(batch_, 1, &cfg_, visits_d, reward_d, outcome_d, best_d, nullptr, nullptr));
+  std::vector<double> reward(A);
+  std::vector<float> outcome(A);
   int32_t best = -1;
   Check(b2s_memcpy_d2h(0, &best, best_d, sizeof best, nullptr));
-  Check(b2s_memcpy_d2h(0, visits_.data(), visits_d, sizeof(int32_t) * (size_t)num_actions_, nullptr));
+  Check(b2s_memcpy_d2h(0, visits_.data(), visits_d, sizeof(int32_t) * A, nullptr));
+  Check(b2s_memcpy_d2h(0, reward.data(), reward_d, sizeof(double) * A, nullptr));
+  Check(b2s_memcpy_d2h(0, outcome.data(), outcome_d, sizeof(float) * A, nullptr));
   Check(b2s_stream_synchronize(0, nullptr));
-  if (best < 0) SpielFatalError("b200: MCTS called on a terminal state");
-  return best;
+  const Player mover = state.CurrentPlayer();
+  auto root = std::make_unique<algorithms::SearchNode>(kInvalidAction, mover, 1.0);
+  std::vector<Action> legal = state.LegalActions();
+  // The device keeps the children in its own (random) expansion order and resolves BestChild ties in that order;
+  // its choice goes first here so that SearchNode::BestChild (first maximum) returns the same child.
+  for (size_t i = 0; i < legal.size(); ++i)
+    if (legal[i] == best) std::rotate(legal.begin(), legal.begin() + i, legal.begin() + i + 1);
+  last_best_ = best;
+  for (Action a : legal) {
+    algorithms::SearchNode child(a, mover, 1.0 / (double)legal.size());     // uniform prior, mcts.cc:74-87
+    child.explore_count = visits_[a];
+    child.total_reward = reward[a];
+    if (outcome[a] == outcome[a]) child.outcome = {(double)outcome[a], -(double)outcome[a]};   // proven (NaN = not)
+    root->explore_count += visits_[a];
+    root->children.push_back(std::move(child));
+  }
+  root->explore_count += 1;                               // the root's own first visit
+  return root;
+}
+
+Action B200MCTSBot::Step(const State& state) {
+  MCTSearch(state);
+  if (last_best_ < 0) SpielFatalError("b200: MCTS found no action");
+  return last_best_;
 }
 
 // ---- CFR -------------------------------------------------------------------------------------------------------
-B200CFRSolver::B200CFRSolver(const Game& game, bool cfr_plus) : game_(game.shared_from_this()) {
+B200CFRSolver::B200CFRSolver(const Game& game, bool cfr_plus) : game_(game.shared_from_this()), cfr_plus_(cfr_plus) {
   b2s_params p;
   int gid = GameIdAndParams(game, &p);
   Check(b2s_cfr_create(gid, &p, cfr_plus ? (B2S_CFR_LINEAR_AVERAGING | B2S_CFR_REGRET_MATCHING_PLUS) : 0, 0, &solver_));
@@ -152,6 +187,24 @@ TabularPolicy B200CFRSolver::CurrentPolicy() const {
   std::vector<double> cur(info_.num_entries);
   Check(b2s_cfr_export(solver_, nullptr, nullptr, cur.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
   return PolicyFrom(cur, false);
+}
+
+B200CFRSolver::Tables B200CFRSolver::Export() const {
+  Tables t;
+  b2s_cfr_info info;
+  Check(b2s_cfr_info_get(solver_, &info));
+  t.iteration = info.iteration;
+  t.regrets.resize(info_.num_entries); t.cumulative_policy.resize(info_.num_entries); t.current_policy.resize(info_.num_entries);
+  Check(b2s_cfr_export(solver_, t.regrets.data(), t.cumulative_policy.data(), t.current_policy.data(), nullptr, nullptr, nullptr, nullptr, nullptr));
+  return t;
+}
+
+void B200CFRSolver::Import(const Tables& t) {
+  if ((int)t.regrets.size() != info_.num_entries || (int)t.cumulative_policy.size() != info_.num_entries ||
+      (int)t.current_policy.size() != info_.num_entries)
+    SpielFatalError("b200: CFR checkpoint does not match this game's table size");
+  Check(b2s_cfr_import(solver_, t.regrets.data(), t.cumulative_policy.data(), t.current_policy.data(), t.iteration, nullptr));
+  Check(b2s_stream_synchronize(0, nullptr));
 }
 
 double B200CFRSolver::NashConv() const {

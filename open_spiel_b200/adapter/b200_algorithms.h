@@ -12,14 +12,11 @@
 #include <unordered_map>
 #include <vector>
 
+#include "b200_games.h"
 #include "open_spiel/algorithms/mcts.h"
 #include "open_spiel/policy.h"
 #include "open_spiel/spiel.h"
 #include "open_spiel/spiel_bots.h"
-
-extern "C" {
-#include "b2s.h"
-}
 
 namespace open_spiel {
 namespace b200 {
@@ -35,6 +32,10 @@ class B200MCTSBot : public Bot {
               algorithms::ChildSelectionPolicy child_selection_policy = algorithms::ChildSelectionPolicy::UCT);
   ~B200MCTSBot() override;
   Action Step(const State& state) override;
+  // MCTSBot::MCTSearch (mcts.cc:353-467): the root SearchNode with one level of children (action, player,
+  // explore_count, total_reward, proven outcome) — the statistics BestChild / ChildrenStr / the callers of
+  // pyspiel.MCTSBot.mcts_search read; deeper levels stay on the device.
+  std::unique_ptr<algorithms::SearchNode> MCTSearch(const State& state);
   void Restart() override {}
   void RestartAt(const State& state) override {}
   // Root statistics of the last Step: visit count per action id (0 for illegal actions).
@@ -45,10 +46,13 @@ class B200MCTSBot : public Bot {
   b2s_mcts_config cfg_;
   int gid_ = -1;
   int num_actions_ = 0;
+  void RootToDevice(const State& state);
+  std::shared_ptr<const Game> b200_game_;   // the packed-state twin of `game` (B200Game), for moving roots to the device
   void* batch_ = nullptr;      // one lane: the search root
   void* dev_ = nullptr;        // device scratch: action, visits, rewards, best
   std::vector<int> visits_;
   uint64_t steps_ = 0;
+  Action last_best_ = kInvalidAction;
 };
 
 class B200CFRSolver {
@@ -60,11 +64,18 @@ class B200CFRSolver {
   TabularPolicy AveragePolicy() const;                  // CFRAveragePolicy (cfr.cc:104-125) as a TabularPolicy
   TabularPolicy CurrentPolicy() const;
   double NashConv() const;                              // on the device (b2s_cfr_nash_conv)
+  // checkpoint: iteration counter + the three per-entry tables in device row order (b2s_cfr_export / b2s_cfr_import)
+  struct Tables { int iteration = 0; std::vector<double> regrets, cumulative_policy, current_policy; };
+  Tables Export() const;
+  void Import(const Tables& t);
+  bool cfr_plus() const { return cfr_plus_; }
+  const Game& game() const { return *game_; }
   int NumInfoStates() const { return info_.num_infosets; }
 
  private:
   TabularPolicy PolicyFrom(const std::vector<double>& per_entry, bool normalise) const;
   std::shared_ptr<const Game> game_;
+  bool cfr_plus_ = false;
   void* solver_ = nullptr;
   b2s_cfr_info info_;
   std::vector<std::string> keys_;                       // information-state string of every device table row

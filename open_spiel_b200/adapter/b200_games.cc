@@ -27,19 +27,6 @@ std::string Num(double v) {        // absl::StrCat(double) / ostream << float pr
   return b;
 }
 
-constexpr int kLeducInvalidCard = -10000;   // leduc_poker.h:60
-constexpr int kLeducStartingMoney = 100;    // leduc_poker.h:68
-
-// pot_ / money_ of LeducState (leduc_poker.cc:628-678, 702-706) from the antes: the pot is paid out at the terminal state
-void LeducMoney(const b2s_host::Decoded& d, bool terminal, const float* returns, int* pot, double money[2]) {
-  *pot = d.ante[0] + d.ante[1];
-  for (int p = 0; p < 2; ++p) money[p] = kLeducStartingMoney - d.ante[p];
-  if (terminal) {
-    for (int p = 0; p < 2; ++p) money[p] = kLeducStartingMoney + (double)returns[p];   // Returns = money - starting money
-    *pot = 0;
-  }
-}
-
 }  // namespace
 
 // ---- game -------------------------------------------------------------------------------------------------------
@@ -105,6 +92,131 @@ std::vector<int> B200Game::ObservationTensorShape() const {
 std::vector<int> B200Game::InformationStateTensorShape() const {
   if (info().information_state_tensor_size <= 0) return Game::InformationStateTensorShape();
   return {info().information_state_tensor_size};
+}
+
+// Structured observers of the two poker games, written against B200State::Poker().  Field names, shapes, order and the
+// string formats are the stock observers' (kuhn_poker.cc:64-170, leduc_poker.cc:92-239), so the named tensors and the
+// public / private observation strings of a playthrough come out identical.
+namespace {
+class B200PokerObserver : public Observer {
+ public:
+  B200PokerObserver(int gid, IIGObservationType t) : Observer(/*has_string=*/true, /*has_tensor=*/true), gid_(gid), t_(t) {}
+
+  void WriteTensor(const State& observed_state, int player, Allocator* allocator) const override {
+    const B200State& state = open_spiel::down_cast<const B200State&>(observed_state);
+    const B200State::PokerView v = state.Poker();
+    SPIEL_CHECK_GE(player, 0);
+    SPIEL_CHECK_LT(player, v.num_players);
+    const int n = v.num_players;
+    const bool single = t_.private_info == PrivateInfoType::kSinglePlayer;
+    if (gid_ == B2S_KUHN_POKER) {
+      if (single) {
+        allocator->Get("player", {n}).at(player) = 1;
+        auto card = allocator->Get("private_card", {n + 1});
+        if (v.private_cards[player] >= 0) card.at(v.private_cards[player]) = 1;
+      }
+      if (t_.public_info) {
+        if (t_.perfect_recall) {
+          auto out = allocator->Get("betting", {2 * n - 1, 2});
+          for (size_t i = 0; i < v.round1.size(); ++i) out.at((int)i, v.round1[i]) = 1;
+        } else {
+          auto out = allocator->Get("pot_contribution", {n});
+          for (int p = 0; p < n; ++p) out.at(p) = v.ante[p];
+        }
+      }
+      return;
+    }
+    const int cards = 2 * (n + 1);                       // leduc: NumObservableCards without suit isomorphism
+    allocator->Get("player", {n}).at(player) = 1;
+    if (single) {
+      auto out = allocator->Get("private_card", {cards});
+      if (v.private_cards[player] >= 0) out.at(v.private_cards[player]) = 1;
+    } else if (t_.private_info == PrivateInfoType::kAllPlayers) {
+      auto out = allocator->Get("private_cards", {n, cards});
+      for (int p = 0; p < n; ++p) if (v.private_cards[p] >= 0) out.at(p, v.private_cards[p]) = 1;
+    }
+    if (t_.public_info) {
+      auto pub = allocator->Get("community_card", {cards});
+      if (v.public_card >= 0) pub.at(v.public_card) = 1;
+      if (t_.perfect_recall) {
+        auto out = allocator->Get("betting", {2, 3 * n - 2, 2});
+        for (int round = 0; round < 2; ++round) {
+          const std::vector<int>& seq = round == 0 ? v.round1 : v.round2;
+          for (size_t i = 0; i < seq.size(); ++i) {
+            if (seq[i] == 1) out.at(round, (int)i, 0) = 1;         // call = 10
+            else if (seq[i] == 2) out.at(round, (int)i, 1) = 1;    // raise = 01
+          }
+        }
+      } else {
+        auto out = allocator->Get("pot_contribution", {n});
+        for (int p = 0; p < n; ++p) out.at(p) = v.ante[p];
+      }
+    }
+  }
+
+  std::string StringFrom(const State& observed_state, int player) const override {
+    const B200State& state = open_spiel::down_cast<const B200State&>(observed_state);
+    const B200State::PokerView v = state.Poker();
+    SPIEL_CHECK_GE(player, 0);
+    SPIEL_CHECK_LT(player, v.num_players);
+    const bool single = t_.private_info == PrivateInfoType::kSinglePlayer;
+    const bool no_private = t_.private_info == PrivateInfoType::kNone;
+    const int n = v.num_players;
+    const int hist = (int)state.History().size();
+    std::string s;
+    if (gid_ == B2S_KUHN_POKER) {
+      if (single) {
+        if (t_.perfect_recall || t_.public_info) {
+          if (hist > player) s += std::to_string(v.private_cards[player]);
+        } else if (hist == 1 + player) {
+          s += "Received card " + std::to_string(v.private_cards[player]);
+        }
+      }
+      if (t_.public_info) {
+        if (t_.perfect_recall) {
+          for (int a : v.round1) s += a ? 'b' : 'p';
+        } else if (no_private) {
+          if (hist == 0) s += "start game";
+          else if (hist > n) s += v.round1.back() ? "Bet" : "Pass";
+        } else if (hist > player) {
+          for (int p = 0; p < n; ++p) s += std::to_string(v.ante[p]);
+        }
+      }
+      if (t_.public_info && no_private && hist > 0 && hist <= n) s += "Deal to player " + std::to_string(hist - 1);
+      return s;
+    }
+    auto join = [](const std::vector<int>& x, const char* sep) {
+      std::string t;
+      for (size_t i = 0; i < x.size(); ++i) { if (i) t += sep; t += std::to_string(x[i]); }
+      return t;
+    };
+    if (single) {
+      s += "[Observer: " + std::to_string(player) + "][Private: " + std::to_string(v.private_cards[player]) + "]";
+    } else if (t_.private_info == PrivateInfoType::kAllPlayers) {
+      s += "[Privates: " + join(v.private_cards, "") + "]";
+    }
+    if (t_.public_info) {
+      s += "[Round " + std::to_string(v.round) + "][Player: " + std::to_string(v.cur_player) + "][Pot: " + std::to_string(v.pot) + "][Money:";
+      for (int p = 0; p < n; ++p) s += " " + Num(v.money[p]);
+      s += "]";
+      if (v.public_card >= 0) s += "[Public: " + std::to_string(v.public_card) + "]";
+      if (t_.perfect_recall) s += "[Round1: " + join(v.round1, " ") + "][Round2: " + join(v.round2, " ") + "]";
+      else s += "[Ante: " + join(v.ante, " ") + "]";
+    }
+    return s;
+  }
+
+ private:
+  int gid_;
+  IIGObservationType t_;
+};
+}  // namespace
+
+std::shared_ptr<Observer> B200Game::MakeObserver(absl::optional<IIGObservationType> iig_obs_type,
+                                                 const GameParameters& params) const {
+  if ((gid_ == B2S_KUHN_POKER || gid_ == B2S_LEDUC_POKER) && params.empty())
+    return std::make_shared<B200PokerObserver>(gid_, iig_obs_type.value_or(kDefaultObsType));
+  return Game::MakeObserver(iig_obs_type, params);
 }
 
 void* B200Game::NewBatch(int64_t n, int device) const {
@@ -313,20 +425,16 @@ std::string B200State::ToString() const {
     }
     case B2S_LEDUC_POKER: {
       static const char* kNames[3] = {"Fold", "Call", "Raise"};
-      float ret[2];
-      rules().Returns(blob_.data(), ret);
-      int pot;
-      double money[2];
-      LeducMoney(d, IsTerminal(), ret, &pot, money);
-      s = "Round: " + std::to_string(d.round) + "\nPlayer: " + std::to_string(d.cur_player) + "\nPot: " + std::to_string(pot) +
+      const PokerView v = Poker();
+      s = "Round: " + std::to_string(v.round) + "\nPlayer: " + std::to_string(v.cur_player) + "\nPot: " + std::to_string(v.pot) +
           "\nMoney (player_0 player_1):";
-      for (int p = 0; p < 2; ++p) s += " " + Num(money[p]);
-      s += "\nCards (public player_0 player_1): " + std::to_string(d.public_card < 0 ? kLeducInvalidCard : d.public_card) + " ";
-      for (int p = 0; p < 2; ++p) s += std::to_string(d.private_card[p] < 0 ? kLeducInvalidCard : d.private_card[p]) + " ";
+      for (int p = 0; p < 2; ++p) s += " " + Num(v.money[p]);
+      s += "\nCards (public player_0 player_1): " + std::to_string(v.public_card) + " ";
+      for (int p = 0; p < 2; ++p) s += std::to_string(v.private_cards[p]) + " ";
       s += "\nRound 1 sequence: ";
-      for (size_t i = 0; i < d.round1.size(); ++i) { if (i) s += ", "; s += kNames[d.round1[i]]; }
+      for (size_t i = 0; i < v.round1.size(); ++i) { if (i) s += ", "; s += kNames[v.round1[i]]; }
       s += "\nRound 2 sequence: ";
-      for (size_t i = 0; i < d.round2.size(); ++i) { if (i) s += ", "; s += kNames[d.round2[i]]; }
+      for (size_t i = 0; i < v.round2.size(); ++i) { if (i) s += ", "; s += kNames[v.round2[i]]; }
       s += "\n";
       return s;
     }
@@ -334,35 +442,13 @@ std::string B200State::ToString() const {
   return HistoryString();
 }
 
-// kuhn_poker.cc:109-166 (KuhnObserver::StringFrom), leduc_poker.cc:198-239 (LeducObserver::StringFrom); the board games
+// The poker games answer through their observers (kuhn_poker.cc:285-327, leduc_poker.cc:516-544); the board games
 // return HistoryString() / ToString() (e.g. connect_four.cc:287-297).
 std::string B200State::InformationStateString(Player player) const {
   SPIEL_CHECK_GE(player, 0);
   SPIEL_CHECK_LT(player, num_players_);
   const int gid = bgame().gid();
-  if (gid == B2S_KUHN_POKER) {
-    std::string s;
-    if ((int)history_.size() > player) s += std::to_string(history_[player].action);
-    for (int i = num_players_; i < (int)history_.size(); ++i) s += history_[i].action ? 'b' : 'p';
-    return s;
-  }
-  if (gid == B2S_LEDUC_POKER) {
-    b2s_host::Decoded d;
-    rules().Decode(blob_.data(), &d);
-    float ret[2];
-    rules().Returns(blob_.data(), ret);
-    int pot;
-    double money[2];
-    LeducMoney(d, IsTerminal(), ret, &pot, money);
-    auto join = [](const std::vector<int>& v) { std::string t; for (size_t i = 0; i < v.size(); ++i) { if (i) t += " "; t += std::to_string(v[i]); } return t; };
-    std::string s = "[Observer: " + std::to_string(player) + "][Private: " +
-                    std::to_string(d.private_card[player] < 0 ? kLeducInvalidCard : d.private_card[player]) + "]";
-    s += "[Round " + std::to_string(d.round) + "][Player: " + std::to_string(d.cur_player) + "][Pot: " + std::to_string(pot) +
-         "][Money: " + Num(money[0]) + " " + Num(money[1]) + "]";
-    if (d.public_card >= 0) s += "[Public: " + std::to_string(d.public_card) + "]";
-    s += "[Round1: " + join(d.round1) + "][Round2: " + join(d.round2) + "]";
-    return s;
-  }
+  if (gid == B2S_KUHN_POKER || gid == B2S_LEDUC_POKER) return B200PokerObserver(gid, kInfoStateObsType).StringFrom(*this, player);
   return HistoryString();
 }
 
@@ -370,34 +456,46 @@ std::string B200State::ObservationString(Player player) const {
   SPIEL_CHECK_GE(player, 0);
   SPIEL_CHECK_LT(player, num_players_);
   const int gid = bgame().gid();
+  if (gid == B2S_KUHN_POKER || gid == B2S_LEDUC_POKER) return B200PokerObserver(gid, kDefaultObsType).StringFrom(*this, player);
+  return ToString();
+}
+
+B200State::PokerView B200State::Poker() const {
+  PokerView v;
+  v.num_players = num_players_;
+  const int gid = bgame().gid();
   if (gid == B2S_KUHN_POKER) {
-    std::string s;
-    if ((int)history_.size() > player) {
-      s += std::to_string(history_[player].action);
-      float obs[16];
-      rules().Tensor(blob_.data(), player, 0, obs);            // pot contributions are the last num_players_ entries
-      const int off = rules().info().observation_tensor_size - num_players_;
-      for (int p = 0; p < num_players_; ++p) s += std::to_string((int)obs[off + p]);
-    }
-    return s;
+    v.private_cards.assign(num_players_, -1);
+    for (int p = 0; p < num_players_ && p < (int)history_.size(); ++p) v.private_cards[p] = (int)history_[p].action;
+    for (int i = num_players_; i < (int)history_.size(); ++i) v.round1.push_back((int)history_[i].action);
+    float obs[16];
+    rules().Tensor(blob_.data(), 0, 0, obs);                   // pot contributions are the last num_players_ entries
+    const int off = rules().info().observation_tensor_size - num_players_;
+    for (int p = 0; p < num_players_; ++p) v.ante.push_back((int)obs[off + p]);
+    return v;
   }
-  if (gid == B2S_LEDUC_POKER) {
-    b2s_host::Decoded d;
-    rules().Decode(blob_.data(), &d);
+  SPIEL_CHECK_EQ(gid, (int)B2S_LEDUC_POKER);
+  b2s_host::Decoded d;
+  rules().Decode(blob_.data(), &d);
+  constexpr int kInvalidCard = -10000, kStartingMoney = 100;   // leduc_poker.h:60,68
+  v.round = d.round;
+  v.cur_player = d.cur_player;
+  v.public_card = d.public_card < 0 ? kInvalidCard : d.public_card;
+  for (int p = 0; p < 2; ++p) {
+    v.private_cards.push_back(d.private_card[p] < 0 ? kInvalidCard : d.private_card[p]);
+    v.ante.push_back(d.ante[p]);
+  }
+  v.round1 = d.round1; v.round2 = d.round2;
+  // pot_ / money_ (leduc_poker.cc:628-678, 702-706): antes leave the stacks for the pot; ResolveWinner pays the pot out
+  v.pot = d.ante[0] + d.ante[1];
+  for (int p = 0; p < 2; ++p) v.money.push_back(kStartingMoney - d.ante[p]);
+  if (IsTerminal()) {
     float ret[2];
     rules().Returns(blob_.data(), ret);
-    int pot;
-    double money[2];
-    LeducMoney(d, IsTerminal(), ret, &pot, money);
-    std::string s = "[Observer: " + std::to_string(player) + "][Private: " +
-                    std::to_string(d.private_card[player] < 0 ? kLeducInvalidCard : d.private_card[player]) + "]";
-    s += "[Round " + std::to_string(d.round) + "][Player: " + std::to_string(d.cur_player) + "][Pot: " + std::to_string(pot) +
-         "][Money: " + Num(money[0]) + " " + Num(money[1]) + "]";
-    if (d.public_card >= 0) s += "[Public: " + std::to_string(d.public_card) + "]";
-    s += "[Ante: " + std::to_string(d.ante[0]) + " " + std::to_string(d.ante[1]) + "]";
-    return s;
+    for (int p = 0; p < 2; ++p) v.money[p] = kStartingMoney + (double)ret[p];      // Returns = money - starting money
+    v.pot = 0;
   }
-  return ToString();
+  return v;
 }
 
 // ---- registration -------------------------------------------------------------------------------------------------

@@ -38,6 +38,10 @@ class B200Game : public Game {
   std::vector<int> ObservationTensorShape() const override;
   std::vector<int> InformationStateTensorShape() const override;
   std::string ActionToString(Player player, Action action_id) const override;
+  // kuhn_poker / leduc_poker: the games' own structured observers (named tensor fields, public / private observation
+  // strings), kuhn_poker.cc:428-437, leduc_poker.cc:853-862; the board games use the built-in observers.
+  std::shared_ptr<Observer> MakeObserver(absl::optional<IIGObservationType> iig_obs_type,
+                                         const GameParameters& params) const override;
 
   // Vectorised entry point: a raw b2s batch of n lanes of this game on `device` (caller owns it; b2s_batch_destroy).
   void* NewBatch(int64_t n, int device = 0) const;
@@ -74,6 +78,17 @@ class B200State : public State {
   std::unique_ptr<State> Clone() const override;
   void UndoAction(Player player, Action action) override;
   std::vector<std::pair<Action, double>> ChanceOutcomes() const override;
+
+  // kuhn_poker / leduc_poker: what the poker observers and strings are made of (reference member names).
+  struct PokerView {
+    int num_players = 2;
+    std::vector<int> private_cards;       // kInvalidCard (-10000) when not dealt (leduc), history-derived for kuhn
+    int public_card = -10000, round = 1, cur_player = -1, pot = 0;
+    std::vector<double> money;
+    std::vector<int> ante;
+    std::vector<int> round1, round2;      // leduc betting sequences: 0 fold, 1 call, 2 raise
+  };
+  PokerView Poker() const;
 
   // The packed lane (b2s_state_get / b2s_state_set layout).
   const void* blob() const { return blob_.data(); }

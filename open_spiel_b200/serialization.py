@@ -69,7 +69,9 @@ def kuhn_information_state_string(tensor):
 
 
 def leduc_information_state_string(tensor):
-    """leduc_poker.cc:198-239 (2 players, default parameters): the perfect-recall observer string of the acting player.
+    """leduc_poker.cc:198-239 (2 players, default parameters): the perfect-recall observer string of the player the
+    tensor was made for (folds are not visible in the tensor, so states after a fold are out of its domain: use the
+    pyspiel module's State.information_state_string for those).
     tensor = player(2) . private card(6) . public card(6) . betting[2 rounds][4 actions][2] (call = 10, raise = 01)."""
     t = np.asarray(tensor).reshape(-1)
     player = int(np.argmax(t[0:2]))
@@ -86,21 +88,35 @@ def leduc_information_state_string(tensor):
             else:
                 break
     # replay the betting to recover pot and money (leduc_poker.cc:298-414: ante 1, raises of 2 then 4, 100 starting chips)
+    # and whose turn it is (cur_player_, printed as "[Player: ...]" whoever observes, leduc_poker.cc:218)
     money, ante, pot, stakes = [99.0, 99.0], [1, 1], 2, 1
+    cur = 0
     for r, seq in enumerate(rounds):
-        actor = 0
+        actor, raises, calls = 0, 0, 0
         for a in seq:
             if a == 2:
                 stakes += 2 if r == 0 else 4
+                raises, calls = raises + 1, 0
+            else:
+                calls += 1
             pay = stakes - ante[actor]
             ante[actor] += pay
             money[actor] -= pay
             pot += pay
             actor ^= 1
+        complete = (raises == 0 and calls == 2) or (raises > 0 and calls == 1)      # ReadyForNextRound, :680-683
+        if r == 0 and not complete:
+            cur = actor
+            break
+        if r == 0 and public is None:
+            cur = -1                                   # waiting for the public card: kChancePlayerId
+            break
+        if r == 1:
+            cur = actor if not complete else actor ^ 1   # after the last call the mover stays (the state is terminal)
     rnd = 2 if public is not None else 1
     fmt = lambda v: ("%d" % v) if float(v).is_integer() else repr(float(v))   # noqa: E731
     s = "[Observer: %d][Private: %d][Round %d][Player: %d][Pot: %d][Money: %s %s]" % (
-        player, private, rnd, player, pot, fmt(money[0]), fmt(money[1]))
+        player, private, rnd, cur, pot, fmt(money[0]), fmt(money[1]))
     if public is not None:
         s += "[Public: %d]" % public
     s += "[Round1: %s][Round2: %s]" % (" ".join(map(str, rounds[0])), " ".join(map(str, rounds[1])))

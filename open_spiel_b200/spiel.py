@@ -521,11 +521,15 @@ class MCTSBot:
         self.uct_c, self.max_simulations, self.solve, self.seed = float(uct_c), int(max_simulations), bool(solve), int(seed)
         self.max_nodes = (int(max_memory_mb) << 20) // 32        # arena nodes are 32 B
         self.child_selection_policy = int(child_selection_policy)
+        self._searches = 0
 
     def mcts_search(self, state):
-        """Returns the root statistics of one search from `state` (a scalar State adapter)."""
+        """Returns the root statistics of one search from `state` (a scalar State adapter).  Every search uses a fresh
+        random stream (seed, tree index = number of earlier searches), like the reference bot's advancing rng_."""
+        self._searches += 1
         return mcts_search(state._b, self.max_simulations, self.uct_c, self.evaluator.n_rollouts, self.solve, self.seed,
-                           n_trees=1, max_nodes_total=self.max_nodes, child_selection_policy=self.child_selection_policy)
+                           tree_index_offset=self._searches - 1, n_trees=1, max_nodes_total=self.max_nodes,
+                           child_selection_policy=self.child_selection_policy)
 
     def step(self, state):
         """Bot::Step (mcts.cc:233-266): the best action at `state`."""

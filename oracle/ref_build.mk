@@ -15,7 +15,8 @@ SRCS := spiel.cc spiel_utils.cc game_parameters.cc observer.cc policy.cc spiel_b
         algorithms/mcts.cc algorithms/cfr.cc algorithms/evaluate_bots.cc algorithms/tabular_exploitability.cc \
         algorithms/best_response.cc algorithms/expected_returns.cc algorithms/history_tree.cc \
         algorithms/get_all_states.cc algorithms/trajectories.cc \
-        algorithms/external_sampling_mccfr.cc tests/basic_tests.cc
+        algorithms/external_sampling_mccfr.cc algorithms/outcome_sampling_mccfr.cc tests/basic_tests.cc \
+        game_transforms/start_at.cc
 OBJS := $(addprefix _ref/obj/,$(SRCS:.cc=.o))
 
 all: _ref/libspiel_ref.a _ref/libspiel_ref_c.so _ref/ref_bench
