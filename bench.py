@@ -12,9 +12,10 @@ private copy of the snapshot (made before the timed region; K+W copies = far mor
 work and none finds its inputs cached.
 
 Printed JSON (one line, rank 0): metric/value = ApplyAction/s with states and actions resident in HBM;
-e2e = the same step through b2s_step_fused_host with pinned HOST buffers (H2D actions, D2H mask/terminal/
-returns inside the timed region); roofline = algorithmic bytes / CUDA-event time of the apply kernel vs the
-measured HBM peak; cpu_baseline = the CPU arm on a bounded sample.
+e2e = the same env step through b2s_step_fused_host_compact with pinned HOST buffers (H2D uint8 actions, D2H one
+status byte per lane — terminal / outcome / next legal mask — inside the timed region; the float32-returns entry
+b2s_step_fused_host is timed as well and reported under extras); roofline = algorithmic bytes / CUDA-event time of
+the apply kernel vs the measured HBM peak; cpu_baseline = the CPU arm on a bounded sample.
 """
 import argparse
 import ctypes as C
@@ -97,39 +98,40 @@ def cpu_loops():
     return out
 
 
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
+def host_cpus():
     host = os.cpu_count() or 1
     try:
         host = min(host, len(os.sched_getaffinity(0)))
     except Exception:
         pass
-    n_sample = 1 << 18
-    # "All the host threads it can use": the reference steps one heap-allocated State per lane, and on
-    # many-core boxes more threads can be slower (allocator / cgroup limits), so calibrate the thread count on a
-    # small sample first and give the CPU arm its best configuration.
-    cands = sorted({1, 2, 4, 8, 16, 32, 64, host} & set(range(1, host + 1)))
-    best_t, best_v = 1, 0.0
-    for t in cands:
-        v, _, _ = cpu_arm(1 << 15, t, 3)
-        if v > best_v:
-            best_t, best_v = t, v
-    cores = best_t
-    _, kind, per = cpu_arm(n_sample, cores, args.warmup + args.steps)
+    return host
+
+
+def run_reference(args):
+    """The unmodified reference's State::ApplyAction on the box's host cores, on OUR arm's configuration: 1,048,576 states
+    per step, same U{0..20}-ply stream.  Thread count is fixed and stated (all host CPUs; no per-run calibration); the
+    1-thread figure — the reference's native mode — is reported next to it."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    host = host_cpus()
+    n_sample = N_STATES
+    _, kind, per = cpu_arm(n_sample, host, args.warmup + args.steps)
     times = per[args.warmup:]
     ms = 1e3 * sum(times) / max(len(times), 1)
     value = n_sample / (ms / 1e3) if ms > 0 else 0.0
+    v1, _, per1 = cpu_arm(n_sample, 1, 4)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "connect_four batched ApplyAction, SoA batch (CPU arm: one heap State per lane)",
-                   "states_per_step": n_sample, "prefix_plies": "U{0..%d}" % MAX_PREFIX},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": "%d states per step (same U{0..20}-ply synthetic stream), Clone excluded; threads calibrated over %s of %d host CPUs" % (n_sample, cands, host),
-                         "host_cores": host},
+        "config": {"workload": "connect_four batched ApplyAction, 1,048,576-state SoA batch per GPU (BASELINE configs[1])",
+                   "states_per_step_per_gpu": n_sample, "prefix_plies": "U{0..%d}" % MAX_PREFIX,
+                   "cpu_arm": "one heap-allocated open_spiel::State per lane, ApplyAction timed, Clone excluded"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": host, "kind": kind,
+                         "sample": "%d states per step x %d steps on all %d host CPUs (fixed, no calibration)" % (n_sample, len(times), host),
+                         "host_cores": host, "value_1_thread": v1,
+                         "sample_1_thread": "%d states x 4 passes, 1 thread (%.2f s timed)" % (n_sample, sum(per1))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -169,8 +171,10 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def build_workload(torch, game, n, dev, seed):
-    """Snapshot batch of n non-terminal positions + one legal action per lane (all on device)."""
+def build_workload(torch, game, n, dev, seed, with_history=False):
+    """Snapshot batch of n non-terminal positions + one legal action per lane (all on device).  with_history also returns
+    the plies that built every lane, int32 [n, MAX_PREFIX] (-1 = no move), so the exact benched batch can be replayed on the
+    reference (tests/test_gpu_bench_workload.py)."""
     snap = game.new_batch(n)
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
@@ -184,6 +188,7 @@ def build_workload(torch, game, n, dev, seed):
 
     # advance lane i by k_i plies, never stepping INTO a terminal state (keep the pre-terminal position)
     probe = game.new_batch(n)
+    hist = []
     for t in range(MAX_PREFIX):
         a, has = random_legal(snap.legal_actions_mask_words())
         a = torch.where((t < k) & has, a, torch.full_like(a, -1))
@@ -192,9 +197,13 @@ def build_workload(torch, game, n, dev, seed):
         _, term, _ = probe.status()
         a = torch.where(term.bool(), torch.full_like(a, -1), a)               # do not enter terminal states
         snap.apply_actions(a)
+        if with_history:
+            hist.append(a.clone())
     actions, has = random_legal(snap.legal_actions_mask_words())
     assert bool(has.all())
     snap.check_errors()
+    if with_history:
+        return game, snap, actions.contiguous(), torch.stack(hist, dim=1).contiguous()
     return game, snap, actions.contiguous()
 
 
@@ -210,6 +219,9 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NUMA: pin this rank to the CPUs next to its GPU BEFORE any pinned buffer is allocated (first touch), so the
+    # host<->device copies of the e2e path do not cross the socket interconnect (GPUs 4-7 hang off node 1).
+    numa_cpus = b2.bind_host_to_device(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -234,6 +246,7 @@ def run_gpu(args):
 
     L = _lib.lib()
     stream = torch.cuda.Stream(device=dev)
+    sides = [torch.cuda.Stream(device=dev) for _ in range(3)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -241,25 +254,41 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def capture(fn_per_slot, lo, hi):
-        """CUDA graph of launches [lo, hi) (the env loop is launch-bound; graphs keep the host out of it)."""
+    def capture(fn_per_slot, lo, hi, n_streams=1):
+        """CUDA graph of launches [lo, hi) (the env loop is launch-bound; graphs keep the host out of it).  n_streams > 1:
+        step i runs on stream i mod n_streams — the steps work on DIFFERENT batches, so they are independent and the
+        graph says so (parallel branches) instead of serialising them on one stream."""
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=stream):
-            for i in range(lo, hi):
-                fn_per_slot(i)
+            if n_streams == 1:
+                for i in range(lo, hi):
+                    fn_per_slot(i)
+            else:
+                lanes = [stream] + sides[:n_streams - 1]
+                fork = torch.cuda.Event()
+                fork.record(stream)
+                for sd in lanes[1:]:
+                    sd.wait_event(fork)
+                for i in range(lo, hi):
+                    with torch.cuda.stream(lanes[(i - lo) % n_streams]):
+                        fn_per_slot(i)
+                for sd in lanes[1:]:
+                    join = torch.cuda.Event()
+                    join.record(sd)
+                    stream.wait_event(join)
         return g
 
-    def time_graphs(fn_per_slot, reps=3):
+    def time_graphs(fn_per_slot, reps=3, n_streams=1):
         """W warm-up launches, then exactly K timed launches (in graphs of <= C) bracketed by barrier + synchronize;
         returns the best-of-`reps` max-over-ranks milliseconds for the K launches (CUDA events on the launching stream)."""
         restore()
         torch.cuda.synchronize()
         chunks = [(k0, min(C, K - k0)) for k0 in range(0, K, C)]
-        gw = capture(fn_per_slot, 0, W)
+        gw = capture(fn_per_slot, 0, W, n_streams)
         graphs = {}
         for _, cnt in chunks:
             if cnt not in graphs:
-                graphs[cnt] = capture(fn_per_slot, W, W + cnt)
+                graphs[cnt] = capture(fn_per_slot, W, W + cnt, n_streams)
         best = None
         for _ in range(reps):
             total = 0.0
@@ -282,6 +311,13 @@ def run_gpu(args):
             best = ms if best is None else min(best, ms)
         return best
 
+    def maxtime(seconds):
+        if dist is None:
+            return seconds
+        t = torch.tensor([seconds], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     mask = torch.empty((n, 1), dtype=torch.int32, device=dev)
     term = torch.empty((n,), dtype=torch.uint8, device=dev)
     rets = torch.empty((n, 2), dtype=torch.float32, device=dev)
@@ -290,40 +326,58 @@ def run_gpu(args):
     if sampler:
         sampler.start()
     launches0 = L.b2s_launch_count()
-    # ---- headline: ApplyAction, device-resident ---------------------------------------------------
+    # ---- headline: ApplyAction, device-resident, one stream, every step ordered after the previous one ----------
     ms_apply_total = time_graphs(lambda i: works[i].apply_actions(acts[i]))
+    for w_ in works:
+        w_.check_errors()
+    # ---- the same K steps with their independence declared: 2 and 4 parallel chains in the graph ------------------
+    ms_apply_s2 = time_graphs(lambda i: works[i].apply_actions(acts[i]), reps=2, n_streams=2)
+    ms_apply_s4 = time_graphs(lambda i: works[i].apply_actions(acts[i]), reps=2, n_streams=4)
     for w_ in works:
         w_.check_errors()
     # ---- extras: fused step, legal mask -------------------------------------------------------------
     ms_fused_total = time_graphs(lambda i: works[i].step(acts[i], mask, term, rets), reps=2)
     ms_mask_total = time_graphs(lambda i: works[i].legal_actions_mask_words(out=mask), reps=2)
-    # ---- e2e: host buffers through b2s_step_fused_host, one synchronous call per step ----------------
-    act_h = actions0.cpu().pin_memory()
+    # ---- e2e: host buffers, one synchronous C-ABI call per step (H2D + kernel + D2H + sync inside the call) ----------
+    act_h8 = actions0.to(torch.uint8).cpu().pin_memory()         # compact entry: 1 B in, 1 B out per lane
+    status_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
+    act_h = actions0.cpu().pin_memory()                          # float entry: 4 B in, 13 B out per lane
     mask_h = torch.empty((n, 1), dtype=torch.int32).pin_memory()
     term_h = torch.empty((n,), dtype=torch.uint8).pin_memory()
     rets_h = torch.empty((n, 2), dtype=torch.float32).pin_memory()
-    restore()
-    for w_ in works:                      # allocate every batch's staging buffers outside the timed region
-        w_.step_host(act_h, mask_h, term_h, rets_h, n=0)
-    barrier()
-    for i in range(W):
-        works[i].step_host(act_h, mask_h, term_h, rets_h)
-    barrier()
-    ms_e2e_total = 0.0
-    for k0 in range(0, K, C):
-        if k0:
-            restore()
-            barrier()
-        t0 = time.perf_counter()
-        for i in range(W, W + min(C, K - k0)):
-            works[i].step_host(act_h, mask_h, term_h, rets_h)      # returns after the D2H copies completed
-        torch.cuda.synchronize()
-        ms_e2e_total += (time.perf_counter() - t0) * 1e3
-    if dist is not None:
-        t = torch.tensor([ms_e2e_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e_total = float(t.item())
-    barrier()
+
+    def time_host_calls(call):
+        restore()
+        for w_ in works:                      # allocate every batch's staging buffers outside the timed region
+            call(w_, 0)
+        barrier()
+        for i in range(W):
+            call(works[i], n)
+        barrier()
+        total = 0.0
+        for k0 in range(0, K, C):
+            if k0:
+                restore()
+                barrier()
+            t0 = time.perf_counter()
+            for i in range(W, W + min(C, K - k0)):
+                call(works[i], n)             # returns after the D2H copies completed
+            torch.cuda.synchronize()
+            total += (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([total], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t.item())
+        barrier()
+        return total
+
+    ms_e2e_total = time_host_calls(lambda w_, m: w_.step_host_compact(act_h8, status_h, n=m))
+    status_snapshot = status_h.clone()
+    ms_e2e_f32_total = time_host_calls(lambda w_, m: w_.step_host(act_h, mask_h, term_h, rets_h, n=m))
+    # the two entry points must describe the same step: terminal flags and legal masks agree lane for lane
+    e2e_consistent = bool(((status_snapshot >> 7) == term_h).all()) and \
+        bool((torch.where(term_h.bool(), torch.zeros_like(mask_h[:, 0]), mask_h[:, 0]).to(torch.uint8) ==
+              torch.where(term_h.bool(), torch.zeros_like(status_snapshot), status_snapshot & 0x7F)).all())
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -333,30 +387,54 @@ def run_gpu(args):
     del works, acts
     torch.cuda.empty_cache()
 
-    # ---- the loops that drive the step kernels (BASELINE configs[2..4]); reported under "extras" -------------
-    def maxtime(seconds):
-        if dist is None:
-            return seconds
-        t = torch.tensor([seconds], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    # ---- the same kernel on a batch larger than L2 (64M lanes = 1 GiB of state) ----------------------
+    big_n = n * 64
+    big = game.new_batch(big_n)
+    acts_big = actions0.repeat(64).contiguous()
+    big_ms = []
+    for rep in range(6):
+        for t in range(64):
+            big.copy_from(snap, src_begin=0, dst_begin=t * n, count=n)
+        barrier()
+        with torch.cuda.stream(stream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            big.apply_actions(acts_big)
+            e1.record(stream)
+        barrier()
+        if rep:
+            big_ms.append(e0.elapsed_time(e1))
+    big.check_errors()
+    ms_big = maxtime(sum(big_ms) / len(big_ms))
+    del big, acts_big
+    torch.cuda.empty_cache()
 
+    # ---- the loops that drive the step kernels (BASELINE configs[2..4]); reported under "extras" -------------
     loops = {}
     from open_spiel_b200 import parallel
     # MCTS: go 9x9, RandomRolloutEvaluator(1), uct_c=2, solve; independent roots sharded over GPUs
     go = b2.Game("go", {"board_size": 9}, device=local)
-    trees, sims = 65536, 128                  # throughput grows with resident trees until ~14 warps/SM
-    roots = go.new_batch(trees)
-    b2.mcts_search(roots, 8, seed=1, tree_index_offset=rank * trees)          # warm-up: allocations, table upload
-    barrier()
-    t0 = time.perf_counter()
-    out = b2.mcts_search(roots, sims, uct_c=2.0, n_rollouts=1, solve=True, seed=1, tree_index_offset=rank * trees)
-    torch.cuda.synchronize()
-    dt = maxtime(time.perf_counter() - t0)
-    nsims = parallel.allreduce_stats(out["sims_run"].sum().to(torch.int64).reshape(1))
-    loops["mcts_go9x9"] = {"sims_per_s": float(nsims.item()) / dt, "trees_per_gpu": trees, "sims_per_tree": sims,
-                           "seconds": dt, "errors": roots.error_count()[0]}
-    del roots, out
+
+    def mcts_line(trees, sims, nodes=0):
+        roots = go.new_batch(trees)
+        b2.mcts_search(roots, 8, seed=1, tree_index_offset=rank * trees, max_nodes_total=nodes)   # warm-up: allocations, table upload
+        barrier()
+        t0 = time.perf_counter()
+        out = b2.mcts_search(roots, sims, uct_c=2.0, n_rollouts=1, solve=True, seed=1, tree_index_offset=rank * trees,
+                             max_nodes_total=nodes)
+        torch.cuda.synchronize()
+        dt = maxtime(time.perf_counter() - t0)
+        nsims = parallel.allreduce_stats(out["sims_run"].sum().to(torch.int64).reshape(1))
+        res = {"sims_per_s": float(nsims.item()) / dt, "trees_per_gpu": trees, "sims_per_tree": sims, "seconds": dt,
+               "errors": roots.error_count()[0], "nodes_used_rank0": b2.mcts_nodes_used(roots)}
+        del roots, out
+        torch.cuda.empty_cache()
+        return res
+
+    loops["mcts_go9x9"] = mcts_line(65536, 128)          # throughput grows with resident trees until ~14 warps/SM
+    # deep trees (BASELINE configs[2] is 100k sims/move; a full 100k-sim run of enough trees takes minutes and is recorded
+    # in profiles/): steady state at 10k simulations per tree, where descents are ~10 levels deep
+    loops["mcts_go9x9_deep"] = mcts_line(args.deep_trees, args.deep_sims, nodes=args.deep_trees * 240000)
     # self-play rollouts: breakthrough 8x8, 2^20 games per GPU, statistics all-reduced
     bt = b2.Game("breakthrough", device=local)
     games = 1 << 20
@@ -372,17 +450,19 @@ def run_gpu(args):
     loops["rollouts_breakthrough"] = {"games_per_s": st[4] / dt, "plies_per_s": st[3] / dt, "p0_wins": st[0], "p1_wins": st[1],
                                       "games": st[4], "seconds": dt}
     del bb, rets_r, plies_r
-    # CFR: leduc_poker; single-GPU bit-exact solver (replicated per rank) and, for N > 1, the NCCL-sharded solver
+    # CFR: leduc_poker at the configured 100,000 iterations; single-GPU bit-exact solver (replicated per rank) and, for
+    # N > 1, the NCCL-sharded solver
     leduc = b2.Game("leduc_poker", device=local)
     solver = b2.CFRSolver(leduc)
     solver.evaluate_and_update_policy(10)
     torch.cuda.synchronize()
-    iters = 2000
+    iters = args.cfr_iters
     t0 = time.perf_counter()
     solver.evaluate_and_update_policy(iters)
     torch.cuda.synchronize()
     dt = maxtime(time.perf_counter() - t0)
-    loops["cfr_leduc"] = {"iters_per_s": iters / dt, "node_visits_per_s": iters * 2 * 9457 / dt, "iters": iters, "seconds": dt}
+    loops["cfr_leduc"] = {"iters_per_s": iters / dt, "node_visits_per_s": iters * 2 * 9457 / dt, "iters": iters, "seconds": dt,
+                          "exploitability": solver.exploitability()}
     if world > 1:
         dsolver = parallel.DistributedCFRSolver(leduc)
         dsolver.evaluate_and_update_policy(5)
@@ -426,21 +506,28 @@ def run_gpu(args):
         if dist is not None:
             dist.destroy_process_group()
         return 0
-    ms_apply, ms_fused, ms_mask, ms_e2e = ms_apply_total / K, ms_fused_total / K, ms_mask_total / K, ms_e2e_total / K
+    ms_apply, ms_fused, ms_mask = ms_apply_total / K, ms_fused_total / K, ms_mask_total / K
+    ms_e2e, ms_e2e_f32 = ms_e2e_total / K, ms_e2e_f32_total / K
     peak, peak_src = hbm_peak()
     value = world * n / (ms_apply / 1e3)
     ach = BYTES_APPLY * n / (ms_apply / 1e3) / 1e9          # per GPU
-    h2d, d2h = 4 * n, (4 + 1 + 8) * n
     cores = os.cpu_count() or 1
     cpu_v, cpu_kind, cpu_per = cpu_arm(1 << 18, 1, 8)
     cpu_secs = sum(cpu_per)
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_apply_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    traffic, traffic_src = None, None
+    for name in ("r02_apply_traffic.json", "r01_apply_traffic.json"):       # ncu --set full capture of this kernel (not measured in-run)
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic_src = "profiles/" + name + " (ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch; constant, not re-measured by this run)"
+                break
+            except Exception:
+                pass
+
+    def frac(ms):
+        return BYTES_APPLY * n / (ms / 1e3) / 1e9 / peak
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_apply, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -449,20 +536,34 @@ def run_gpu(args):
                    "states_per_step_per_gpu": n, "state_bytes": 16, "action_dtype": "int32",
                    "prefix_plies": "U{0..%d}" % MAX_PREFIX,
                    "l2": "inputs larger than L2: every step has its own 16 MiB batch + 4 MiB actions (%d x 20 MiB)" % slots,
-                   "timing": "K launches in one CUDA graph between two events, barrier+sync both sides, best of 3, max over ranks",
-                   "parallelism": "independent shards x%d, no data-path collective" % world},
+                   "timing": "K launches in one CUDA graph on ONE stream (every step ordered after the previous one) between two events, barrier+sync both sides, best of 3, max over ranks",
+                   "parallelism": "independent shards x%d, no data-path collective" % world,
+                   "host_numa_cpus": numa_cpus},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": traffic, "kernel": "k_apply<ConnectFourRules,4>", "bytes_per_step": BYTES_APPLY,
-                     "peak_source": peak_src},
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_apply<ConnectFourRules,4>",
+                     "bytes_per_step": BYTES_APPLY, "peak_source": peak_src,
+                     "frac_2_streams": frac(ms_apply_s2 / K), "frac_4_streams": frac(ms_apply_s4 / K),
+                     "frac_64M_lanes": BYTES_APPLY * big_n / (ms_big / 1e3) / 1e9 / peak,
+                     "note": "1M lanes are 5.7 us of pure transfer per launch; back-to-back launches ordered on one stream pay a grid "
+                             "ramp + drain each (frac); the same K steps declared independent (different batches -> parallel graph "
+                             "branches) overlap them (frac_2_streams / frac_4_streams); one launch over 64M lanes (> L2) is frac_64M_lanes"},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                          "sample": "%d states x 8 passes, 1 thread, Clone excluded (%.2f s timed)" % (1 << 18, cpu_secs),
                          "host_cores": cores},
-        "e2e": {"value": world * n / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e, "call": "b2s_step_fused_host (pinned host actions in; mask, terminal, returns out)"},
+        "e2e": {"value": world * n / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n,
+                "ms_per_step": ms_e2e,
+                "call": "b2s_step_fused_host_compact (pinned host uint8 actions in; one status byte per lane out: terminal, outcome, next legal mask)",
+                "consistent_with_float_entry": e2e_consistent},
         "gpu_launches": K,
-        "extras": {"fused_step_steps_per_s": world * n / (ms_fused / 1e3), "fused_ms": ms_fused,
+        "extras": {"apply_2_streams_steps_per_s": world * n / (ms_apply_s2 / K / 1e3), "apply_2_streams_ms": ms_apply_s2 / K,
+                   "apply_4_streams_steps_per_s": world * n / (ms_apply_s4 / K / 1e3), "apply_4_streams_ms": ms_apply_s4 / K,
+                   "apply_64M_lanes_steps_per_s": world * big_n / (ms_big / 1e3), "apply_64M_lanes_ms": ms_big,
+                   "apply_64M_lanes_gbs": BYTES_APPLY * big_n / (ms_big / 1e3) / 1e9,
+                   "fused_step_steps_per_s": world * n / (ms_fused / 1e3), "fused_ms": ms_fused,
                    "fused_gbs": BYTES_FUSED * n / (ms_fused / 1e3) / 1e9,
                    "legal_mask_per_s": world * n / (ms_mask / 1e3), "legal_mask_ms": ms_mask,
+                   "e2e_float_entry": {"value": world * n / (ms_e2e_f32 / 1e3), "ms_per_step": ms_e2e_f32, "h2d_bytes_per_step": 4 * n,
+                                       "d2h_bytes_per_step": 13 * n, "call": "b2s_step_fused_host (int32 actions; mask words, terminal, float32 returns)"},
                    "launches_total_incl_setup": total_launches, "loops": loops, "cpu_reference_loops": cpu_loops()},
         "clocks": sampler.summary() if sampler else None,
     }
@@ -478,6 +579,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--deep-trees", type=int, default=8192, help="trees per GPU of the deep MCTS line")
+    ap.add_argument("--deep-sims", type=int, default=10000, help="simulations per tree of the deep MCTS line")
+    ap.add_argument("--cfr-iters", type=int, default=100000, help="CFRSolver iterations (BASELINE configs[3]: 100k)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

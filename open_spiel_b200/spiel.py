@@ -252,6 +252,15 @@ class BatchedState:
                                         terminal_h.data_ptr() if terminal_h is not None else None,
                                         returns_h.data_ptr() if returns_h is not None else None, n))
 
+    def step_host_compact(self, actions_h, status_h, mask_h=None, n=None):
+        """b2s_step_fused_host_compact: uint8 (0xFF = skip) or int32 actions in, one status byte per lane out
+        (bit 7 terminal; terminal: bits 0-1 outcome 0 draw / 1 player 0 / 2 player 1; else bits 0-6 the legal mask when
+        the game has <= 7 actions); mask_h optionally receives the full mask words."""
+        n = self._n(n)
+        ab = {torch.uint8: 1, torch.int32: 4}[actions_h.dtype]
+        check(lib().b2s_step_fused_host_compact(self._h, actions_h.data_ptr(), ab, status_h.data_ptr(),
+                                                mask_h.data_ptr() if mask_h is not None else None, n))
+
     def rollout(self, seed, lane_offset=0, n=None):
         n = self._n(n)
         rets = torch.empty((n, self.info.num_players), dtype=torch.float32, device=self._dev)
@@ -493,6 +502,15 @@ def mcts_search(batch, max_simulations, uct_c=2.0, n_rollouts=1, solve=True, see
                                 out["outcome_p0"].data_ptr(), out["best_action"].data_ptr(), out["sims_run"].data_ptr(),
                                 batch._stream()))
     return out
+
+
+def bind_host_to_device(device=0):
+    """Pins the calling thread to the CPUs of the GPU's NUMA node (b2s_bind_host_to_device); returns the CPU count,
+    or 0 when the topology cannot be read (containers without sysfs PCI entries)."""
+    n = C.c_int(0)
+    if lib().b2s_bind_host_to_device(int(device), C.byref(n)) != 0:
+        return 0
+    return n.value
 
 
 def mcts_nodes_used(batch):

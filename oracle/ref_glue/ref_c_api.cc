@@ -3,6 +3,7 @@
 // orc_* surface of oracle/oracle_c.cc so tests can drive the restatement and the real reference alike.
 #include <cstring>
 #include <memory>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -244,4 +245,54 @@ void* ref_deserialize_state(void* g, const char* text) {
   GUARD(return ((GameHolder*)g)->game->DeserializeState(text).release(), return nullptr);
 }
 
+
+// Replays n recorded lanes on the unmodified reference, `threads` at a time: lane i applies hist[i*L .. i*L+L) (entries
+// < 0 are skipped) from the initial state, then `final_action[i]` (if >= 0).  Outputs, any nullable:
+//   mask_before [n][W] u32  LegalActions() as bits just before the final action
+//   terminal [n] u8, cur_player [n] i8, returns [n][P] f32, mask_after [n][W] u32 after it
+//   obs_bits [n][OW] u32    ObservationTensor(0) != 0 as a bit string (OW = ceil(size / 32))
+// Returns the number of lanes on which the reference raised an error (illegal action), -1 on setup failure.
+long ref_replay_batch(void* g, long n, int L, const int32_t* hist, const int32_t* final_action, int W, int OW, int threads,
+                      uint32_t* mask_before, uint8_t* terminal, int8_t* cur_player, float* returns, uint32_t* mask_after,
+                      uint32_t* obs_bits) {
+  auto game = ((GameHolder*)g)->game;
+  const int P = game->NumPlayers();
+  int obs_size = 0;
+  GUARD(obs_size = game->ObservationTensorSize(), return -1);
+  if (threads < 1) threads = 1;
+  std::vector<long> bad(threads, 0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t) {
+    pool.emplace_back([&, t]() {
+      std::vector<float> obs(obs_size);
+      for (long i = n * t / threads; i < n * (t + 1) / threads; ++i) {
+        try {
+          std::unique_ptr<State> s = game->NewInitialState();
+          for (int k = 0; k < L; ++k) if (hist[i * L + k] >= 0) s->ApplyAction(hist[i * L + k]);
+          auto bits = [&](uint32_t* out) {
+            for (int w = 0; w < W; ++w) out[w] = 0;
+            for (Action a : s->LegalActions()) out[a >> 5] |= 1u << (a & 31);
+          };
+          if (mask_before) bits(mask_before + i * W);
+          if (final_action[i] >= 0) s->ApplyAction(final_action[i]);
+          if (terminal) terminal[i] = s->IsTerminal() ? 1 : 0;
+          if (cur_player) cur_player[i] = (int8_t)s->CurrentPlayer();
+          if (returns) { auto r = s->Returns(); for (int p = 0; p < P; ++p) returns[i * P + p] = (float)r[p]; }
+          if (mask_after) bits(mask_after + i * W);
+          if (obs_bits) {
+            s->ObservationTensor(0, absl::MakeSpan(obs));
+            for (int w = 0; w < OW; ++w) obs_bits[i * OW + w] = 0;
+            for (int e = 0; e < obs_size; ++e) if (obs[e] != 0.f) obs_bits[i * OW + (e >> 5)] |= 1u << (e & 31);
+          }
+        } catch (const std::exception&) {
+          ++bad[t];
+        }
+      }
+    });
+  }
+  for (auto& th : pool) th.join();
+  long total = 0;
+  for (long b : bad) total += b;
+  return total;
+}
 }  // extern "C"

@@ -57,6 +57,8 @@ def lib():
         L.ref_cfr_exploitability.argtypes = [vp, vp]
         L.ref_cfr_nash_conv.restype = C.c_double
         L.ref_cfr_nash_conv.argtypes = [vp, vp]
+        L.ref_replay_batch.restype = C.c_long
+        L.ref_replay_batch.argtypes = [vp, C.c_long, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
         L.ref_mcts_search.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, i64p,
                                       C.POINTER(C.c_int), dp, C.c_int, i64p, C.POINTER(C.c_int)]
         _LIB = L
@@ -317,3 +319,25 @@ def deserialize_state(game, text):
     ptr = L.ref_deserialize_state(game._g, text.encode())
     assert ptr, L.ref_last_error()
     return RefState(game, ptr)
+
+
+def replay_batch(game_string, hist, final_actions, mask_words, threads=0):
+    """Replays n recorded lanes on the unmodified reference (ref_replay_batch): hist int32 [n, L] (-1 = no move) then
+    final_actions int32 [n].  Returns dict of numpy arrays: mask_before / mask_after uint32 [n, W], terminal uint8 [n],
+    cur_player int8 [n], returns float32 [n, P], obs_bits uint32 [n, ceil(obs/32)] and the number of failed lanes."""
+    L = lib()
+    g = RefGame(game_string)
+    hist = np.ascontiguousarray(hist, dtype=np.int32)
+    fin = np.ascontiguousarray(final_actions, dtype=np.int32)
+    n, plies = hist.shape
+    P = L.ref_num_players(g._g)
+    OW = (L.ref_observation_tensor_size(g._g) + 31) // 32
+    out = {"mask_before": np.zeros((n, mask_words), np.uint32), "terminal": np.zeros(n, np.uint8), "cur_player": np.zeros(n, np.int8),
+           "returns": np.zeros((n, P), np.float32), "mask_after": np.zeros((n, mask_words), np.uint32),
+           "obs_bits": np.zeros((n, OW), np.uint32)}
+    threads = threads or min(len(os.sched_getaffinity(0)), 64)
+    bad = L.ref_replay_batch(g._g, n, plies, hist.ctypes.data, fin.ctypes.data, mask_words, OW, threads, out["mask_before"].ctypes.data,
+                             out["terminal"].ctypes.data, out["cur_player"].ctypes.data, out["returns"].ctypes.data,
+                             out["mask_after"].ctypes.data, out["obs_bits"].ctypes.data)
+    out["failed_lanes"] = int(bad)
+    return out
