@@ -95,7 +95,22 @@ struct Search {
   int n_rollouts;
   bool solve;
   uint32_t expansions = 0;
-  long nodes = 1;
+  int nodes = 1;                   // MCTSBot::nodes_ (mcts.h:209)
+  int max_nodes = 1;               // MCTSBot::max_nodes_ = (max_memory_mb << 20) / sizeof(SearchNode) + 1; <= 1: never collect
+  int gc_limit = 5;                // MCTSBot::gc_limit_, starts at MIN_GC_LIMIT (mcts.cc:37, 355)
+  int gc_runs = 0;
+
+  // MCTSBot::GarbageCollect (mcts.cc:469-482): drop the children of every node explored fewer than gc_limit times
+  void GarbageCollect(Node* node) {
+    if (node->children.empty()) return;
+    bool clear_children = node->explore_count < gc_limit;
+    for (Node& child : node->children) GarbageCollect(&child);
+    if (clear_children) {
+      nodes -= (int)node->children.capacity();
+      node->children.clear();
+      node->children.shrink_to_fit();
+    }
+  }
 
   std::vector<double> Evaluate(const State& state, uint32_t sim) {        // mcts.cc:43-72
     std::vector<double> result;
@@ -132,7 +147,7 @@ struct Search {
         int player = ws->CurrentPlayer();
         cur->children.reserve(legal.size());
         for (auto a : legal) { Node c; c.action = a; c.player = player; cur->children.push_back(c); }
-        nodes += (long)cur->children.capacity();
+        nodes += (int)cur->children.capacity();
       }
       Node* chosen = nullptr;
       double max_value = -std::numeric_limits<double>::infinity();
@@ -184,6 +199,12 @@ struct Search {
         }
       }
       if (!root->outcome.empty() || root->children.size() == 1) { ++i; break; }
+      if (max_nodes > 1 && nodes >= max_nodes) {                          // mcts.cc:441-463
+        GarbageCollect(root);
+        ++gc_runs;
+        gc_limit *= (nodes > max_nodes / 2 ? 1.25 : 0.9);                 // int *= double, as the reference's int gc_limit_
+        gc_limit = std::max(5, gc_limit);
+      }
     }
     return i;
   }
@@ -196,11 +217,12 @@ extern "C" {
 
 // One MCTSearch from `state` for tree #tree_index.  Root children are reported in child (shuffled) order:
 // child_actions/visits/rewards/outcome_p0 (NaN when unproven).  Returns the number of root children.
-int orc_mcts_search(void* game, void* state, double uct_c, int max_simulations, int n_rollouts, int solve,
-                    uint64_t seed, uint64_t tree_index, int64_t* child_actions, int* child_visits,
-                    double* child_rewards, double* child_outcome_p0, int cap, int64_t* best_action,
-                    int* root_visits, double* root_outcome_p0, long* nodes_out, int* sims_run,
-                    int child_selection_policy, int rng_mode) {
+// max_nodes = MCTSBot::max_nodes_ (<= 1: no garbage collection); gc_runs_out (nullable) = collections performed.
+int orc_mcts_search_gc(void* game, void* state, double uct_c, int max_simulations, int n_rollouts, int solve,
+                       uint64_t seed, uint64_t tree_index, int64_t* child_actions, int* child_visits,
+                       double* child_rewards, double* child_outcome_p0, int cap, int64_t* best_action,
+                       int* root_visits, double* root_outcome_p0, long* nodes_out, int* sims_run,
+                       int child_selection_policy, int rng_mode, int max_nodes, int* gc_runs_out) {
   using namespace oracle;
   Game* g = (Game*)game;
   State* s = (State*)state;
@@ -212,6 +234,7 @@ int orc_mcts_search(void* game, void* state, double uct_c, int max_simulations, 
   srch.solve = solve != 0;
   srch.puct = child_selection_policy == 1;
   srch.rng_mode = rng_mode;
+  srch.max_nodes = max_nodes;
   if (rng_mode == 1) { srch.bot_rng.seed((uint32_t)seed); srch.eval_rng.seed((uint32_t)seed); }
   Node root;
   root.player = s->CurrentPlayer();
@@ -235,7 +258,18 @@ int orc_mcts_search(void* game, void* state, double uct_c, int max_simulations, 
   if (root_outcome_p0) *root_outcome_p0 = root.outcome.empty() ? std::nan("") : root.outcome[0];
   if (nodes_out) *nodes_out = srch.nodes;
   if (sims_run) *sims_run = ran;
+  if (gc_runs_out) *gc_runs_out = srch.gc_runs;
   return n;
+}
+
+int orc_mcts_search(void* game, void* state, double uct_c, int max_simulations, int n_rollouts, int solve,
+                    uint64_t seed, uint64_t tree_index, int64_t* child_actions, int* child_visits,
+                    double* child_rewards, double* child_outcome_p0, int cap, int64_t* best_action,
+                    int* root_visits, double* root_outcome_p0, long* nodes_out, int* sims_run,
+                    int child_selection_policy, int rng_mode) {
+  return orc_mcts_search_gc(game, state, uct_c, max_simulations, n_rollouts, solve, seed, tree_index, child_actions, child_visits,
+                            child_rewards, child_outcome_p0, cap, best_action, root_visits, root_outcome_p0, nodes_out, sims_run,
+                            child_selection_policy, rng_mode, 1, nullptr);
 }
 
 }  // extern "C"

@@ -141,13 +141,24 @@ double ref_cfr_nash_conv(void* g, void* c) {
 
 // ---- MCTSBot (algorithms/mcts.h:149-230) --------------------------------------------------------------------
 // Runs MCTSearch from `state` and reports the root's children (action, visits, total reward, proven outcome flag).
+int ref_mcts_search_mb(void* g, void* state, double uct_c, int max_simulations, int n_rollouts, int solve, int seed,
+                       int64_t* child_actions, int* child_visits, double* child_rewards, int cap, int64_t* best_action,
+                       int* root_visits, int max_memory_mb);
 int ref_mcts_search(void* g, void* state, double uct_c, int max_simulations, int n_rollouts, int solve, int seed,
                     int64_t* child_actions, int* child_visits, double* child_rewards, int cap, int64_t* best_action,
                     int* root_visits) {
+  return ref_mcts_search_mb(g, state, uct_c, max_simulations, n_rollouts, solve, seed, child_actions, child_visits, child_rewards, cap,
+                            best_action, root_visits, 1000);
+}
+// sizeof(SearchNode) decides MCTSBot::max_nodes_ = (max_memory_mb << 20) / sizeof(SearchNode) + 1 (mcts.cc:214)
+int ref_sizeof_search_node() { return (int)sizeof(open_spiel::algorithms::SearchNode); }
+int ref_mcts_search_mb(void* g, void* state, double uct_c, int max_simulations, int n_rollouts, int solve, int seed,
+                       int64_t* child_actions, int* child_visits, double* child_rewards, int cap, int64_t* best_action,
+                       int* root_visits, int max_memory_mb) {
   try {
     auto game = ((GameHolder*)g)->game;
     auto evaluator = std::make_shared<open_spiel::algorithms::RandomRolloutEvaluator>(n_rollouts, seed);
-    open_spiel::algorithms::MCTSBot bot(*game, evaluator, uct_c, max_simulations, /*max_memory_mb=*/1000, solve != 0, seed,
+    open_spiel::algorithms::MCTSBot bot(*game, evaluator, uct_c, max_simulations, max_memory_mb, solve != 0, seed,
                                         /*verbose=*/false);
     std::unique_ptr<open_spiel::algorithms::SearchNode> root = bot.MCTSearch(*(State*)state);
     int n = (int)root->children.size();

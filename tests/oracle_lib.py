@@ -186,24 +186,24 @@ class OracleState:
 
 
 def oracle_mcts(state, uct_c, max_simulations, n_rollouts=1, solve=True, seed=0, tree_index=0, puct=False,
-                reference_rng=False):
+                reference_rng=False, max_nodes=1):
     """oracle/algorithms/mcts.cc: one search; returns dict(children=[(action, visits, reward, outcome_p0)], ...)."""
     import math
     L = lib()
-    L.orc_mcts_search.restype = C.c_int
-    L.orc_mcts_search.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
-                                  C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
-                                  C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_double),
-                                  C.POINTER(C.c_long), C.POINTER(C.c_int), C.c_int, C.c_int]
+    L.orc_mcts_search_gc.restype = C.c_int
+    L.orc_mcts_search_gc.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_long), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     cap = state.game.num_distinct_actions + 4
     acts, vis = (C.c_int64 * cap)(), (C.c_int * cap)()
     rew, outc = (C.c_double * cap)(), (C.c_double * cap)()
-    best, rv, ro, nodes, ran = C.c_int64(), C.c_int(), C.c_double(), C.c_long(), C.c_int()
-    n = L.orc_mcts_search(state.game._g, state._s, uct_c, max_simulations, n_rollouts, int(solve), seed, tree_index,
-                          acts, vis, rew, outc, cap, C.byref(best), C.byref(rv), C.byref(ro), C.byref(nodes), C.byref(ran), int(puct),
-                          int(reference_rng))
+    best, rv, ro, nodes, ran, gcs = C.c_int64(), C.c_int(), C.c_double(), C.c_long(), C.c_int(), C.c_int()
+    n = L.orc_mcts_search_gc(state.game._g, state._s, uct_c, max_simulations, n_rollouts, int(solve), seed, tree_index,
+                             acts, vis, rew, outc, cap, C.byref(best), C.byref(rv), C.byref(ro), C.byref(nodes), C.byref(ran), int(puct),
+                             int(reference_rng), int(max_nodes), C.byref(gcs))
     return {"children": [(acts[i], vis[i], rew[i], outc[i]) for i in range(n)], "best_action": best.value,
-            "root_visits": rv.value, "root_outcome_p0": ro.value, "nodes": nodes.value, "sims_run": ran.value}
+            "root_visits": rv.value, "root_outcome_p0": ro.value, "nodes": nodes.value, "sims_run": ran.value, "gc_runs": gcs.value}
 
 
 def oracle_record_trajectory(state, seed, lane, T, forced=None):

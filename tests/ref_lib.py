@@ -197,16 +197,22 @@ class RefCFR:
         return lib().ref_cfr_nash_conv(self.game._g, self._c)
 
 
-def ref_mcts(game, state, uct_c, max_simulations, n_rollouts=1, solve=True, seed=0):
+def ref_mcts(game, state, uct_c, max_simulations, n_rollouts=1, solve=True, seed=0, max_memory_mb=1000):
     """The unmodified reference's MCTSBot::MCTSearch (RandomRolloutEvaluator); returns root children stats."""
     L = lib()
+    L.ref_mcts_search_mb.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.c_int]
     cap = game.num_distinct_actions + 4
     acts, vis, rew = (C.c_int64 * cap)(), (C.c_int * cap)(), (C.c_double * cap)()
     best, rv = C.c_int64(), C.c_int()
-    n = L.ref_mcts_search(game._g, state._s, uct_c, max_simulations, n_rollouts, int(solve), seed, acts, vis, rew, cap,
-                          C.byref(best), C.byref(rv))
+    n = L.ref_mcts_search_mb(game._g, state._s, uct_c, max_simulations, n_rollouts, int(solve), seed, acts, vis, rew, cap,
+                             C.byref(best), C.byref(rv), int(max_memory_mb))
     assert n >= 0, L.ref_last_error()
     return {"children": [(acts[i], vis[i], rew[i]) for i in range(n)], "best_action": best.value, "root_visits": rv.value}
+
+
+def sizeof_search_node():
+    return lib().ref_sizeof_search_node()
 
 
 def ref_record_batched_trajectory(game, batch_size, seed, T):

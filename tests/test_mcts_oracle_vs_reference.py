@@ -47,3 +47,21 @@ def test_oracle_mcts_equals_reference_mctsbot_bitwise(gs, prefix, sims, nroll, s
     assert [c[2] for c in mine["children"]] == [c[2] for c in ref["children"]]          # total rewards, exact doubles
     assert mine["best_action"] == ref["best_action"]
     assert mine["root_visits"] == ref["root_visits"]
+
+
+@pytest.mark.parametrize("gs,sims,seed", [("connect_four", 12000, 3), ("hex(board_size=4)", 9000, 5)])
+def test_oracle_garbage_collection_equals_reference_bitwise(gs, sims, seed):
+    """MCTSBot's node budget (max_memory_mb -> max_nodes_, mcts.cc:205-231) and GarbageCollect (mcts.cc:441-482): with
+    max_memory_mb = 1 the tree is collected several times inside these searches; the oracle must prune the same nodes at
+    the same simulations (same gc_limit_ trajectory), i.e. reproduce the final root statistics bit for bit."""
+    rg, og = ref_lib.RefGame(gs), OracleGame(gs)
+    rs, os_ = rg.new_initial_state(), og.new_initial_state()
+    max_nodes = (1 << 20) // ref_lib.sizeof_search_node() + 1
+    ref = ref_lib.ref_mcts(rg, rs, 2.0, sims, 1, False, seed, max_memory_mb=1)
+    mine = oracle_mcts(os_, 2.0, sims, 1, False, seed, reference_rng=True, max_nodes=max_nodes)
+    assert mine["gc_runs"] >= 2, mine["gc_runs"]
+    assert mine["children"] and [c[:3] for c in mine["children"]] == [tuple(c) for c in ref["children"]]
+    assert mine["best_action"] == ref["best_action"] and mine["root_visits"] == ref["root_visits"]
+    # and the budget changes the search: without it the statistics differ
+    free = oracle_mcts(os_, 2.0, sims, 1, False, seed, reference_rng=True)
+    assert free["gc_runs"] == 0 and [c[:3] for c in free["children"]] != [c[:3] for c in mine["children"]]
