@@ -210,9 +210,10 @@ int b2s_record_trajectories(void* batch, uint64_t seed, int64_t lane_offset, int
  * MCTS-Solver, run entirely on the device.  Field meaning = the MCTSBot constructor arguments
  * (mcts.h:161-169): uct_c, max_simulations, solve, seed; n_rollouts = RandomRolloutEvaluator's.
  * Deterministic perfect-information games only (tic_tac_toe, connect_four, breakthrough, hex, go).
- * The reference's max_memory_mb garbage collection is not reproduced: max_nodes_total bounds the node
- * arena shared by all trees (0 = size from free device memory); a tree that cannot allocate stops and is
- * counted by b2s_error_count. */
+ * Every tree owns an arena of 16-byte nodes (24 bytes when n_rollouts is not a power of two); max_nodes_per_tree is the
+ * reference's node budget with its garbage collection, max_nodes_total the physical arena size (0 = derived).  A tree
+ * that cannot allocate stops and is counted by b2s_error_count.  Chance nodes in the tree, Dirichlet noise and custom
+ * evaluators are not device features (the host adapters route such bots to the stock MCTSBot). */
 enum { B2S_MCTS_UCT = 0, B2S_MCTS_PUCT = 1 };   /* UCTValue mcts.cc:90-101 / PUCTValue :103-112 (uniform prior, :74-87) */
 typedef struct b2s_mcts_config {
   int32_t max_simulations;
@@ -222,7 +223,12 @@ typedef struct b2s_mcts_config {
   double uct_c;
   uint64_t seed;
   int64_t tree_index_offset;   /* tree i uses random stream (seed, i + tree_index_offset): shard roots across GPUs */
-  int64_t max_nodes_total;
+  int64_t max_nodes_total;     /* physical arena nodes over all trees (0 = size from max_nodes_per_tree / free memory) */
+  int64_t max_nodes_per_tree;  /* MCTSBot::max_nodes_ = (max_memory_mb << 20) / sizeof(SearchNode) + 1 (mcts.cc:214; 80-byte
+                                  SearchNode): when a tree's node count reaches it the tree is garbage-collected exactly as
+                                  MCTSBot::GarbageCollect does (mcts.cc:441-482).  0 / 1 = never (max_memory_mb = 0) */
+  double  max_wall_clock_time; /* seconds; > 0: a tree stops starting simulations once this much time has passed (mcts.cc:362-365) */
+  int32_t* gc_runs_d;          /* nullable device output [n_trees]: collections performed per tree */
 } b2s_mcts_config;
 /* MCTSBot::MCTSearch (mcts.cc:353-467) from lanes [0, n_trees) of roots_batch.  Outputs (device):
  * visit_counts_d [n][A] int32 and total_reward_d [n][A] double = explore_count / total_reward of the root's
@@ -233,7 +239,7 @@ typedef struct b2s_mcts_config {
 int b2s_mcts_search(void* roots_batch, int64_t n_trees, const b2s_mcts_config* cfg, int32_t* visit_counts_d,
                     double* total_reward_d, float* outcome_p0_d, int32_t* best_action_d, int32_t* sims_run_d,
                     void* stream);
-/* Arena nodes (32 B each) consumed by the last b2s_mcts_search on this batch. */
+/* Arena nodes consumed by the last b2s_mcts_search on this batch (sum over trees of the arena high-water marks). */
 int b2s_mcts_nodes_used(void* roots_batch, int64_t* nodes);
 
 /* ---- CFR ----------------------------------------------------------------------------------- */

@@ -39,7 +39,8 @@ class GameInfo(C.Structure):
 class MctsConfig(C.Structure):
     _fields_ = [("max_simulations", C.c_int32), ("n_rollouts", C.c_int32), ("solve", C.c_int32),
                 ("child_selection_policy", C.c_int32), ("uct_c", C.c_double), ("seed", C.c_uint64),
-                ("tree_index_offset", C.c_int64), ("max_nodes_total", C.c_int64)]
+                ("tree_index_offset", C.c_int64), ("max_nodes_total", C.c_int64), ("max_nodes_per_tree", C.c_int64),
+                ("max_wall_clock_time", C.c_double), ("gc_runs_d", C.c_void_p)]
 
 
 class TrajectoryOut(C.Structure):

@@ -51,7 +51,8 @@ B200MCTSBot::B200MCTSBot(const Game& game, int n_rollouts, double uct_c, int max
   cfg_.child_selection_policy = policy == algorithms::ChildSelectionPolicy::PUCT ? B2S_MCTS_PUCT : B2S_MCTS_UCT;
   cfg_.uct_c = uct_c;
   cfg_.seed = (uint64_t)seed;
-  cfg_.max_nodes_total = max_memory_mb > 0 ? (max_memory_mb << 20) / 32 : 0;     // arena nodes are 32 bytes
+  // MCTSBot::max_nodes_ (mcts.cc:214): the node budget that triggers the garbage collector
+  cfg_.max_nodes_per_tree = max_memory_mb > 0 ? (max_memory_mb << 20) / (int64_t)sizeof(algorithms::SearchNode) + 1 : 0;
   b200_game_ = B200Game::Create(game.GetType(), game.GetParameters());
   if (!b200_game_) SpielFatalError("b200: " + game.ToString() + " does not fit the packed device layouts");
   Check(b2s_batch_create(gid_, &params_, 1, 0, &batch_));

@@ -49,7 +49,7 @@ struct Batch {
   // MCTS scratch (b2s_mcts_search): work lanes, log table, node arena
   void* mcts_work = nullptr; u64* mcts_hist = nullptr; long long mcts_work_cap = 0;
   double* mcts_log = nullptr; int mcts_log_n = 0;
-  MctsNode* mcts_pool = nullptr; unsigned long long mcts_pool_cap = 0; unsigned long long* mcts_top = nullptr;
+  void* mcts_pool = nullptr; unsigned long long mcts_pool_bytes = 0; unsigned long long* mcts_top = nullptr;
   Ctx ctx() const { Ctx c; c.planes = planes; c.cap = cap; c.hist = hist; c.err = err; return c; }
   ~Batch() {
     if (planes) cudaFree(planes);
@@ -492,6 +492,7 @@ int b2s_mcts_search(void* roots_batch, int64_t n_trees, const b2s_mcts_config* c
   if (int r = check(roots_batch, n_trees)) return r;
   if (!cfg || !visit_counts_d || !total_reward_d || !best_action_d) return fail("mcts: null argument");
   if (cfg->max_simulations < 1 || cfg->n_rollouts < 1) return fail("mcts: max_simulations and n_rollouts must be >= 1");
+  if (cfg->max_wall_clock_time < 0 || cfg->max_nodes_per_tree < 0) return fail("mcts: negative budget");
   if (cfg->child_selection_policy != B2S_MCTS_UCT && cfg->child_selection_policy != B2S_MCTS_PUCT)
     return fail("mcts: unknown child_selection_policy");
   if (n_trees == 0) return 0;
@@ -520,37 +521,53 @@ int b2s_mcts_search(void* roots_batch, int64_t n_trees, const b2s_mcts_config* c
     CU(cudaMemcpy(B->mcts_log, t.data(), sizeof(double) * need, cudaMemcpyHostToDevice));
     B->mcts_log_n = need;
   }
-  // node arena: roots + children; sized by the caller or from free memory
-  unsigned long long want = (unsigned long long)cfg->max_nodes_total;
-  if (want == 0) {
-    unsigned long long worst = (unsigned long long)n_trees * (1ull + (unsigned long long)cfg->max_simulations * B->info.num_distinct_actions);
+  // node arenas, one per tree (mcts.cuh): nodes_per_tree slots of 16 B (n_rollouts a power of two) or 24 B
+  const unsigned long long A = (unsigned long long)B->info.num_distinct_actions;
+  const long long work_units = (long long)cfg->max_simulations * cfg->n_rollouts;
+  const int compact = (cfg->n_rollouts & (cfg->n_rollouts - 1)) == 0 && work_units < (1ll << 30);
+  const size_t node_bytes = compact ? sizeof(MctsNodeC) : sizeof(MctsNodeW);
+  unsigned long long per_tree;
+  if (cfg->max_nodes_total > 0) {
+    per_tree = (unsigned long long)cfg->max_nodes_total / (unsigned long long)n_trees;
+  } else {
+    const unsigned long long worst = 2ull + (unsigned long long)cfg->max_simulations * A;      // one expansion per simulation at most
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    unsigned long long fit = (unsigned long long)((free_b + B->mcts_pool_cap * sizeof(MctsNode)) * 0.6 / sizeof(MctsNode));
-    want = worst < fit ? worst : fit;
+    const unsigned long long fit = (unsigned long long)((free_b + B->mcts_pool_bytes) * 0.6 / node_bytes) / (unsigned long long)n_trees;
+    per_tree = worst < fit ? worst : fit;
+    if (cfg->max_nodes_per_tree > 1) {
+      // the budget is logical (MCTSBot::nodes_, live nodes <= budget + one expansion); blocks freed by the collector are reused
+      // by exact size (a pruned node re-expands to the same number of children) or split, never coalesced, so the arena is
+      // twice the budget; a tree that still cannot allocate stops and is reported by b2s_error_count
+      const unsigned long long want = 2ull * (unsigned long long)cfg->max_nodes_per_tree + 8 * A + 64;
+      if (want < per_tree) per_tree = want;
+    }
   }
-  if (want < (unsigned long long)n_trees * 2) return fail("mcts: node arena too small");
-  if (B->mcts_pool_cap < want) {
+  if (per_tree > 0xffffffffull) per_tree = 0xffffffffull;
+  if (per_tree < A + 2) return fail("mcts: node arena too small (max_nodes_total / free memory)");
+  if (cfg->max_nodes_per_tree > 0x7fffffffll) return fail("mcts: max_nodes_per_tree out of range");
+  const unsigned long long want_bytes = per_tree * (unsigned long long)n_trees * node_bytes;
+  if (B->mcts_pool_bytes < want_bytes) {
     if (B->mcts_pool) cudaFree(B->mcts_pool);
-    B->mcts_pool = nullptr; B->mcts_pool_cap = 0;
-    CU(cudaMalloc((void**)&B->mcts_pool, sizeof(MctsNode) * want));
-    B->mcts_pool_cap = want;
+    B->mcts_pool = nullptr; B->mcts_pool_bytes = 0;
+    CU(cudaMalloc(&B->mcts_pool, want_bytes));
+    B->mcts_pool_bytes = want_bytes;
   }
   if (!B->mcts_top) CU(cudaMalloc((void**)&B->mcts_top, sizeof(unsigned long long)));
-  unsigned long long top0 = (unsigned long long)n_trees;
-  CU(cudaMemcpyAsync(B->mcts_top, &top0, sizeof top0, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(B->mcts_top, 0, sizeof(unsigned long long), st));
   MctsArgs a;
   memset(&a, 0, sizeof a);
   a.sims = cfg->max_simulations; a.n_rollouts = cfg->n_rollouts; a.solve = cfg->solve; a.uct_c = cfg->uct_c;
   a.puct = cfg->child_selection_policy == B2S_MCTS_PUCT;
+  a.max_nodes = (int)cfg->max_nodes_per_tree; a.max_seconds = cfg->max_wall_clock_time;
   a.seed = cfg->seed; a.tree_offset = cfg->tree_index_offset; a.log_table = B->mcts_log;
-  a.pool = B->mcts_pool; a.pool_top = B->mcts_top; a.pool_cap = B->mcts_pool_cap;
+  a.pool = B->mcts_pool; a.nodes_per_tree = per_tree; a.nodes_used = B->mcts_top; a.compact = compact;
   a.visits_out = visit_counts_d; a.reward_out = total_reward_d; a.outcome_out = outcome_p0_d;
-  a.best_out = best_action_d; a.sims_out = sims_run_d; a.err = B->err;
+  a.best_out = best_action_d; a.sims_out = sims_run_d; a.gc_out = cfg->gc_runs_d; a.err = B->err;
   const char* e = B->ops->mcts(B->ctx(), work, n_trees, a, st);
   if (e) return fail(e);
   if (int r = post()) return r;
-  CU(cudaStreamSynchronize(st));          // top0 lives on this stack frame; the search is a long-running call anyway
+  CU(cudaStreamSynchronize(st));          // the search is a long-running call; results are ready on return
   return 0;
 }
 

@@ -601,16 +601,22 @@ template <class R>
 const char* GameOpsT<R>::mcts(const Ctx& roots, const Ctx& work, long long n, const MctsArgs& args, cudaStream_t st) {
   if constexpr (R::kMaxPath > 0) {
     if (info.max_game_length + 2 > R::kMaxPath) return "mcts: max_game_length too large for the device search path stack";
+    if (info.min_utility != -1.0 || info.max_utility != 1.0) return "mcts: the device search needs win / loss / draw returns";
     if (n <= 0) return nullptr;
     MctsArgs a = args;
     a.num_actions = info.num_distinct_actions;
     a.mask_words = info.mask_words;
     a.max_plies = info.max_game_length + 4;
     a.max_utility = info.max_utility;
+    const unsigned grid = (unsigned)((n + 127) / 128);
     // many trees: cap registers (6 CTAs of 128 threads per SM) so more warps are resident; few trees (deep
     // searches are memory-limited to a few thousand roots): let the compiler keep everything in registers
-    if (n >= 100000) k_mcts<R, R::kMaxPath, 6><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(roots, work, cfg, a, n);
-    else k_mcts<R, R::kMaxPath, 4><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(roots, work, cfg, a, n);
+    if (a.compact) {
+      if (n >= 100000) k_mcts<R, StatsC, R::kMaxPath, 6><<<grid, 128, 0, st>>>(roots, work, cfg, a, n);
+      else k_mcts<R, StatsC, R::kMaxPath, 4><<<grid, 128, 0, st>>>(roots, work, cfg, a, n);
+    } else {
+      k_mcts<R, StatsW, R::kMaxPath, 4><<<grid, 128, 0, st>>>(roots, work, cfg, a, n);
+    }
     ++g_launches;
     return nullptr;
   } else {

@@ -29,6 +29,7 @@ struct GoRules {
   static constexpr int kMaskWords = 3;     // 81 points + pass
   static constexpr int kPlayers = 2;
   static constexpr int kMaxPath = 176;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
+  static constexpr int kMaxLegal = 82;   // most legal actions any state can have (MCTS children block size)
   static constexpr int kIlp = 1;
   static constexpr int kMinBlocks = 4;
   static constexpr bool kHasInfoState = false;

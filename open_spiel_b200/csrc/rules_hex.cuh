@@ -17,6 +17,7 @@ struct HexRules {
   static constexpr int kMaskWords = 4;     // up to 121 cells + swap
   static constexpr int kPlayers = 2;
   static constexpr int kMaxPath = 128;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
+  static constexpr int kMaxLegal = 122;   // most legal actions any state can have (MCTS children block size)
   static constexpr int kIlp = 1;
   static constexpr int kMinBlocks = 4;
   static constexpr bool kHasInfoState = false;

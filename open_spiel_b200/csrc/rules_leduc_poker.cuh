@@ -17,6 +17,7 @@ struct LeducRules {
   static constexpr int kMaskWords = 1;
   static constexpr int kPlayers = 2;
   static constexpr int kMaxPath = 0;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
+  static constexpr int kMaxLegal = 6;   // most legal actions any state can have (MCTS children block size)
   static constexpr int kIlp = 2;
   static constexpr int kMinBlocks = 4;
   static constexpr bool kHasInfoState = true;

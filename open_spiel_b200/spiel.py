@@ -481,10 +481,12 @@ class ChildSelectionPolicy:
 
 
 def mcts_search(batch, max_simulations, uct_c=2.0, n_rollouts=1, solve=True, seed=0, tree_index_offset=0,
-                n_trees=None, max_nodes_total=0, child_selection_policy=ChildSelectionPolicy.UCT):
+                n_trees=None, max_nodes_total=0, child_selection_policy=ChildSelectionPolicy.UCT, max_nodes_per_tree=0,
+                max_wall_clock_time=0.0):
     """Batched MCTSBot.mcts_search (python/pybind11/bots.cc:129-149 -> algorithms/mcts.cc:353-467) over the lanes of
     `batch`.  Returns dict of device tensors: visits [n, A] int32, total_reward [n, A] float64, outcome_p0 [n, A]
-    float32 (NaN = unproven), best_action [n] int32, sims_run [n] int32."""
+    float32 (NaN = unproven), best_action [n] int32, sims_run [n] int32, gc_runs [n] int32.  max_nodes_per_tree is
+    MCTSBot's node budget max_nodes_ (garbage collection as mcts.cc:441-482), max_wall_clock_time its time budget."""
     from ._lib import MctsConfig
     n = batch.n if n_trees is None else int(n_trees)
     A = batch.info.num_distinct_actions
@@ -495,9 +497,11 @@ def mcts_search(batch, max_simulations, uct_c=2.0, n_rollouts=1, solve=True, see
         "outcome_p0": torch.empty((n, A), dtype=torch.float32, device=dev),
         "best_action": torch.empty((n,), dtype=torch.int32, device=dev),
         "sims_run": torch.empty((n,), dtype=torch.int32, device=dev),
+        "gc_runs": torch.empty((n,), dtype=torch.int32, device=dev),
     }
     cfg = MctsConfig(int(max_simulations), int(n_rollouts), int(bool(solve)), int(child_selection_policy), float(uct_c), int(seed),
-                     int(tree_index_offset), int(max_nodes_total))
+                     int(tree_index_offset), int(max_nodes_total), int(max_nodes_per_tree), float(max_wall_clock_time),
+                     out["gc_runs"].data_ptr())
     check(lib().b2s_mcts_search(batch._h, n, C.byref(cfg), out["visits"].data_ptr(), out["total_reward"].data_ptr(),
                                 out["outcome_p0"].data_ptr(), out["best_action"].data_ptr(), out["sims_run"].data_ptr(),
                                 batch._stream()))
@@ -537,7 +541,8 @@ class MCTSBot:
             raise B2SError("the device MCTSBot supports RandomRolloutEvaluator only")
         self.game, self.evaluator = game, evaluator
         self.uct_c, self.max_simulations, self.solve, self.seed = float(uct_c), int(max_simulations), bool(solve), int(seed)
-        self.max_nodes = (int(max_memory_mb) << 20) // 32        # arena nodes are 32 B
+        # MCTSBot::max_nodes_ = (max_memory_mb << 20) / sizeof(SearchNode) + 1, sizeof(SearchNode) = 80 (mcts.cc:214)
+        self.max_nodes = ((int(max_memory_mb) << 20) // 80 + 1) if max_memory_mb else 0
         self.child_selection_policy = int(child_selection_policy)
         self._searches = 0
 
@@ -546,7 +551,7 @@ class MCTSBot:
         random stream (seed, tree index = number of earlier searches), like the reference bot's advancing rng_."""
         self._searches += 1
         return mcts_search(state._b, self.max_simulations, self.uct_c, self.evaluator.n_rollouts, self.solve, self.seed,
-                           tree_index_offset=self._searches - 1, n_trees=1, max_nodes_total=self.max_nodes,
+                           tree_index_offset=self._searches - 1, n_trees=1, max_nodes_per_tree=self.max_nodes,
                            child_selection_policy=self.child_selection_policy)
 
     def step(self, state):

@@ -168,23 +168,38 @@ struct EmuT : Emu {
     }
     std::vector<double> logt((size_t)mc.max_simulations + 2, 0.0);
     for (size_t k = 1; k < logt.size(); ++k) logt[k] = std::log((double)k);
-    unsigned long long cap_nodes = mc.max_nodes_total > 0 ? (unsigned long long)mc.max_nodes_total
-                                                          : (unsigned long long)n * ((unsigned long long)mc.max_simulations * info.num_distinct_actions + 2);
-    std::vector<MctsNode> pool(cap_nodes);
-    unsigned long long top = (unsigned long long)n;
+    // arena sizing as api.cu (b2s_mcts_search)
+    const unsigned long long A = (unsigned long long)info.num_distinct_actions;
+    const int compact = (mc.n_rollouts & (mc.n_rollouts - 1)) == 0 && (long long)mc.max_simulations * mc.n_rollouts < (1ll << 30);
+    unsigned long long per_tree;
+    if (mc.max_nodes_total > 0) per_tree = (unsigned long long)mc.max_nodes_total / (unsigned long long)n;
+    else {
+      per_tree = 2ull + (unsigned long long)mc.max_simulations * A;
+      if (mc.max_nodes_per_tree > 1) {
+        unsigned long long want = 2ull * (unsigned long long)mc.max_nodes_per_tree + 8 * A + 64;
+        if (want < per_tree) per_tree = want;
+      }
+    }
+    const size_t node_bytes = compact ? sizeof(MctsNodeC) : sizeof(MctsNodeW);
+    std::vector<char> pool((size_t)per_tree * (size_t)n * node_bytes + 16);
+    unsigned long long used = 0;
+    std::vector<int> gc(n, 0);
     MctsArgs a;
     memset(&a, 0, sizeof a);
     a.sims = mc.max_simulations; a.n_rollouts = mc.n_rollouts; a.solve = mc.solve; a.uct_c = mc.uct_c;
     a.puct = mc.child_selection_policy == B2S_MCTS_PUCT;
+    a.max_nodes = (int)mc.max_nodes_per_tree; a.max_seconds = 0;
     a.seed = mc.seed; a.tree_offset = mc.tree_index_offset; a.log_table = logt.data();
-    a.pool = pool.data(); a.pool_top = &top; a.pool_cap = cap_nodes;
-    a.visits_out = visits; a.reward_out = reward; a.outcome_out = outcome; a.best_out = best; a.sims_out = sims_run; a.err = &err;
+    a.pool = (void*)(((uintptr_t)pool.data() + 15) & ~(uintptr_t)15); a.nodes_per_tree = per_tree; a.nodes_used = &used; a.compact = compact;
+    a.visits_out = visits; a.reward_out = reward; a.outcome_out = outcome; a.best_out = best; a.sims_out = sims_run;
+    a.gc_out = mc.gc_runs_d ? mc.gc_runs_d : gc.data(); a.err = &err;
     a.num_actions = info.num_distinct_actions; a.mask_words = info.mask_words;
     a.max_plies = info.max_game_length + 4; a.max_utility = info.max_utility;
     blockDim.x = 1; threadIdx.x = 0;
     for (long long t = 0; t < n; ++t) {
       blockIdx.x = (unsigned)t;
-      k_mcts<R, R::kMaxPath, 4>(ctx(), work, cfg, a, n);
+      if (compact) k_mcts<R, StatsC, R::kMaxPath, 4>(ctx(), work, cfg, a, n);
+      else k_mcts<R, StatsW, R::kMaxPath, 4>(ctx(), work, cfg, a, n);
     }
     return 0;
   }

@@ -50,6 +50,25 @@ CASES = [
     ("go(board_size=5)", 32, 10, 150, 1, True),
     ("go(board_size=9)", 16, 30, 40, 1, True),
     ("go(board_size=3,komi=0.5)", 32, 4, 300, 1, True),
+    # mid-game roots on tiny boards: positional superko decides most playouts and tree descents, so the root's hash history
+    # must reach the search's work lanes (only the host-compiled kernel body covered these)
+    ("go(board_size=2)", 48, 5, 120, 2, False),
+    ("go(board_size=2)", 48, 12, 80, 1, True),
+    ("go(board_size=3)", 48, 8, 150, 1, True),
+    ("go(board_size=3)", 32, 14, 100, 4, False),
+    # n_rollouts not a power of two: 24-byte nodes, the reference's double accumulator
+    ("connect_four", 24, 6, 200, 5, True),
+]
+
+# node budget + garbage collection (MCTSBot max_memory_mb -> max_nodes_, mcts.cc:205-231, 441-482): game, trees, prefix, sims,
+# n_rollouts, solve, budget (max_nodes_ per tree)
+GC_CASES = [
+    ("connect_four", 32, 6, 3000, 1, False, 300),
+    ("tic_tac_toe", 32, 2, 1500, 2, True, 120),
+    ("hex(board_size=4)", 24, 2, 2500, 1, True, 400),
+    ("go(board_size=5)", 16, 6, 1200, 1, True, 600),
+    ("breakthrough(rows=5,columns=4)", 16, 3, 1500, 1, False, 250),
+    ("go(board_size=9)", 8, 20, 600, 1, True, 3000),
 ]
 
 
@@ -72,17 +91,41 @@ def test_device_puct_equals_oracle_puct(gs, n, prefix, sims, nroll, solve):
     _check_against_oracle(gs, n, prefix, sims, nroll, solve, puct=True)
 
 
-def _check_against_oracle(gs, n, prefix, sims, nroll, solve, puct):
+@pytest.mark.parametrize("gs,n,prefix,sims,nroll,solve,budget", GC_CASES, ids=["%s-%d" % (c[0], c[3]) for c in GC_CASES])
+def test_device_garbage_collection_equals_oracle(gs, n, prefix, sims, nroll, solve, budget):
+    """The oracle's collector is pinned to the unmodified reference bit for bit (tests/test_mcts_oracle_vs_reference.py);
+    the device must collect after the same simulations and end with identical root statistics."""
+    collections = _check_against_oracle(gs, n, prefix, sims, nroll, solve, puct=False, budget=budget)
+    assert collections >= n
+
+
+def test_wall_clock_budget_stops_the_search():
+    """max_wall_clock_time (mcts.cc:362-365): simulations stop once the budget has passed; everything run so far is kept."""
+    game = b2.load_game("go(board_size=9)")
+    batch = game.new_batch(256)
+    out = b2.mcts_search(batch, 1000000, seed=3, max_wall_clock_time=0.25, max_nodes_total=256 * 200000)
+    ran = out["sims_run"].cpu().numpy()
+    assert (ran > 0).all() and (ran < 1000000).all()
+    assert bool((out["visits"].sum(dim=1).cpu().numpy() == ran - 1).all())
+    assert batch.error_count()[0] == 0
+
+
+def _check_against_oracle(gs, n, prefix, sims, nroll, solve, puct, budget=0):
     game, batch, states = make_roots(gs, n, prefix, seed=sum(map(ord, gs)) % 1000)
     seed, offset = 0xC0FFEE, 17
     out = b2.mcts_search(batch, sims, uct_c=2.0, n_rollouts=nroll, solve=solve, seed=seed, tree_index_offset=offset,
-                         child_selection_policy=b2.ChildSelectionPolicy.PUCT if puct else b2.ChildSelectionPolicy.UCT)
+                         child_selection_policy=b2.ChildSelectionPolicy.PUCT if puct else b2.ChildSelectionPolicy.UCT,
+                         max_nodes_per_tree=budget)
     assert batch.error_count()[0] == 0
     visits, reward = out["visits"].cpu().numpy(), out["total_reward"].cpu().numpy()
     outcome, best, ran = out["outcome_p0"].cpu().numpy(), out["best_action"].cpu().numpy(), out["sims_run"].cpu().numpy()
+    gcs = out["gc_runs"].cpu().numpy()
+    collections = 0
     for i, st in enumerate(states):
-        o = oracle_mcts(st, 2.0, sims, nroll, solve, seed, tree_index=i + offset, puct=puct)
+        o = oracle_mcts(st, 2.0, sims, nroll, solve, seed, tree_index=i + offset, puct=puct, max_nodes=budget or 1)
         assert ran[i] == o["sims_run"], (gs, i)
+        assert gcs[i] == o["gc_runs"], (gs, i)
+        collections += o["gc_runs"]
         assert int(visits[i].sum()) == sum(v for _, v, _, _ in o["children"])
         for a, v, r, oc in o["children"]:
             assert visits[i, a] == v, (gs, i, a)
@@ -91,6 +134,7 @@ def _check_against_oracle(gs, n, prefix, sims, nroll, solve, puct):
         illegal = sorted(set(range(game.num_distinct_actions())) - {a for a, _, _, _ in o["children"]})
         assert not visits[i, illegal].any()
         assert best[i] == o["best_action"], (gs, i)
+    return collections
 
 
 def _solve(game_string, actions, sims=10000):

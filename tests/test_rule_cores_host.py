@@ -91,10 +91,12 @@ class Emu:
         self.L.emu_rollout(self.h, seed, lane_offset, rets.ctypes.data, plies.ctypes.data, self.n)
         return rets, plies
 
-    def mcts(self, sims, uct_c=2.0, n_rollouts=1, solve=True, seed=0, offset=0, puct=False, max_nodes=0):
+    def mcts(self, sims, uct_c=2.0, n_rollouts=1, solve=True, seed=0, offset=0, puct=False, max_nodes=0, budget=0):
+        """max_nodes: physical arena nodes over all trees (0 = derived); budget: MCTSBot::max_nodes_ per tree (GC)."""
         from open_spiel_b200._lib import MctsConfig
         A = self.info.num_distinct_actions
-        cfg = MctsConfig(sims, n_rollouts, int(solve), int(puct), uct_c, seed, offset, max_nodes or self.n * (sims * A + 2))
+        self.gc_runs = np.zeros(self.n, dtype=np.int32)
+        cfg = MctsConfig(sims, n_rollouts, int(solve), int(puct), uct_c, seed, offset, max_nodes, budget, 0.0, self.gc_runs.ctypes.data)
         visits = np.zeros((self.n, A), dtype=np.int32)
         reward = np.zeros((self.n, A), dtype=np.float64)
         outcome = np.zeros((self.n, A), dtype=np.float32)
@@ -225,11 +227,19 @@ MCTS_CASES = [("tic_tac_toe", 16, 3, 300, 2, True, False), ("connect_four", 12, 
               ("go(board_size=9)", 6, 20, 30, 1, True, False),
               # tiny boards: positional superko decides playouts, so the root's hash history must reach the work lanes
               ("go(board_size=2)", 6, 5, 80, 2, False, True), ("go(board_size=3)", 6, 5, 80, 2, False, True),
-              ("go(board_size=2)", 6, 12, 60, 1, True, True)]
+              ("go(board_size=2)", 6, 12, 60, 1, True, True),
+              # n_rollouts not a power of two: 24-byte nodes with the reference's double accumulator
+              ("tic_tac_toe", 8, 2, 200, 3, True, False), ("connect_four", 6, 4, 150, 5, False, True),
+              # node budget + garbage collection (mcts.cc:441-482): (.., budget) as an 8th field
+              ("connect_four", 6, 4, 1500, 1, False, False, 300), ("tic_tac_toe", 6, 1, 1200, 2, True, False, 120),
+              ("hex(board_size=4)", 6, 2, 1500, 1, True, True, 400), ("go(board_size=5)", 4, 4, 600, 1, True, False, 500),
+              ("breakthrough(rows=5,columns=4)", 4, 3, 800, 1, False, False, 250)]
 
 
-@pytest.mark.parametrize("gs,n,prefix,sims,nroll,solve,puct", MCTS_CASES, ids=["%s-%d" % (c[0], c[3]) for c in MCTS_CASES])
-def test_mcts_kernel_body_on_host_equals_oracle(gs, n, prefix, sims, nroll, solve, puct):
+@pytest.mark.parametrize("case", MCTS_CASES, ids=["%s-%d-%d%s" % (c[0], c[3], c[4], "-gc" if len(c) > 7 else "") for c in MCTS_CASES])
+def test_mcts_kernel_body_on_host_equals_oracle(case):
+    gs, n, prefix, sims, nroll, solve, puct = case[:7]
+    budget = case[7] if len(case) > 7 else 0
     """The body of the k_mcts kernel (mcts.cuh), executed on the host one tree at a time, vs the oracle's MCTS on the same
     Philox stream: visit counts, total rewards (exact doubles), proven outcomes, BestChild, simulations run."""
     import math
@@ -253,16 +263,21 @@ def test_mcts_kernel_body_on_host_equals_oracle(gs, n, prefix, sims, nroll, solv
                 acts[i] = a
         emu.apply(acts)
     assert emu.errors() == 0
-    visits, reward, outcome, best, ran = emu.mcts(sims, 2.0, nroll, solve, seed=0xC0FFEE, offset=17, puct=puct)
+    visits, reward, outcome, best, ran = emu.mcts(sims, 2.0, nroll, solve, seed=0xC0FFEE, offset=17, puct=puct, budget=budget)
     assert emu.errors() == 0
+    collections = 0
     for i, st in enumerate(states):
-        o = oracle_mcts(st, 2.0, sims, nroll, solve, 0xC0FFEE, tree_index=i + 17, puct=puct)
+        o = oracle_mcts(st, 2.0, sims, nroll, solve, 0xC0FFEE, tree_index=i + 17, puct=puct, max_nodes=budget or 1)
         assert ran[i] == o["sims_run"], (gs, i)
+        assert emu.gc_runs[i] == o["gc_runs"], (gs, i)
+        collections += o["gc_runs"]
         for a, v, r, oc in o["children"]:
             assert visits[i, a] == v and reward[i, a] == r, (gs, i, a)
             assert (math.isnan(oc) and math.isnan(outcome[i, a])) or outcome[i, a] == oc, (gs, i, a)
         assert int(visits[i].sum()) == sum(v for _, v, _, _ in o["children"])
         assert best[i] == o["best_action"], (gs, i)
+    if budget:
+        assert collections >= n, "the budget must actually trigger garbage collections in this case"
 
 
 def _sweep_variants():
