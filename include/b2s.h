@@ -280,16 +280,31 @@ int  b2s_cfr_import(void* solver, const double* regrets_h, const double* cum_pol
 int  b2s_cfr_nash_conv(void* solver, int use_average, double* nash_conv_out, double* values_out, void* stream);
 /* Device pointers of the three per-entry tables. */
 int  b2s_cfr_tables(void* solver, double** regrets_d, double** cum_policy_d, double** cur_policy_d);
-/* Multi-GPU CFR (the path's one real exchange step).  One player-traversal of iteration `iteration`
- * (1-based, CFRSolverBase::iteration_) is split in two launches around an all-reduce the CALLER performs
- * (NCCL over NVLink) on the delta buffer (2*num_entries doubles: regret deltas, then average-policy deltas):
- *   b2s_cfr_traverse_shard(s, player, iteration, rank, world)  ->  all-reduce(delta, sum)  ->  b2s_cfr_apply_deltas(s)
- * Every rank evaluates reach/value for the whole tree; history k of an information state contributes on rank
- * k mod world.  Summation order differs from the single-GPU kernel, so results agree to rounding (1e-6 asked),
- * not bit for bit. */
+/* Multi-GPU CFR (the path's one real exchange step; SURVEY §8e).  One player-traversal of iteration `iteration`
+ * (1-based, CFRSolverBase::iteration_) is split in two launches around an all-reduce:
+ *   traverse_shard(player, iteration, rank, world) -> all-reduce(contribution buffer, sum) -> apply_deltas
+ * Every rank evaluates reach/value for the whole tree; the regret / average-policy contribution of history slot k (one
+ * value per action) is written by rank k mod world and as 0.0 by the others, so the all-reduce — x + 0 + ... + 0, exact in
+ * any order — hands every rank every contribution, and apply_deltas adds them in the reference's DFS order
+ * (cfr.cc:387-401): the tables are BIT-IDENTICAL to the single-GPU solver and to the reference for any world size.
+ * Either the caller performs the all-reduce (the three calls below, buffer = b2s_cfr_delta_buffer, length =
+ * b2s_cfr_delta_count doubles) or the library does (b2s_cfr_iterate_sharded). */
 int  b2s_cfr_traverse_shard(void* solver, int player, int iteration, int shard, int num_shards, void* stream);
 int  b2s_cfr_apply_deltas(void* solver, void* stream);
 int  b2s_cfr_delta_buffer(void* solver, double** delta_d);
+int  b2s_cfr_delta_count(void* solver, int64_t* count);
+/* In-library exchange (NCCL over NVLink; NCCL is resolved with dlopen, the copy already loaded in the process wins).
+ * b2s_nccl_unique_id: 128-byte ncclUniqueId created on one rank, to be handed to all ranks by the caller's own means.
+ * b2s_cfr_comm_init creates a communicator owned by the solver; b2s_cfr_comm_adopt uses the caller's ncclComm_t.
+ * b2s_cfr_iterate_sharded: `iters` x CFRSolverBase::EvaluateAndUpdatePolicy (cfr.cc:263-282) with traverse -> ncclAllReduce
+ * -> apply enqueued back to back on a solver-owned stream (ordered after / before `stream`), 16 iterations per CUDA graph
+ * launch — no host code between the steps.  Collective: every rank must make the same call.
+ * b2s_cfr_allreduce_probe: device seconds of `count` back-to-back all-reduces of the buffer alone (the latency floor). */
+int  b2s_nccl_unique_id(void* id128);
+int  b2s_cfr_comm_init(void* solver, const void* id128, int rank, int world);
+int  b2s_cfr_comm_adopt(void* solver, void* nccl_comm, int rank, int world);
+int  b2s_cfr_iterate_sharded(void* solver, int iters, void* stream);
+int  b2s_cfr_allreduce_probe(void* solver, int count, double* seconds);
 int  b2s_cfr_set_iteration(void* solver, int iteration);
 
 /* Replaces algorithms::ExternalSamplingMCCFRSolver (open_spiel/algorithms/external_sampling_mccfr.h:55-110,

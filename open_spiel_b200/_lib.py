@@ -98,6 +98,12 @@ SIGNATURES = {
     "b2s_cfr_traverse_shard": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP]),
     "b2s_cfr_apply_deltas": (C.c_int, [_VP, _VP]),
     "b2s_cfr_delta_buffer": (C.c_int, [_VP, C.POINTER(_VP)]),
+    "b2s_cfr_delta_count": (C.c_int, [_VP, C.POINTER(_I64)]),
+    "b2s_nccl_unique_id": (C.c_int, [_VP]),
+    "b2s_cfr_comm_init": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    "b2s_cfr_comm_adopt": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    "b2s_cfr_iterate_sharded": (C.c_int, [_VP, C.c_int, _VP]),
+    "b2s_cfr_allreduce_probe": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double)]),
     "b2s_mccfr_external_iterate": (C.c_int, [_VP, C.c_int, C.c_int, _U64, _VP]),
     "b2s_mccfr_traverse_lanes": (C.c_int, [_VP, C.c_int, C.c_int, _U64, C.c_int, C.c_int, _VP, _VP]),
     "b2s_mccfr_apply_partials": (C.c_int, [_VP, C.c_int, _VP, _VP]),

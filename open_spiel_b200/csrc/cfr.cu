@@ -30,6 +30,7 @@
 #include "../../include/b2s.h"
 #include "common.cuh"
 #include "errors.h"
+#include "nccl_dyn.h"
 
 namespace b2s {
 extern long long g_launches;
@@ -60,10 +61,54 @@ struct CfrDev {
   double* regrets;             // [E]
   double* cum_policy;          // [E]
   double* cur_policy;          // [E]
-  double* delta;               // [2E]: regret deltas then average-policy deltas of one sharded traversal
+  double* delta;               // [2C]: per-(history, action) regret contributions, then average-policy contributions, of one sharded traversal
+  const int* hist_entry_off;   // [n_hist + 1] offset of history slot hh in the contribution buffer (prefix sum of its action count)
+  const int* hist_is;          // [n_hist] information state of history slot hh
+  int n_hist, n_contrib;       // history slots (= decision nodes), C = sum of their action counts
+  int* iter_d;                 // device iteration counter for graph-captured sharded iterations
   const signed char* entry_player;   // [E] the player an entry's information state belongs to
   const int4* mc_node;         // [n] MCCFR traversal record: {first_child, table offset of the information state, kind | actor << 8 | nchild << 16, 0}
 };
+
+// One traversal's tree passes, shared by the single-GPU kernel and the sharded one: (1) edge probabilities from the frozen
+// policy, (2) L level steps in which the reach probabilities move one level DOWN while the state values move one level UP.
+__device__ __forceinline__ void cfr_level_passes(const CfrDev& d, int tid, int nt) {
+  const int L = d.n_levels;
+  for (int n = 1 + tid; n < d.n_nodes; n += nt) {
+    int pi = d.policy_index[n];
+    d.edge_prob[n] = pi >= 0 ? d.cur_policy[pi] : d.chance_prob[n];
+  }
+  if (tid == 0) { d.reach[0] = 1.0; d.reach[1] = 1.0; }
+  __syncthreads();
+  for (int k = 0; k < L; ++k) {
+    int ld = k + 1;                       // reach: new_reach_probabilities[current_player] *= prob (cfr.cc:457)
+    if (ld < L) {
+      for (int n = d.level_off[ld] + tid; n < d.level_off[ld + 1]; n += nt) {
+        int par = d.parent[n];
+        double r0 = d.reach[2 * par], r1 = d.reach[2 * par + 1];
+        int a = d.par_actor[n];
+        if (a == 0) r0 = __dmul_rn(r0, d.edge_prob[n]); else if (a == 1) r1 = __dmul_rn(r1, d.edge_prob[n]);
+        d.reach[2 * n] = r0; d.reach[2 * n + 1] = r1;
+      }
+    }
+    int lu = L - 1 - k;                   // values: state_value[i] += prob * child_value[i] (cfr.cc:461-463)
+    for (int n = d.level_off[lu] + tid; n < d.level_off[lu + 1]; n += nt) {
+      double v0, v1;
+      if (d.kind[n] == 0) { v0 = d.ret[2 * n]; v1 = d.ret[2 * n + 1]; }
+      else {
+        v0 = 0.0; v1 = 0.0;
+        int fc = d.first_child[n];
+        for (int c = 0; c < d.nchild[n]; ++c) {
+          double pr = d.edge_prob[fc + c];
+          v0 = __dadd_rn(v0, __dmul_rn(pr, d.value[2 * (fc + c)]));
+          v1 = __dadd_rn(v1, __dmul_rn(pr, d.value[2 * (fc + c) + 1]));
+        }
+      }
+      d.value[2 * n] = v0; d.value[2 * n + 1] = v1;
+    }
+    __syncthreads();
+  }
+}
 
 __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration0, int linear_averaging, int rm_plus) {
   // One traversal = (1) edge probabilities from the frozen policy, (2) L level steps in which the reach
@@ -81,40 +126,7 @@ __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration
   for (int it = 0; it < iters; ++it) {
     const double iteration = (double)(iteration0 + it + 1);          // ++iteration_ (cfr.cc:264)
     for (int p = 0; p < 2; ++p) {
-      for (int n = 1 + tid; n < d.n_nodes; n += nt) {
-        int pi = d.policy_index[n];
-        d.edge_prob[n] = pi >= 0 ? d.cur_policy[pi] : d.chance_prob[n];
-      }
-      if (tid == 0) { d.reach[0] = 1.0; d.reach[1] = 1.0; }
-      __syncthreads();
-      for (int k = 0; k < L; ++k) {
-        int ld = k + 1;                       // reach: new_reach_probabilities[current_player] *= prob (cfr.cc:457)
-        if (ld < L) {
-          for (int n = d.level_off[ld] + tid; n < d.level_off[ld + 1]; n += nt) {
-            int par = d.parent[n];
-            double r0 = d.reach[2 * par], r1 = d.reach[2 * par + 1];
-            int a = d.par_actor[n];
-            if (a == 0) r0 = __dmul_rn(r0, d.edge_prob[n]); else if (a == 1) r1 = __dmul_rn(r1, d.edge_prob[n]);
-            d.reach[2 * n] = r0; d.reach[2 * n + 1] = r1;
-          }
-        }
-        int lu = L - 1 - k;                   // values: state_value[i] += prob * child_value[i] (cfr.cc:461-463)
-        for (int n = d.level_off[lu] + tid; n < d.level_off[lu + 1]; n += nt) {
-          double v0, v1;
-          if (d.kind[n] == 0) { v0 = d.ret[2 * n]; v1 = d.ret[2 * n + 1]; }
-          else {
-            v0 = 0.0; v1 = 0.0;
-            int fc = d.first_child[n];
-            for (int c = 0; c < d.nchild[n]; ++c) {
-              double pr = d.edge_prob[fc + c];
-              v0 = __dadd_rn(v0, __dmul_rn(pr, d.value[2 * (fc + c)]));
-              v1 = __dadd_rn(v1, __dmul_rn(pr, d.value[2 * (fc + c) + 1]));
-            }
-          }
-          d.value[2 * n] = v0; d.value[2 * n + 1] = v1;
-        }
-        __syncthreads();
-      }
+      cfr_level_passes(d, tid, nt);
       // regret / average-policy update (cfr.cc:379-405) + regret matching (cfr.cc:596-615) for player p
       for (int I = tid; I < d.n_infosets; I += nt) {
         if (d.is_player[I] != p) continue;
@@ -150,80 +162,62 @@ __global__ void __launch_bounds__(1024) k_cfr(CfrDev d, int iters, int iteration
   }
 }
 
-// ---- multi-GPU variant: one traversal split into "compute my shard's deltas" / all-reduce / "apply" -----------
-// Every rank evaluates reach and value for the whole (tiny) tree; the regret / average-policy contributions of
-// history k of an information state are accumulated only by rank (k mod num_shards) into `delta`, the ranks
-// all-reduce `delta` (NCCL, 2E doubles), then every rank applies the summed deltas and runs regret matching.
-// Summation order differs from the reference's running total, so this path is within rounding (asked: 1e-6),
-// not bit-exact; the single-GPU kernel above stays exact.
-__global__ void __launch_bounds__(1024) k_cfr_traverse(CfrDev d, int p, int iteration, int linear_averaging, int shard, int num_shards) {
+// ---- multi-GPU variant: one traversal split into "my shard's contributions" / all-reduce / "apply in order" ---------
+// Every rank runs the level passes of the whole (tiny) tree; history slot hh's regret and average-policy contributions
+// (one pair per action, the very expressions of k_cfr above) are written by rank (hh mod num_shards) into the
+// contribution buffer `delta` and as 0.0 by every other rank, the ranks all-reduce the buffer (NCCL sum over NVLink, 2C
+// doubles — x + 0 + ... + 0 is exact in any order), then every rank adds the contributions to its tables in the
+// reference's DFS order and runs regret matching.  The tables therefore stay BIT-IDENTICAL to the single-GPU kernel and
+// to the reference, whatever the number of ranks; the price is a 2C- instead of a 2E-double message (Leduc: 150 KB
+// instead of 45 KB — still latency-, not bandwidth-sized on NVLink).
+// iteration: CFRSolverBase::iteration_ of this traversal (1-based) — from `iteration`, or, when d.iter_d is used
+// (graph-captured loops), from the device counter, which player 0's traversal advances.
+__global__ void __launch_bounds__(1024) k_cfr_traverse(CfrDev d, int p, int iteration, int use_counter, int linear_averaging, int shard, int num_shards) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) { d.reach[0] = 1.0; d.reach[1] = 1.0; d.reach[2] = 1.0; }
-  for (int k = tid; k < 2 * d.n_entries; k += nt) d.delta[k] = 0.0;
-  __syncthreads();
-  for (int l = 1; l < d.n_levels; ++l) {
-    for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
-      int par = d.parent[n];
-      double r0 = d.reach[3 * par], r1 = d.reach[3 * par + 1], r2 = d.reach[3 * par + 2];
-      double prob = d.kind[par] == 1 ? d.chance_prob[n] : d.cur_policy[d.is_off[d.infoset[par]] + d.aidx[n]];
-      int a = d.actor[par];
-      if (a == 0) r0 = __dmul_rn(r0, prob); else if (a == 1) r1 = __dmul_rn(r1, prob); else r2 = __dmul_rn(r2, prob);
-      d.reach[3 * n] = r0; d.reach[3 * n + 1] = r1; d.reach[3 * n + 2] = r2;
-      d.edge_prob[n] = prob;
-    }
-    __syncthreads();
-  }
-  for (int l = d.n_levels - 1; l >= 0; --l) {
-    for (int n = d.level_off[l] + tid; n < d.level_off[l + 1]; n += nt) {
-      double v0, v1;
-      if (d.kind[n] == 0) { v0 = d.ret[2 * n]; v1 = d.ret[2 * n + 1]; }
-      else if (d.kind[n] == 2 && d.reach[3 * n] == 0.0 && d.reach[3 * n + 1] == 0.0) { v0 = 0.0; v1 = 0.0; }
-      else {
-        v0 = 0.0; v1 = 0.0;
-        int fc = d.first_child[n];
-        for (int c = 0; c < d.nchild[n]; ++c) {
-          double pr = d.edge_prob[fc + c];
-          v0 = __dadd_rn(v0, __dmul_rn(pr, d.value[2 * (fc + c)]));
-          v1 = __dadd_rn(v1, __dmul_rn(pr, d.value[2 * (fc + c) + 1]));
-        }
-      }
-      d.value[2 * n] = v0; d.value[2 * n + 1] = v1;
-    }
-    __syncthreads();
-  }
+  if (use_counter) iteration = *d.iter_d + (p == 0 ? 1 : 0);
+  cfr_level_passes(d, tid, nt);
   const double iter = (double)iteration;
+  const int C = d.n_contrib;
+  for (int hh = tid; hh < d.n_hist; hh += nt) {
+    const int I = d.hist_is[hh];
+    if (d.is_player[I] != p) continue;
+    const int off = d.is_off[I], na = d.is_off[I + 1] - off, co = d.hist_entry_off[hh];
+    if (hh % num_shards != shard) {
+      for (int a = 0; a < na; ++a) { d.delta[co + a] = 0.0; d.delta[C + co + a] = 0.0; }
+      continue;
+    }
+    const int h = d.hist[hh];
+    double self_reach = d.reach[2 * h + p];
+    double cfr_reach = __dmul_rn(__dmul_rn(1.0, d.reach[2 * h + (1 - p)]), d.chance_reach[h]);
+    double vh = d.value[2 * h + p];
+    int fc = d.first_child[h];
+    for (int a = 0; a < na; ++a) {
+      d.delta[co + a] = __dmul_rn(cfr_reach, __dsub_rn(d.value[2 * (fc + a) + p], vh));
+      double pol = d.cur_policy[off + a];
+      d.delta[C + co + a] = linear_averaging ? __dmul_rn(__dmul_rn(iter, self_reach), pol) : __dmul_rn(self_reach, pol);
+    }
+  }
+  __syncthreads();
+  if (use_counter && p == 0 && tid == 0) *d.iter_d = iteration;
+}
+
+__global__ void __launch_bounds__(1024) k_cfr_apply(CfrDev d, int p, int rm_plus) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int C = d.n_contrib;
   for (int I = tid; I < d.n_infosets; I += nt) {
     if (d.is_player[I] != p) continue;
     int off = d.is_off[I], na = d.is_off[I + 1] - off;
-    for (int hh = d.hist_off[I]; hh < d.hist_off[I + 1]; ++hh) {
-      if ((hh - d.hist_off[I]) % num_shards != shard) continue;
-      int h = d.hist[hh];
-      double self_reach = d.reach[3 * h + p];
-      double cfr_reach = 1.0;
-      for (int i = 0; i < 3; ++i) if (i != p) cfr_reach = __dmul_rn(cfr_reach, d.reach[3 * h + i]);
-      double vh = d.value[2 * h + p];
-      int fc = d.first_child[h];
+    for (int hh = d.hist_off[I]; hh < d.hist_off[I + 1]; ++hh) {      // the reference's DFS order (cfr.cc:387-401)
+      const int co = d.hist_entry_off[hh];
       for (int a = 0; a < na; ++a) {
-        double regret = __dmul_rn(cfr_reach, __dsub_rn(d.value[2 * (fc + a) + p], vh));
-        d.delta[off + a] = __dadd_rn(d.delta[off + a], regret);
-        double pol = d.cur_policy[off + a];
-        double inc = linear_averaging ? __dmul_rn(__dmul_rn(iter, self_reach), pol) : __dmul_rn(self_reach, pol);
-        d.delta[d.n_entries + off + a] = __dadd_rn(d.delta[d.n_entries + off + a], inc);
+        d.regrets[off + a] = __dadd_rn(d.regrets[off + a], d.delta[co + a]);
+        d.cum_policy[off + a] = __dadd_rn(d.cum_policy[off + a], d.delta[C + co + a]);
       }
     }
-  }
-}
-
-__global__ void __launch_bounds__(1024) k_cfr_apply(CfrDev d, int rm_plus) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int I = tid; I < d.n_infosets; I += nt) {
-    int off = d.is_off[I], na = d.is_off[I + 1] - off;
     double sum = 0.0;
     for (int a = 0; a < na; ++a) {
-      double r = __dadd_rn(d.regrets[off + a], d.delta[off + a]);
-      if (rm_plus && r < 0) r = 0;
-      d.regrets[off + a] = r;
-      d.cum_policy[off + a] = __dadd_rn(d.cum_policy[off + a], d.delta[d.n_entries + off + a]);
+      double r = d.regrets[off + a];
+      if (rm_plus && r < 0) { r = 0; d.regrets[off + a] = 0; }
       if (r > 0) sum = __dadd_rn(sum, r);
     }
     for (int a = 0; a < na; ++a) {
@@ -506,6 +500,11 @@ __global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_combine(CfrDev d, 
 }
 
 struct CfrSolver {
+  // multi-GPU: communicator (owned or adopted), private stream + a CUDA graph of kGraphIters sharded iterations
+  ncclComm_t comm = nullptr; bool comm_owned = false; int rank = 0, world = 1;
+  cudaStream_t dist_stream = nullptr; cudaEvent_t dist_ev = nullptr;
+  cudaGraphExec_t dist_graph = nullptr;
+  int last_shard_player = 0;
   int mccfr_tables = 0;
   double* mc_rows = nullptr; int mc_rows_k = 0;
   int* mc_err = nullptr;
@@ -520,7 +519,15 @@ struct CfrSolver {
   // host copies of the structure (export)
   std::vector<int> is_player, is_off, legal_actions, node_counts;    // node_counts = {chance, decision, terminal}
   std::vector<float> keys;                                           // [I][tensor_size] information-state tensors
-  ~CfrSolver() { for (void* p : allocs) cudaFree(p); if (mc_rows) cudaFree(mc_rows); if (mc_err) cudaFree(mc_err); }
+  ~CfrSolver() {
+    if (dist_graph) cudaGraphExecDestroy(dist_graph);
+    if (comm && comm_owned && nccl_api().ok()) nccl_api().CommDestroy(comm);
+    if (dist_ev) cudaEventDestroy(dist_ev);
+    if (dist_stream) cudaStreamDestroy(dist_stream);
+    for (void* p : allocs) cudaFree(p);
+    if (mc_rows) cudaFree(mc_rows);
+    if (mc_err) cudaFree(mc_err);
+  }
 };
 
 template <typename T>
@@ -697,6 +704,17 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
   CK(upload(S, infoset, &d.infoset)); CK(upload(S, S->is_player, &d.is_player)); CK(upload(S, S->is_off, &d.is_off));
   CK(upload(S, hist_off, &d.hist_off)); CK(upload(S, hist, &d.hist));
   {
+    std::vector<int> hist_is(hist.size(), 0), hist_entry_off(1, 0);
+    for (int i = 0; i < I; ++i)
+      for (int hh = hist_off[i]; hh < hist_off[i + 1]; ++hh) {
+        hist_is[hh] = i;
+        hist_entry_off.push_back(hist_entry_off.back() + (S->is_off[i + 1] - S->is_off[i]));
+      }
+    d.n_hist = (int)hist.size();
+    d.n_contrib = hist_entry_off.back();
+    CK(upload(S, hist_is, &d.hist_is)); CK(upload(S, hist_entry_off, &d.hist_entry_off));
+  }
+  {
     std::vector<int> policy_index(N, -1);
     std::vector<signed char> par_actor(N, 2);
     std::vector<double> chance_reach(N, 1.0);
@@ -730,7 +748,14 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
   }
   CK(alloc_d(S, 3 * (size_t)N, &d.reach)); CK(alloc_d(S, N, &d.edge_prob)); CK(alloc_d(S, 2 * (size_t)N, &d.value));
   CK(alloc_d(S, E, &d.regrets)); CK(alloc_d(S, E, &d.cum_policy)); CK(alloc_d(S, E, &d.cur_policy));
-  CK(alloc_d(S, 2 * (size_t)E, &d.delta));
+  CK(alloc_d(S, 2 * (size_t)d.n_contrib, &d.delta));
+  {
+    void* it = nullptr;
+    B2S_CU(cudaMalloc(&it, sizeof(int)));
+    B2S_CU(cudaMemset(it, 0, sizeof(int)));
+    S->allocs.push_back(it);
+    d.iter_d = (int*)it;
+  }
   // CFRInfoStateValues(legal_actions): regrets 0, cumulative policy 0, current policy uniform (cfr.h:42-98)
   std::vector<double> uni(E);
   for (int i = 0; i < I; ++i)
@@ -896,24 +921,168 @@ int b2s_cfr_traverse_shard(void* solver, int player, int iteration, int shard, i
   if (player < 0 || player > 1 || num_shards < 1 || shard < 0 || shard >= num_shards) return fail("cfr: bad shard arguments");
   CfrSolver* S = (CfrSolver*)solver;
   B2S_CU(cudaSetDevice(S->device));
-  k_cfr_traverse<<<1, 1024, 0, (cudaStream_t)stream>>>(S->d, player, iteration, S->linear_averaging, shard, num_shards);
+  k_cfr_traverse<<<1, 1024, 0, (cudaStream_t)stream>>>(S->d, player, iteration, 0, S->linear_averaging, shard, num_shards);
   ++g_launches;
+  S->last_shard_player = player;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_cfr_traverse launch");
   return 0;
 }
-// Step 2 of 2 (after the caller all-reduced the delta buffer): tables += deltas, RM+ reset, regret matching.
+// Step 2 of 2 (after the caller all-reduced the contribution buffer): tables += contributions in the reference's order,
+// RM+ reset, regret matching — for the player of the preceding b2s_cfr_traverse_shard.
 int b2s_cfr_apply_deltas(void* solver, void* stream) {
   if (!solver) return fail("cfr: null solver");
   CfrSolver* S = (CfrSolver*)solver;
   B2S_CU(cudaSetDevice(S->device));
-  k_cfr_apply<<<1, 1024, 0, (cudaStream_t)stream>>>(S->d, S->rm_plus);
+  k_cfr_apply<<<1, 1024, 0, (cudaStream_t)stream>>>(S->d, S->last_shard_player, S->rm_plus);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_cfr_apply launch");
   return 0;
 }
-// The delta buffer: 2 * num_entries doubles (regret deltas, then average-policy deltas), device pointer.
+int b2s_cfr_delta_count(void* solver, int64_t* count) {
+  if (!solver || !count) return fail("cfr: null argument");
+  *count = 2 * (int64_t)((CfrSolver*)solver)->d.n_contrib;
+  return 0;
+}
+
+// ---- in-library NCCL: the whole sharded iteration loop enqueued by the library, no host code between the steps -----
+#define B2S_NCCL(x) do { ncclResult_t _r = (x); if (_r != ncclSuccess) return fail(std::string("nccl: ") + #x + ": " + nccl_api().GetErrorString(_r)); } while (0)
+
+int b2s_nccl_unique_id(void* id128) {
+  if (!id128) return fail("nccl: null id");
+  const NcclApi& N = nccl_api();
+  if (!N.ok()) return fail(N.error);
+  ncclUniqueId id;
+  B2S_NCCL(N.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+
+static int dist_prepare(CfrSolver* S) {
+  if (!S->dist_stream) B2S_CU(cudaStreamCreateWithFlags(&S->dist_stream, cudaStreamNonBlocking));
+  if (!S->dist_ev) B2S_CU(cudaEventCreateWithFlags(&S->dist_ev, cudaEventDisableTiming));
+  return 0;
+}
+
+int b2s_cfr_comm_init(void* solver, const void* id128, int rank, int world) {
+  if (!solver || !id128) return fail("cfr: null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail("cfr: bad rank / world");
+  CfrSolver* S = (CfrSolver*)solver;
+  const NcclApi& N = nccl_api();
+  if (!N.ok()) return fail(N.error);
+  B2S_CU(cudaSetDevice(S->device));
+  if (S->comm && S->comm_owned) N.CommDestroy(S->comm);
+  S->comm = nullptr;
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  B2S_NCCL(N.CommInitRank(&S->comm, world, id, rank));
+  S->comm_owned = true; S->rank = rank; S->world = world;
+  if (S->dist_graph) { cudaGraphExecDestroy(S->dist_graph); S->dist_graph = nullptr; }
+  return dist_prepare(S);
+}
+
+int b2s_cfr_comm_adopt(void* solver, void* nccl_comm, int rank, int world) {
+  if (!solver || !nccl_comm) return fail("cfr: null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail("cfr: bad rank / world");
+  CfrSolver* S = (CfrSolver*)solver;
+  const NcclApi& N = nccl_api();
+  if (!N.ok()) return fail(N.error);
+  if (S->comm && S->comm_owned) N.CommDestroy(S->comm);
+  S->comm = (ncclComm_t)nccl_comm; S->comm_owned = false; S->rank = rank; S->world = world;
+  if (S->dist_graph) { cudaGraphExecDestroy(S->dist_graph); S->dist_graph = nullptr; }
+  B2S_CU(cudaSetDevice(S->device));
+  return dist_prepare(S);
+}
+
+constexpr int kGraphIters = 16;     // sharded iterations per CUDA-graph launch
+
+// one EvaluateAndUpdatePolicy (cfr.cc:263-282), sharded: per player traverse -> all-reduce -> apply, all on `st`
+static int enqueue_sharded_iteration(CfrSolver* S, cudaStream_t st) {
+  const NcclApi& N = nccl_api();
+  for (int p = 0; p < 2; ++p) {
+    k_cfr_traverse<<<1, 1024, 0, st>>>(S->d, p, 0, 1, S->linear_averaging, S->rank, S->world);
+    B2S_NCCL(N.AllReduce(S->d.delta, S->d.delta, 2 * (size_t)S->d.n_contrib, ncclDouble, ncclSum, S->comm, st));
+    k_cfr_apply<<<1, 1024, 0, st>>>(S->d, p, S->rm_plus);
+    g_launches += 2;
+  }
+  return 0;
+}
+
+int b2s_cfr_iterate_sharded(void* solver, int iters, void* stream) {
+  if (!solver) return fail("cfr: null solver");
+  if (iters < 0) return fail("cfr: negative iteration count");
+  CfrSolver* S = (CfrSolver*)solver;
+  if (!S->comm) return fail("cfr: no communicator (b2s_cfr_comm_init / b2s_cfr_comm_adopt first)");
+  B2S_CU(cudaSetDevice(S->device));
+  if (iters == 0) return 0;
+  cudaStream_t user = (cudaStream_t)stream, st = S->dist_stream;
+  // order after the caller's stream, run on the solver's own stream (graphs cannot be captured on the legacy stream)
+  B2S_CU(cudaEventRecord(S->dist_ev, user));
+  B2S_CU(cudaStreamWaitEvent(st, S->dist_ev, 0));
+  B2S_CU(cudaMemcpyAsync(S->d.iter_d, &S->iteration, sizeof(int), cudaMemcpyHostToDevice, st));
+  B2S_CU(cudaStreamSynchronize(st));          // the source of the copy above is a host field that changes below
+  int left = iters;
+  if (left >= kGraphIters) {
+    if (!S->dist_graph) {
+      cudaGraph_t g = nullptr;
+      B2S_CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int rc = 0;
+      for (int i = 0; i < kGraphIters && !rc; ++i) rc = enqueue_sharded_iteration(S, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (ce != cudaSuccess) return cuda_fail(ce, "cfr: graph capture");
+      ce = cudaGraphInstantiate(&S->dist_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) return cuda_fail(ce, "cfr: graph instantiate");
+    }
+    for (; left >= kGraphIters; left -= kGraphIters) B2S_CU(cudaGraphLaunch(S->dist_graph, st));
+  }
+  for (; left > 0; --left) if (int rc = enqueue_sharded_iteration(S, st)) return rc;
+  S->iteration += iters;
+  B2S_CU(cudaEventRecord(S->dist_ev, st));
+  B2S_CU(cudaStreamWaitEvent(user, S->dist_ev, 0));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "cfr: sharded iteration");
+  return 0;
+}
+
+// Latency floor of the exchange alone: `count` back-to-back all-reduces of the contribution buffer on the solver's stream
+// (what two of them per iteration cost however fast the kernels are).  Synchronous; *seconds = elapsed device time.
+int b2s_cfr_allreduce_probe(void* solver, int count, double* seconds) {
+  if (!solver || !seconds || count < 1) return fail("cfr: bad probe arguments");
+  CfrSolver* S = (CfrSolver*)solver;
+  if (!S->comm) return fail("cfr: no communicator");
+  const NcclApi& N = nccl_api();
+  B2S_CU(cudaSetDevice(S->device));
+  cudaStream_t st = S->dist_stream;
+  cudaEvent_t e0, e1;
+  B2S_CU(cudaEventCreate(&e0)); B2S_CU(cudaEventCreate(&e1));
+  cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+  B2S_CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  ncclResult_t nr = ncclSuccess;
+  for (int i = 0; i < count && nr == ncclSuccess; ++i)
+    nr = N.AllReduce(S->d.delta, S->d.delta, 2 * (size_t)S->d.n_contrib, ncclDouble, ncclSum, S->comm, st);
+  cudaError_t ce = cudaStreamEndCapture(st, &g);
+  if (nr != ncclSuccess) return fail(std::string("nccl: ") + N.GetErrorString(nr));
+  if (ce != cudaSuccess) return cuda_fail(ce, "probe capture");
+  B2S_CU(cudaGraphInstantiate(&ge, g, 0));
+  B2S_CU(cudaGraphLaunch(ge, st));            // warm-up
+  B2S_CU(cudaStreamSynchronize(st));
+  B2S_CU(cudaEventRecord(e0, st));
+  B2S_CU(cudaGraphLaunch(ge, st));
+  B2S_CU(cudaEventRecord(e1, st));
+  B2S_CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  B2S_CU(cudaEventElapsedTime(&ms, e0, e1));
+  *seconds = ms * 1e-3;
+  cudaGraphExecDestroy(ge); cudaGraphDestroy(g);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+// The contribution buffer: b2s_cfr_delta_count doubles (regret contributions, then average-policy contributions), device pointer.
 int b2s_cfr_delta_buffer(void* solver, double** delta_d) {
   if (!solver || !delta_d) return fail("cfr: null argument");
   *delta_d = ((CfrSolver*)solver)->d.delta;

@@ -79,23 +79,42 @@ class _DevArray:
 
 
 class DistributedCFRSolver:
-    """CFRSolver whose traversal work is split over the ranks: per player traversal every rank computes its share of
-    the regret / average-policy deltas, the delta buffer is all-reduced (NCCL), every rank applies the sum and runs
-    regret matching — tables stay replicated.  Agrees with the single-GPU solver to rounding (north star: 1e-6)."""
+    """CFRSolver whose per-history regret / average-policy contributions are computed by rank (slot mod world), summed by
+    an all-reduce and applied by every rank in the reference's order — tables stay replicated and BIT-IDENTICAL to the
+    single-GPU solver (include/b2s.h).  in_library=True (default on CUDA with world > 1): the library owns an NCCL
+    communicator and enqueues traverse -> ncclAllReduce -> apply itself, 16 iterations per CUDA-graph launch
+    (b2s_cfr_iterate_sharded); in_library=False: this class performs the all-reduce with torch.distributed between the
+    two library calls (works with gloo-backed tests via a CPU bounce of the buffer)."""
 
-    def __init__(self, game, linear_averaging=False, regret_matching_plus=False):
+    def __init__(self, game, linear_averaging=False, regret_matching_plus=False, in_library=None):
         from .spiel import CFRSolver
+        import torch.distributed as dist
         self.solver = CFRSolver(game, linear_averaging, regret_matching_plus)
         self.rank, self.world = world()
         self.iteration = 0
-        ptr = C.c_void_p()
+        ptr, cnt = C.c_void_p(), C.c_int64()
         check(lib().b2s_cfr_delta_buffer(self.solver._h, C.byref(ptr)))
-        n = 2 * self.solver._info.num_entries
-        self.delta = torch.as_tensor(_DevArray(ptr.value, n), device=torch.device("cuda", game.device))
+        check(lib().b2s_cfr_delta_count(self.solver._h, C.byref(cnt)))
+        self.delta = torch.as_tensor(_DevArray(ptr.value, cnt.value), device=torch.device("cuda", game.device))
+        if in_library is None:
+            in_library = self.world > 1 and dist.is_initialized() and dist.get_backend() == "nccl"
+        self.in_library = bool(in_library)
+        if self.in_library:
+            ident = (C.c_char * 128)()
+            if self.rank == 0:
+                check(lib().b2s_nccl_unique_id(ident))
+            box = [bytes(ident)]
+            if self.world > 1:
+                dist.broadcast_object_list(box, src=0)
+            check(lib().b2s_cfr_comm_init(self.solver._h, box[0], self.rank, self.world))
 
     def evaluate_and_update_policy(self, iterations=1):
         L, h = lib(), self.solver._h
         st = C.c_void_p(torch.cuda.current_stream(self.delta.device).cuda_stream)
+        if self.in_library:
+            check(L.b2s_cfr_iterate_sharded(h, int(iterations), st))
+            self.iteration += int(iterations)
+            return
         for _ in range(int(iterations)):
             self.iteration += 1
             for player in (0, 1):
@@ -103,6 +122,12 @@ class DistributedCFRSolver:
                 allreduce_stats(self.delta)
                 check(L.b2s_cfr_apply_deltas(h, st))
         check(L.b2s_cfr_set_iteration(h, self.iteration))
+
+    def allreduce_seconds(self, count=200):
+        """Device seconds of `count` back-to-back all-reduces of the contribution buffer (latency floor of the exchange)."""
+        secs = C.c_double()
+        check(lib().b2s_cfr_allreduce_probe(self.solver._h, int(count), C.byref(secs)))
+        return secs.value
 
     def table(self):
         return self.solver.table()

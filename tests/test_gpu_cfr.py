@@ -74,37 +74,39 @@ def test_checkpoint_resume_is_exact():
         assert np.array_equal(ta[f], tb[f])
 
 
-def test_sharded_traversal_path_agrees_within_tolerance():
-    """The multi-GPU code path (traverse_shard -> all-reduce -> apply_deltas) run on one GPU: with 1 shard, and with
-    3 shards evaluated one after the other and their delta buffers summed by hand (what the NCCL all-reduce does)."""
-    import ctypes as C
+def test_sharded_traversal_path_is_bit_identical():
+    """The multi-GPU code path (traverse_shard -> all-reduce -> apply_deltas) run on one GPU: with 1 shard, and with 3 and
+    8 shards evaluated one after the other and their contribution buffers summed by hand (what the NCCL all-reduce does:
+    every slot is one rank's value plus zeros).  Tables must equal the single-GPU kernel's bit for bit — the summation
+    order problem of a per-entry partial-sum exchange (SURVEY §7 "CFR floating point") does not arise."""
     import torch
     from open_spiel_b200 import parallel
     from open_spiel_b200._lib import check, lib
-    game = b2.load_game("leduc_poker")
-    ref = b2.CFRSolver(game)
-    ref.evaluate_and_update_policy(30)
-    tr = ref.table()
-    one = parallel.DistributedCFRSolver(game)
-    one.evaluate_and_update_policy(30)
-    t1 = one.table()
-    # emulate world_size 3 on one device
-    three = parallel.DistributedCFRSolver(game)
-    L, h = lib(), three.solver._h
-    for it in range(1, 31):
-        for player in (0, 1):
-            acc = torch.zeros_like(three.delta)
-            for shard in range(3):
-                check(L.b2s_cfr_traverse_shard(h, player, it, shard, 3, None))
-                torch.cuda.synchronize()
-                acc += three.delta
-            three.delta.copy_(acc)
-            check(L.b2s_cfr_apply_deltas(h, None))
-    t3 = three.table()
-    for f in ("regrets", "cum_policy", "cur_policy"):
-        assert np.abs(t1[f] - tr[f]).max() <= TOL
-        assert np.abs(t3[f] - tr[f]).max() <= TOL
-    assert np.abs(t1["regrets"]).max() > 1.0       # the tables are not trivially zero
+    for plus in (False, True):
+        game = b2.load_game("leduc_poker")
+        ref = b2.CFRSolver(game, linear_averaging=plus, regret_matching_plus=plus)
+        ref.evaluate_and_update_policy(60)
+        tr = ref.table()
+        one = parallel.DistributedCFRSolver(game, linear_averaging=plus, regret_matching_plus=plus, in_library=False)
+        one.evaluate_and_update_policy(60)
+        tables = [one.table()]
+        for shards in (3, 8):
+            multi = parallel.DistributedCFRSolver(game, linear_averaging=plus, regret_matching_plus=plus, in_library=False)
+            L, h = lib(), multi.solver._h
+            for it in range(1, 61):
+                for player in (0, 1):
+                    acc = torch.zeros_like(multi.delta)
+                    for shard in range(shards):
+                        check(L.b2s_cfr_traverse_shard(h, player, it, shard, shards, None))
+                        torch.cuda.synchronize()
+                        acc += multi.delta
+                    multi.delta.copy_(acc)
+                    check(L.b2s_cfr_apply_deltas(h, None))
+            tables.append(multi.table())
+        for t in tables:
+            for f in ("regrets", "cum_policy", "cur_policy"):
+                assert np.array_equal(t[f], tr[f]), (plus, f)
+        assert np.abs(tr["regrets"]).max() > 1.0       # the tables are not trivially zero
 
 
 @pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not shipped")
