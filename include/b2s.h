@@ -318,6 +318,18 @@ int  b2s_cfr_set_iteration(void* solver, int iteration);
  * Synchronises `stream`; fails if a sampling step found sum(probabilities) <= z (the reference's
  * SpielFatalError in SampleActionIndex, cfr.cc:617-628). */
 int  b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_update, uint64_t seed, void* stream);
+/* ... with options.  B2S_MCCFR_FULL_AVERAGE = AverageType::kFull (external_sampling_mccfr.h:53-54): no averaging inside the
+ * traversals; after the two traversal phases of every iteration one pass over the whole tree adds
+ * reach[player](h) * regret-matching policy at every decision node (FullUpdateAverage, external_sampling_mccfr.cc:188-230). */
+enum { B2S_MCCFR_FULL_AVERAGE = 1 };
+int  b2s_mccfr_external_iterate_ex(void* solver, int iters, int traversals_per_update, uint64_t seed, int flags, void* stream);
+/* Replaces algorithms::OutcomeSamplingMCCFRSolver (open_spiel/algorithms/outcome_sampling_mccfr.h:40-66; default uniform
+ * policy, no baseline) on a solver created with B2S_CFR_MCCFR_TABLES: `iters` x RunIteration (outcome_sampling_mccfr.cc:
+ * 60-67).  Every (iteration, player) phase runs `trajectories_per_update` independent SampleEpisode trajectories (:150-247) in
+ * parallel against the tables as they stand at the start of the phase; their regret / average-policy deltas are added in the
+ * same fixed order as the external-sampling solver's.  trajectories_per_update = 1 is exactly the reference's algorithm; the
+ * uniform variates come from the position-keyed Philox stream oracle/algorithms/os_mccfr.cc restates.  Synchronises. */
+int  b2s_mccfr_outcome_iterate(void* solver, int iters, int trajectories_per_update, uint64_t seed, double epsilon, void* stream);
 /* The same phase split over GPUs, bit-identical to the single-GPU call: the 64 lanes of the fixed-order reduction are
  * the unit of sharding.  Every rank runs the traversals k with k mod 64 in [lane_begin, lane_end) of phase
  * (current iteration, player) and writes those lanes of partials_d [64][num_entries]; after the lanes of all ranks have

@@ -6,5 +6,5 @@ extension (Game.new_batch -> BatchedState) that the kernels exist for.  All comp
 C ABI in include/b2s.h (libb2s.so); torch is used only for device buffers and streams.
 """
 from ._lib import B2SError as SpielError  # noqa: F401
-from .spiel import (BatchedState, BatchedTrajectory, CFRSolver, ChildSelectionPolicy, ExternalSamplingMCCFRSolver, Game, MCTSBot, RandomRolloutEvaluator, State, load_game, bind_host_to_device, mcts_nodes_used,
+from .spiel import (BatchedState, BatchedTrajectory, CFRSolver, ChildSelectionPolicy, ExternalSamplingMCCFRSolver, OutcomeSamplingMCCFRSolver, Game, MCTSBot, RandomRolloutEvaluator, State, load_game, bind_host_to_device, mcts_nodes_used,
                     mcts_search, registered_names)  # noqa: F401

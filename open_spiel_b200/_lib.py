@@ -105,6 +105,8 @@ SIGNATURES = {
     "b2s_cfr_iterate_sharded": (C.c_int, [_VP, C.c_int, _VP]),
     "b2s_cfr_allreduce_probe": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double)]),
     "b2s_mccfr_external_iterate": (C.c_int, [_VP, C.c_int, C.c_int, _U64, _VP]),
+    "b2s_mccfr_external_iterate_ex": (C.c_int, [_VP, C.c_int, C.c_int, _U64, C.c_int, _VP]),
+    "b2s_mccfr_outcome_iterate": (C.c_int, [_VP, C.c_int, C.c_int, _U64, C.c_double, _VP]),
     "b2s_mccfr_traverse_lanes": (C.c_int, [_VP, C.c_int, C.c_int, _U64, C.c_int, C.c_int, _VP, _VP]),
     "b2s_mccfr_apply_partials": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "b2s_cfr_set_iteration": (C.c_int, [_VP, C.c_int]),

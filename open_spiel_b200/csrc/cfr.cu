@@ -340,7 +340,7 @@ __device__ __forceinline__ u64 mc_child_hash(u64 h, int idx) { return h * 0x9E37
 // Sharding: the rank that owns reduction lanes [lane_begin, lane_begin + L) runs the traversals k with k mod 64 in
 // that range; thread t is traversal k = lane_begin + t mod L + 64 (t div L) and owns row t.  One GPU: L = 64, k = t.
 __global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u64 seed, int K, int lane_begin, int L, int n_threads,
-                                                   double* __restrict__ rows, int* __restrict__ err) {
+                                                   double* __restrict__ rows, int* __restrict__ err, int simple_average) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_threads) return;
   int k = lane_begin + t % L + 64 * (t / L);
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u6
           sum = __dadd_rn(sum, sig[a]);
         }
         if (aidx < 0) { atomicAdd(err, 1); aidx = n - 1; }
-        if (actor == ((p + 1) & 1))                      // simple averaging at the next player's nodes (:176-183)
+        if (simple_average && actor == ((p + 1) & 1))    // simple averaging at the next player's nodes (:176-183)
           for (int a = 0; a < n; ++a) avg_row[off + a] = __dadd_rn(avg_row[off + a], sig[a]);
         h = mc_child_hash(h, aidx);
         node = fc + aidx;
@@ -432,7 +432,10 @@ __global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u6
 // in 128-byte coalesced segments, 8 independent loads in flight per thread.  Touched cells are re-zeroed for the
 // next phase.
 constexpr int kMcLanes = 64, kMcTile = 16;
-__global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_apply(CfrDev d, int p, int K, double* __restrict__ rows) {
+// `stride` = doubles per row (E for external sampling, 2E for outcome sampling); mode 0: an entry of player p receives a regret
+// delta, an entry of the other player an average-policy delta (external sampling); mode 1: every entry -> regrets; mode 2:
+// every entry -> cumulative policy (outcome sampling: two passes over the two halves of its rows).
+__global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_apply(CfrDev d, int p, int K, double* __restrict__ rows, int stride, int mode) {
   __shared__ double part[kMcLanes][kMcTile + 1];
   const int E = d.n_entries;
   const int ex = threadIdx.x, q = threadIdx.y;
@@ -444,13 +447,13 @@ __global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_apply(CfrDev d, in
     for (; k + kMcLanes * (U - 1) < K; k += kMcLanes * U) {
       double v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = rows[(size_t)(k + kMcLanes * u) * E + e];
+      for (int u = 0; u < U; ++u) v[u] = rows[(size_t)(k + kMcLanes * u) * stride + e];
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (v[u] != 0.0) { acc = __dadd_rn(acc, v[u]); rows[(size_t)(k + kMcLanes * u) * E + e] = 0.0; }
+        if (v[u] != 0.0) { acc = __dadd_rn(acc, v[u]); rows[(size_t)(k + kMcLanes * u) * stride + e] = 0.0; }
     }
     for (; k < K; k += kMcLanes) {
-      double* cell = rows + (size_t)k * E + e;
+      double* cell = rows + (size_t)k * stride + e;
       double v = *cell;
       if (v != 0.0) { acc = __dadd_rn(acc, v); *cell = 0.0; }
     }
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_apply(CfrDev d, in
     __syncthreads();
   }
   if (q == 0 && e < E) {
-    double* dst = d.entry_player[e] == p ? d.regrets + e : d.cum_policy + e;
+    double* dst = mode == 0 ? (d.entry_player[e] == p ? d.regrets + e : d.cum_policy + e) : (mode == 1 ? d.regrets + e : d.cum_policy + e);
     *dst = __dadd_rn(*dst, part[0][ex]);
   }
 }
@@ -496,6 +499,126 @@ __global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_combine(CfrDev d, 
   if (q == 0 && e < E) {
     double* dst = d.entry_player[e] == p ? d.regrets + e : d.cum_policy + e;
     *dst = __dadd_rn(*dst, part[0][ex]);
+  }
+}
+
+// ---- AverageType::kFull of external sampling (external_sampling_mccfr.cc:188-230) ------------------------------------------
+// Once per iteration, after both players' traversals: regret matching for every information state, players' reach
+// probabilities down the whole tree (chance nodes pass them through), then every information state adds
+// reach[its player](h) * policy[a] for its histories h in DFS order — the order the reference's post-order recursion
+// produces for the (same-depth, disjoint) histories of one information state.  The reference prunes subtrees whose reach
+// vector is all zero; their contributions would be +0.0 to tables that are never -0.0, so nothing changes.
+__global__ void __launch_bounds__(1024) k_mccfr_full_average(CfrDev d) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int I = tid; I < d.n_infosets; I += nt) {
+    int off = d.is_off[I], na = d.is_off[I + 1] - off;
+    double sum = 0.0;
+    for (int a = 0; a < na; ++a) { double r = d.regrets[off + a]; if (r > 0) sum = __dadd_rn(sum, r); }
+    for (int a = 0; a < na; ++a) {
+      double r = d.regrets[off + a];
+      d.cur_policy[off + a] = sum > 0 ? (r > 0 ? __ddiv_rn(r, sum) : 0.0) : __ddiv_rn(1.0, (double)na);
+    }
+  }
+  __syncthreads();
+  cfr_level_passes(d, tid, nt);
+  for (int I = tid; I < d.n_infosets; I += nt) {
+    const int off = d.is_off[I], na = d.is_off[I + 1] - off, pl = d.is_player[I];
+    for (int hh = d.hist_off[I]; hh < d.hist_off[I + 1]; ++hh) {
+      const double r = d.reach[2 * d.hist[hh] + pl];
+      for (int a = 0; a < na; ++a) d.cum_policy[off + a] = __dadd_rn(d.cum_policy[off + a], __dmul_rn(r, d.cur_policy[off + a]));
+    }
+  }
+}
+
+// ---- outcome-sampling MCCFR (outcome_sampling_mccfr.cc, default uniform policy, no baseline) ---------------------------------
+// One thread = one SampleEpisode (:150-247) of update player p: a single sampled path to a terminal node (epsilon-on-policy
+// at p's nodes :139-147, on-policy elsewhere, chance by its distribution), then the importance-weighted value estimates are
+// unwound and every node of p on the path contributes regret and average-policy deltas to row k of `rows` ([K][2E]: regret
+// deltas, then average-policy deltas), which k_mccfr_apply adds in its fixed order.  Tables are read-only here.
+// u(node, redraw) = U53(Philox(seed; h + 0x632BE59BD9B4E019 redraw, phase, k)); a draw is lo + u (hi - lo), redrawn while it
+// rounds up to hi — the stream and the two samplers oracle/algorithms/os_mccfr.cc (rng_mode 1) restates.
+__device__ __forceinline__ double os_real(u64 seed, u64 h, u32 phase, u32 k, double lo, double hi) {
+  for (u32 redraw = 0;; ++redraw) {
+    double u = mc_uniform(seed, h + 0x632BE59BD9B4E019ull * (u64)redraw, phase, k);
+    double r = __dadd_rn(lo, __dmul_rn(u, __dsub_rn(hi, lo)));
+    if (r < hi || lo == hi) return r;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_mccfr_os(CfrDev d, int p, u32 phase, u64 seed, int K, double epsilon, double* __restrict__ rows,
+                                                   int* __restrict__ err) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int E = d.n_entries;
+  double* reg_row = rows + (size_t)k * 2 * E;
+  double* pol_row = reg_row + E;
+  struct Frame { int off, n, sampled, actor; double my_reach, opp_reach, sample_reach, sample_prob; double sig[kMcMaxActions]; };
+  Frame st[kMcMaxDepth];
+  int sp = 0, node = 0;
+  u64 h = 0;
+  double my_reach = 1.0, opp_reach = 1.0, sample_reach = 1.0, value;
+  for (;;) {
+    const int4 rec = __ldg(d.mc_node + node);
+    const int kind = rec.z & 0xff, actor = (rec.z >> 8) & 0xff, n = rec.z >> 16, fc = rec.x;
+    if (kind == 0) { value = d.ret[2 * node + p]; break; }
+    if (kind == 1) {                                     // SampleAction(ChanceOutcomes(), z), spiel.cc:372-409
+      double z = os_real(seed, h, phase, (u32)k, 0.0, 1.0);
+      int chosen = -1;
+      double sum = 0.0;
+      for (int c = 0; c < n; ++c) {
+        double prob = d.chance_prob[fc + c];
+        if (sum <= z && z < __dadd_rn(sum, prob)) { chosen = c; break; }
+        sum = __dadd_rn(sum, prob);
+      }
+      if (chosen < 0) { atomicAdd(err, 1); chosen = n - 1; }
+      const double prob = d.chance_prob[fc + chosen];
+      opp_reach = __dmul_rn(prob, opp_reach);
+      sample_reach = __dmul_rn(prob, sample_reach);
+      h = mc_child_hash(h, chosen);
+      node = fc + chosen;
+      continue;
+    }
+    Frame& f = st[sp++];
+    f.off = rec.y; f.n = n; f.actor = actor;
+    f.my_reach = my_reach; f.opp_reach = opp_reach; f.sample_reach = sample_reach;
+    {                                                    // info_state_copy.ApplyRegretMatching(), cfr.cc:596-615
+      double sum_pos = 0.0;
+      for (int a = 0; a < n; ++a) { double rg = d.regrets[f.off + a]; if (rg > 0) sum_pos = __dadd_rn(sum_pos, rg); }
+      for (int a = 0; a < n; ++a) {
+        double rg = d.regrets[f.off + a];
+        f.sig[a] = sum_pos > 0 ? (rg > 0 ? __ddiv_rn(rg, sum_pos) : 0.0) : __ddiv_rn(1.0, (double)n);
+      }
+    }
+    double sp_a[kMcMaxActions], total = 0.0;             // SamplePolicy (:139-147) / the current policy; discrete_distribution
+    for (int a = 0; a < n; ++a) {
+      sp_a[a] = actor == p ? __dadd_rn(__ddiv_rn(__dmul_rn(epsilon, 1.0), (double)n), __dmul_rn(__dsub_rn(1.0, epsilon), f.sig[a])) : f.sig[a];
+      total = __dadd_rn(total, sp_a[a]);
+    }
+    const double u = os_real(seed, h, phase, (u32)k, 0.0, total);
+    int sampled = n - 1;
+    double acc = 0.0;
+    for (int a = 0; a < n; ++a) { acc = __dadd_rn(acc, sp_a[a]); if (u < acc) { sampled = a; break; } }
+    f.sampled = sampled; f.sample_prob = sp_a[sampled];
+    if (actor == p) my_reach = __dmul_rn(my_reach, f.sig[sampled]); else opp_reach = __dmul_rn(opp_reach, f.sig[sampled]);
+    sample_reach = __dmul_rn(sample_reach, sp_a[sampled]);
+    h = mc_child_hash(h, sampled);
+    node = fc + sampled;
+  }
+  // ---- unwind: child values, value estimates, updates at the update player's nodes (:206-245) ----
+  while (sp > 0) {
+    const Frame& f = st[--sp];
+    double value_estimate = 0.0, cv_sampled = __dadd_rn(0.0, __ddiv_rn(__dsub_rn(value, 0.0), f.sample_prob));
+    for (int a = 0; a < f.n; ++a) value_estimate = __dadd_rn(value_estimate, __dmul_rn(f.sig[a], a == f.sampled ? cv_sampled : 0.0));
+    if (f.actor == p) {
+      const double cf_value = __ddiv_rn(__dmul_rn(value_estimate, f.opp_reach), f.sample_reach);
+      for (int a = 0; a < f.n; ++a) {
+        const double cv = a == f.sampled ? cv_sampled : 0.0;
+        const double cf_action_value = __ddiv_rn(__dmul_rn(cv, f.opp_reach), f.sample_reach);
+        reg_row[f.off + a] = __dsub_rn(cf_action_value, cf_value);
+        pol_row[f.off + a] = __ddiv_rn(__dmul_rn(f.my_reach, f.sig[a]), f.sample_reach);
+      }
+    }
+    value = value_estimate;
   }
 }
 
@@ -822,7 +945,7 @@ int b2s_mccfr_traverse_lanes(void* solver, int player, int traversals_per_update
   if (int r = mccfr_prepare(S, n_threads)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned phase = (unsigned)(S->iteration * 2 + player);
-  k_mccfr_es<<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, S->mc_rows, S->mc_err);
+  k_mccfr_es<<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, S->mc_rows, S->mc_err, 1);
   k_mccfr_partial<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, K, lane_begin, L, S->mc_rows, partials_d);
   g_launches += 2;
   cudaError_t e = cudaGetLastError();
@@ -847,22 +970,7 @@ int b2s_mccfr_apply_partials(void* solver, int player, const double* partials_d,
   return 0;
 }
 
-int b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_update, uint64_t seed, void* stream) {
-  if (!solver) return fail("mccfr: null solver");
-  CfrSolver* S = (CfrSolver*)solver;
-  if (iters < 0 || traversals_per_update < 1) return fail("mccfr: iters >= 0 and traversals_per_update >= 1 required");
-  if (int r = mccfr_prepare(S, traversals_per_update)) return r;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int K = traversals_per_update, E = S->d.n_entries;
-  for (int it = 0; it < iters; ++it) {
-    for (int p = 0; p < 2; ++p) {
-      unsigned phase = (unsigned)(S->iteration * 2 + p);
-      k_mccfr_es<<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, 0, kMcLanes, K, S->mc_rows, S->mc_err);
-      k_mccfr_apply<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, p, K, S->mc_rows);
-      g_launches += 2;
-    }
-    ++S->iteration;
-  }
+static int mccfr_check_errors(CfrSolver* S, cudaStream_t st) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_mccfr launch");
   int bad = 0;
@@ -870,6 +978,54 @@ int b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_updat
   B2S_CU(cudaStreamSynchronize(st));
   if (bad) return fail("mccfr: a sampling step found sum of probabilities <= z (SampleActionIndex, cfr.cc:617-628)");
   return 0;
+}
+
+int b2s_mccfr_external_iterate_ex(void* solver, int iters, int traversals_per_update, uint64_t seed, int flags, void* stream) {
+  if (!solver) return fail("mccfr: null solver");
+  CfrSolver* S = (CfrSolver*)solver;
+  if (iters < 0 || traversals_per_update < 1) return fail("mccfr: iters >= 0 and traversals_per_update >= 1 required");
+  if (int r = mccfr_prepare(S, traversals_per_update)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = traversals_per_update, E = S->d.n_entries;
+  const int full = (flags & B2S_MCCFR_FULL_AVERAGE) ? 1 : 0;
+  for (int it = 0; it < iters; ++it) {
+    for (int p = 0; p < 2; ++p) {
+      unsigned phase = (unsigned)(S->iteration * 2 + p);
+      k_mccfr_es<<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, 0, kMcLanes, K, S->mc_rows, S->mc_err, full ? 0 : 1);
+      k_mccfr_apply<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, p, K, S->mc_rows, E, 0);
+      g_launches += 2;
+    }
+    if (full) { k_mccfr_full_average<<<1, 1024, 0, st>>>(S->d); ++g_launches; }     // RunIteration, external_sampling_mccfr.cc:76-79
+    ++S->iteration;
+  }
+  return mccfr_check_errors(S, st);
+}
+
+int b2s_mccfr_external_iterate(void* solver, int iters, int traversals_per_update, uint64_t seed, void* stream) {
+  return b2s_mccfr_external_iterate_ex(solver, iters, traversals_per_update, seed, 0, stream);
+}
+
+int b2s_mccfr_outcome_iterate(void* solver, int iters, int trajectories_per_update, uint64_t seed, double epsilon, void* stream) {
+  if (!solver) return fail("mccfr: null solver");
+  CfrSolver* S = (CfrSolver*)solver;
+  if (iters < 0 || trajectories_per_update < 1) return fail("mccfr: iters >= 0 and trajectories_per_update >= 1 required");
+  if (!(epsilon >= 0.0 && epsilon <= 1.0)) return fail("mccfr: epsilon must lie in [0, 1]");
+  if (int r = mccfr_prepare(S, 2 * trajectories_per_update)) return r;       // rows are [K][2E]
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = trajectories_per_update, E = S->d.n_entries;
+  const dim3 ablock(kMcTile, kMcLanes);
+  const unsigned agrid = (unsigned)((E + kMcTile - 1) / kMcTile);
+  for (int it = 0; it < iters; ++it) {
+    for (int p = 0; p < 2; ++p) {
+      unsigned phase = (unsigned)(S->iteration * 2 + p);
+      k_mccfr_os<<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, epsilon, S->mc_rows, S->mc_err);
+      k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows, 2 * E, 1);
+      k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows + E, 2 * E, 2);
+      g_launches += 3;
+    }
+    ++S->iteration;
+  }
+  return mccfr_check_errors(S, st);
 }
 
 int b2s_cfr_info_get(void* solver, b2s_cfr_info* out) {

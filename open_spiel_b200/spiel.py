@@ -690,15 +690,35 @@ class ExternalSamplingMCCFRSolver(CFRSolver):
     (algorithms/external_sampling_mccfr.h:55-110) with device-resident tables.  `traversals_per_update` independent
     traversals run in parallel per (iteration, traverser) phase against frozen tables; 1 = the reference's algorithm."""
 
-    def __init__(self, game, seed=0, traversals_per_update=1):
+    def __init__(self, game, seed=0, traversals_per_update=1, full_average=False):
+        """full_average = AverageType::kFull (external_sampling_mccfr.h:53-54) instead of the default kSimple."""
         super().__init__(game, _mccfr_tables=True)
-        self.seed, self.traversals_per_update = int(seed), int(traversals_per_update)
+        self.seed, self.traversals_per_update, self.full_average = int(seed), int(traversals_per_update), bool(full_average)
 
     def run_iteration(self, iterations=1):
         """ExternalSamplingMCCFRSolver::RunIteration (external_sampling_mccfr.cc:71-80), `iterations` times."""
         st = C.c_void_p(torch.cuda.current_stream(torch.device("cuda", self.game.device)).cuda_stream)
-        check(lib().b2s_mccfr_external_iterate(self._h, int(iterations), self.traversals_per_update, self.seed, st))
+        check(lib().b2s_mccfr_external_iterate_ex(self._h, int(iterations), self.traversals_per_update, self.seed,
+                                                  1 if self.full_average else 0, st))
 
     def evaluate_and_update_policy(self, iterations=1):
         raise B2SError("ExternalSamplingMCCFRSolver: use run_iteration()")
+
+
+class OutcomeSamplingMCCFRSolver(CFRSolver):
+    """Mirror of pyspiel.OutcomeSamplingMCCFRSolver(game, epsilon, seed) (algorithms/outcome_sampling_mccfr.h:40-66; default
+    uniform policy, no baseline) with device-resident tables.  `trajectories_per_update` independent episodes run in parallel
+    per (iteration, player) phase against frozen tables; 1 = the reference's algorithm."""
+
+    def __init__(self, game, epsilon=0.6, seed=0, trajectories_per_update=1):
+        super().__init__(game, _mccfr_tables=True)
+        self.epsilon, self.seed, self.trajectories_per_update = float(epsilon), int(seed), int(trajectories_per_update)
+
+    def run_iteration(self, iterations=1):
+        """OutcomeSamplingMCCFRSolver::RunIteration (outcome_sampling_mccfr.cc:60-67), `iterations` times."""
+        st = C.c_void_p(torch.cuda.current_stream(torch.device("cuda", self.game.device)).cuda_stream)
+        check(lib().b2s_mccfr_outcome_iterate(self._h, int(iterations), self.trajectories_per_update, self.seed, self.epsilon, st))
+
+    def evaluate_and_update_policy(self, iterations=1):
+        raise B2SError("OutcomeSamplingMCCFRSolver: use run_iteration()")
 

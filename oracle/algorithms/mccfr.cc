@@ -45,6 +45,7 @@ struct Delta { std::string key; bool average; std::vector<double> d; };
 struct EsMccfr {
   const Game* game = nullptr;
   int n = 2, rng_mode = 0, K = 1, iteration = 0;
+  bool full_average = false;       // AverageType::kFull (external_sampling_mccfr.h:53-54)
   uint64_t seed = 0;
   std::mt19937 mt;
   std::uniform_real_distribution<double> dist{0.0, 1.0};
@@ -133,8 +134,41 @@ struct EsMccfr {
       for (size_t a = 0; a < A; ++a) d.d[a] = child_values[a] - value;
       out->push_back(d);
     }
-    if (cur == (player + 1) % n) out->push_back(Delta{key, true, policy});
+    if (!full_average && cur == (player + 1) % n) out->push_back(Delta{key, true, policy});
     return value;
+  }
+
+  // FullUpdateAverage (external_sampling_mccfr.cc:188-230): one pass over the whole tree per iteration; every decision
+  // node adds reach[current player] * regret-matching policy to its information state's cumulative policy (post-order)
+  void FullUpdateAverage(const State& s, const std::vector<double>& reach) {
+    if (s.IsTerminal()) return;
+    if (s.IsChanceNode()) {
+      for (auto a : s.LegalActions()) { auto c = s.Clone(); c->ApplyAction(a); FullUpdateAverage(*c, reach); }
+      return;
+    }
+    double sum = 0.0;
+    for (double r : reach) sum += r;
+    if (sum == 0.0) return;
+    int cur = s.CurrentPlayer();
+    auto la = s.LegalActions();
+    const size_t A = la.size();
+    std::string key = s.InformationStateString(cur);
+    std::vector<double> policy(A);
+    {
+      const McValues& v = Lookup(s, cur, la);
+      double sum_pos = 0.0;
+      for (size_t a = 0; a < A; ++a) if (v.regrets[a] > 0) sum_pos += v.regrets[a];
+      for (size_t a = 0; a < A; ++a) policy[a] = sum_pos > 0 ? (v.regrets[a] > 0 ? v.regrets[a] / sum_pos : 0) : 1.0 / A;
+    }
+    for (size_t a = 0; a < A; ++a) {
+      std::vector<double> nr = reach;
+      nr[cur] *= policy[a];
+      auto c = s.Clone();
+      c->ApplyAction(la[a]);
+      FullUpdateAverage(*c, nr);
+    }
+    McValues& v = table[key];
+    for (size_t a = 0; a < A; ++a) v.cum_policy[a] += reach[cur] * policy[a];
   }
 
   void RunIteration() {
@@ -162,6 +196,10 @@ struct EsMccfr {
         for (size_t a = 0; a < ps[0].size(); ++a) (kv.first.second ? v.cum_policy : v.regrets)[a] += ps[0][a];
       }
     }
+    if (full_average) {
+      auto root = game->NewInitialState();
+      FullUpdateAverage(*root, std::vector<double>(n, 1.0));
+    }
     ++iteration;
   }
 };
@@ -171,6 +209,7 @@ struct EsMccfr {
 
 extern "C" {
 
+void orc_mccfr_set_full_average(void* m, int on) { ((oracle::EsMccfr*)m)->full_average = on != 0; }
 void* orc_mccfr_new(void* game, uint64_t seed, int rng_mode, int traversals_per_update) {
   auto* m = new oracle::EsMccfr;
   m->game = (oracle::Game*)game;

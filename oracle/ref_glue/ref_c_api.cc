@@ -11,6 +11,7 @@
 #include "open_spiel/algorithms/cfr.h"
 #include "open_spiel/algorithms/external_sampling_mccfr.h"
 #include "open_spiel/algorithms/mcts.h"
+#include "open_spiel/algorithms/outcome_sampling_mccfr.h"
 #include "open_spiel/algorithms/tabular_exploitability.h"
 #include "open_spiel/algorithms/trajectories.h"
 #include "open_spiel/policy.h"
@@ -210,6 +211,10 @@ int ref_record_batched_trajectory(void* g, int batch_size, int seed, int T, floa
 void* ref_mccfr_new(void* g, int seed) {
   GUARD(return new open_spiel::algorithms::ExternalSamplingMCCFRSolver(*((GameHolder*)g)->game, seed), return nullptr);
 }
+void* ref_mccfr_new_full(void* g, int seed) {      // AverageType::kFull (external_sampling_mccfr.h:53-54)
+  GUARD(return new open_spiel::algorithms::ExternalSamplingMCCFRSolver(*((GameHolder*)g)->game, seed,
+                                                                        open_spiel::algorithms::AverageType::kFull), return nullptr);
+}
 void ref_mccfr_free(void* c) { delete (open_spiel::algorithms::ExternalSamplingMCCFRSolver*)c; }
 int ref_mccfr_iterate(void* c, int iters) {
   GUARD(for (int i = 0; i < iters; ++i) ((open_spiel::algorithms::ExternalSamplingMCCFRSolver*)c)->RunIteration(); return 0,
@@ -241,6 +246,32 @@ double ref_mccfr_nash_conv(void* g, void* c) {
   auto* solver = (open_spiel::algorithms::ExternalSamplingMCCFRSolver*)c;
   GUARD(return open_spiel::algorithms::NashConv(*((GameHolder*)g)->game, *solver->AveragePolicy(), /*use_state_get_policy=*/true),
                return -1.0);
+}
+
+// ---- OutcomeSamplingMCCFRSolver (algorithms/outcome_sampling_mccfr.h:40-66) -------------------------------------------
+using OsSolver = open_spiel::algorithms::OutcomeSamplingMCCFRSolver;
+void* ref_osmccfr_new(void* g, double epsilon, int seed) { GUARD(return new OsSolver(*((GameHolder*)g)->game, epsilon, seed), return nullptr); }
+void ref_osmccfr_free(void* c) { delete (OsSolver*)c; }
+int ref_osmccfr_iterate(void* c, int iters) { GUARD(for (int i = 0; i < iters; ++i) ((OsSolver*)c)->RunIteration(); return 0, return 1); }
+int ref_osmccfr_keys(void* c, char* buf, int cap) {
+  std::vector<std::string> keys;
+  for (auto& kv : ((OsSolver*)c)->InfoStateValuesTable()) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end());
+  std::string s;
+  for (auto& k : keys) { s += k; s += '\n'; }
+  return CopyStr(s, buf, cap);
+}
+int ref_osmccfr_get(void* c, const char* key, int64_t* legal, double* regrets, double* cum_policy, int cap) {
+  auto& table = ((OsSolver*)c)->InfoStateValuesTable();
+  auto it = table.find(key);
+  if (it == table.end()) return -1;
+  const auto& v = it->second;
+  int n = (int)v.legal_actions.size();
+  for (int i = 0; i < n && i < cap; ++i) { legal[i] = v.legal_actions[i]; regrets[i] = v.cumulative_regrets[i]; cum_policy[i] = v.cumulative_policy[i]; }
+  return n;
+}
+double ref_osmccfr_nash_conv(void* g, void* c) {
+  GUARD(return open_spiel::algorithms::NashConv(*((GameHolder*)g)->game, *((OsSolver*)c)->AveragePolicy(), /*use_state_get_policy=*/true), return -1.0);
 }
 
 // ---- text formats (Game::ToString spiel.cc:802-806, CFRSolverBase::Serialize cfr.cc:284-307, DeserializeCFRSolver :704-715) ----

@@ -273,7 +273,7 @@ class OracleMCCFR:
     """oracle/algorithms/mccfr.cc: restatement of algorithms::ExternalSamplingMCCFRSolver (kSimple averaging).
     rng_mode 0 = the reference's std::mt19937 stream, 1 = the device solver's position-keyed Philox stream."""
 
-    def __init__(self, game, seed=0, rng_mode=1, traversals_per_update=1):
+    def __init__(self, game, seed=0, rng_mode=1, traversals_per_update=1, full_average=False):
         L = lib()
         L.orc_mccfr_new.restype = C.c_void_p
         L.orc_mccfr_new.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
@@ -284,6 +284,8 @@ class OracleMCCFR:
                                     C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
         self.game = game
         self._c = L.orc_mccfr_new(game._g, seed, rng_mode, traversals_per_update)
+        L.orc_mccfr_set_full_average.argtypes = [C.c_void_p, C.c_int]
+        L.orc_mccfr_set_full_average(self._c, int(full_average))
 
     def __del__(self):
         try:
@@ -303,6 +305,45 @@ class OracleMCCFR:
             r, cu = (C.c_double * 16)(), (C.c_double * 16)()
             pl = C.c_int()
             n = L.orc_mccfr_get(self._c, k, key, 512, legal, r, cu, 16, C.byref(pl))
+            out[key.value.decode()] = {"legal": list(legal[:n]), "regrets": list(r[:n]), "cum_policy": list(cu[:n]),
+                                       "player": pl.value}
+        return out
+
+
+class OracleOSMCCFR:
+    """oracle/algorithms/os_mccfr.cc: restatement of algorithms::OutcomeSamplingMCCFRSolver(game, epsilon, seed).
+    rng_mode 0 = the reference's mt19937 stream through the shim's distributions, 1 = the device's Philox stream."""
+
+    def __init__(self, game, seed=0, rng_mode=1, trajectories_per_update=1, epsilon=0.6):
+        L = lib()
+        L.orc_osmccfr_new.restype = C.c_void_p
+        L.orc_osmccfr_new.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_double]
+        L.orc_osmccfr_free.argtypes = [C.c_void_p]
+        L.orc_osmccfr_iterate.argtypes = [C.c_void_p, C.c_int]
+        L.orc_osmccfr_num_infosets.argtypes = [C.c_void_p]
+        L.orc_osmccfr_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int)]
+        self.game = game
+        self._c = L.orc_osmccfr_new(game._g, seed, rng_mode, trajectories_per_update, epsilon)
+
+    def __del__(self):
+        try:
+            lib().orc_osmccfr_free(self._c)
+        except Exception:
+            pass
+
+    def iterate(self, iters=1):
+        assert lib().orc_osmccfr_iterate(self._c, iters) == 0, "sampling failed"
+
+    def table(self):
+        L = lib()
+        out = {}
+        for k in range(L.orc_osmccfr_num_infosets(self._c)):
+            key = C.create_string_buffer(512)
+            legal = (C.c_int64 * 16)()
+            r, cu = (C.c_double * 16)(), (C.c_double * 16)()
+            pl = C.c_int()
+            n = L.orc_osmccfr_get(self._c, k, key, 512, legal, r, cu, 16, C.byref(pl))
             out[key.value.decode()] = {"legal": list(legal[:n]), "regrets": list(r[:n]), "cum_policy": list(cu[:n]),
                                        "player": pl.value}
         return out

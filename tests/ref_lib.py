@@ -240,10 +240,12 @@ def ref_record_batched_trajectory(game, batch_size, seed, T):
 class RefMCCFR:
     """The unmodified reference's algorithms::ExternalSamplingMCCFRSolver(game, seed) (AverageType::kSimple)."""
 
-    def __init__(self, game, seed=0):
+    def __init__(self, game, seed=0, full_average=False):
         L = lib()
         L.ref_mccfr_new.restype = C.c_void_p
         L.ref_mccfr_new.argtypes = [C.c_void_p, C.c_int]
+        L.ref_mccfr_new_full.restype = C.c_void_p
+        L.ref_mccfr_new_full.argtypes = [C.c_void_p, C.c_int]
         L.ref_mccfr_free.argtypes = [C.c_void_p]
         L.ref_mccfr_iterate.argtypes = [C.c_void_p, C.c_int]
         L.ref_mccfr_keys.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
@@ -252,7 +254,7 @@ class RefMCCFR:
         L.ref_mccfr_nash_conv.restype = C.c_double
         L.ref_mccfr_nash_conv.argtypes = [C.c_void_p, C.c_void_p]
         self.game = game
-        self._c = L.ref_mccfr_new(game._g, seed)
+        self._c = (L.ref_mccfr_new_full if full_average else L.ref_mccfr_new)(game._g, seed)
 
     def __del__(self):
         try:
@@ -347,3 +349,46 @@ def replay_batch(game_string, hist, final_actions, mask_words, threads=0):
                              out["mask_after"].ctypes.data, out["obs_bits"].ctypes.data)
     out["failed_lanes"] = int(bad)
     return out
+
+
+class RefOSMCCFR:
+    """The unmodified reference's algorithms::OutcomeSamplingMCCFRSolver(game, epsilon, seed)."""
+
+    def __init__(self, game, seed=0, epsilon=0.6):
+        L = lib()
+        L.ref_osmccfr_new.restype = C.c_void_p
+        L.ref_osmccfr_new.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.ref_osmccfr_free.argtypes = [C.c_void_p]
+        L.ref_osmccfr_iterate.argtypes = [C.c_void_p, C.c_int]
+        L.ref_osmccfr_keys.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.ref_osmccfr_get.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+        L.ref_osmccfr_nash_conv.restype = C.c_double
+        L.ref_osmccfr_nash_conv.argtypes = [C.c_void_p, C.c_void_p]
+        self.game = game
+        self._c = L.ref_osmccfr_new(game._g, epsilon, seed)
+
+    def __del__(self):
+        try:
+            lib().ref_osmccfr_free(self._c)
+        except Exception:
+            pass
+
+    def iterate(self, iters=1):
+        assert lib().ref_osmccfr_iterate(self._c, iters) == 0, lib().ref_last_error()
+
+    def table(self):
+        L = lib()
+        buf = C.create_string_buffer(1 << 20)
+        L.ref_osmccfr_keys(self._c, buf, 1 << 20)
+        out = {}
+        for key in buf.value.decode().split("\n"):
+            legal = (C.c_int64 * 16)()
+            r, cu = (C.c_double * 16)(), (C.c_double * 16)()
+            n = L.ref_osmccfr_get(self._c, key.encode(), legal, r, cu, 16)
+            if n < 0:
+                continue
+            out[key] = {"legal": list(legal[:n]), "regrets": list(r[:n]), "cum_policy": list(cu[:n])}
+        return out
+
+    def nash_conv(self):
+        return lib().ref_osmccfr_nash_conv(self.game._g, self._c)

@@ -88,3 +88,51 @@ def test_lane_sharded_path_is_bit_identical_to_single_gpu(gs, K, world):
         for f in ("regrets", "cum_policy"):
             assert np.array_equal(a[f], b[f]), (gs, K, world, f)
     assert sharded.info().iteration == 3
+
+
+@pytest.mark.parametrize("gs,K,steps", [("kuhn_poker", 1, [1, 5, 40]), ("leduc_poker", 1, [1, 6, 30]), ("leduc_poker", 64, [1, 4])])
+def test_device_full_average_equals_oracle_bitwise(gs, K, steps):
+    """AverageType::kFull (external_sampling_mccfr.cc:76-79, 188-230): the oracle's restatement equals the unmodified
+    reference bit for bit (tests/test_os_mccfr_oracle.py); the device must equal the oracle on the Philox stream."""
+    game, og = b2.load_game(gs), OracleGame(gs)
+    dev = b2.ExternalSamplingMCCFRSolver(game, seed=77 + K, traversals_per_update=K, full_average=True)
+    cpu = OracleMCCFR(og, seed=77 + K, rng_mode=1, traversals_per_update=K, full_average=True)
+    tensors = infostate_tensors(og)
+    for n in steps:
+        dev.run_iteration(n)
+        cpu.iterate(n)
+        compare_all_states(dev.table(), cpu.table(), tensors)
+
+
+def compare_all_states(dev_table, cpu_table, tensors):
+    """Like compare(); information states the sampled traversals have not reached are created by FullUpdateAverage on the
+    CPU side too, so every device row has a counterpart (or still holds the initial values)."""
+    compare(dev_table, cpu_table, tensors)
+
+
+@pytest.mark.parametrize("gs,K,eps,steps", [("kuhn_poker", 1, 0.6, [1, 5, 60, 600]), ("leduc_poker", 1, 0.6, [1, 10, 300]),
+                                            ("leduc_poker", 1, 0.25, [200]), ("kuhn_poker", 64, 0.6, [1, 3, 20]),
+                                            ("leduc_poker", 256, 0.6, [1, 2, 8]), ("leduc_poker", 4096, 0.9, [2])])
+def test_device_outcome_sampling_equals_oracle_bitwise(gs, K, eps, steps):
+    """OutcomeSamplingMCCFRSolver (outcome_sampling_mccfr.cc): device vs oracle/algorithms/os_mccfr.cc on the same Philox
+    stream, bit for bit; the oracle equals the unmodified reference on the reference's own stream."""
+    from oracle_lib import OracleOSMCCFR
+    game, og = b2.load_game(gs), OracleGame(gs)
+    seed = 0xABCD + K
+    dev = b2.OutcomeSamplingMCCFRSolver(game, epsilon=eps, seed=seed, trajectories_per_update=K)
+    cpu = OracleOSMCCFR(og, seed=seed, rng_mode=1, trajectories_per_update=K, epsilon=eps)
+    tensors = infostate_tensors(og)
+    for n in steps:
+        dev.run_iteration(n)
+        cpu.iterate(n)
+        compare(dev.table(), cpu.table(), tensors)
+
+
+def test_outcome_sampling_converges():
+    # outcome_sampling_mccfr_test.cc: NashConv of the average policy falls with iterations (kuhn: < 0.17 after 10000 there)
+    s = b2.OutcomeSamplingMCCFRSolver(b2.load_game("kuhn_poker"), seed=4, trajectories_per_update=256)
+    s.run_iteration(400)
+    assert s.nash_conv() < 0.1
+    t = b2.OutcomeSamplingMCCFRSolver(b2.load_game("leduc_poker"), seed=4, trajectories_per_update=4096)
+    t.run_iteration(100)
+    assert t.nash_conv() < 2.0
