@@ -32,6 +32,7 @@ struct Ctx {
   u64* hist;          // go: [max_len+1][cap] zobrist history, else nullptr
   ErrBuf* err;
   long long lane0 = 0;   // batch lane of this view's lane 0 (sub-range views: planes / hist are pre-offset, errors report lane0 + i)
+  u32* filter = nullptr; // optional thread-private membership filter over this lane's history hashes (go superko, see rules_go.cuh)
 };
 
 // ---- Philox4x32-10 counter RNG (Salmon et al. 2011), key = seed, counter = (lane, ply) ----------

@@ -208,6 +208,14 @@ __global__ void __launch_bounds__(128, MINBLOCKS) k_mcts(Ctx rootctx, Ctx workct
     r.meta = mcts_meta(0, 0, R::cur_player(root, cfg), 0, 0);
     pool[0] = r;
   }
+  // optional per-lane history filter (go: Bloom filter over the superko hash history, rules_go.cuh): built once from the
+  // root's history, copied at the start of every simulation, updated by the rule core along the descent and the playout
+  constexpr int kFW = R::kFilterWords > 0 ? R::kFilterWords : 1;
+  u32 root_filter[kFW], filter[kFW];
+  if constexpr (R::kFilterWords > 0) {
+    R::filter_build(root_filter, workctx, tree, root);
+    workctx.filter = filter;
+  }
   const double inv_rollouts = __ddiv_rn(1.0, (double)P.n_rollouts);
   const float inv_rollouts_f = (float)inv_rollouts, c_f = (float)P.uct_c;
   u32 path[MAXPATH];
@@ -221,6 +229,8 @@ __global__ void __launch_bounds__(128, MINBLOCKS) k_mcts(Ctx rootctx, Ctx workct
   for (; sim < P.sims && !failed; ++sim) {
     if (P.max_seconds > 0 && (double)(mcts_now_ns() - t_start) * 1e-9 >= P.max_seconds) break;
     typename R::S s = root;
+    if constexpr (R::kFilterWords > 0)
+      for (int w = 0; w < kFW; ++w) filter[w] = root_filter[w];
     int depth = 0;
     u32 cur = 0;
     path[depth++] = cur;

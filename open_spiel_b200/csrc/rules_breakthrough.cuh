@@ -17,6 +17,7 @@ struct BreakthroughRules {
   static constexpr int kPlayers = 2;
   static constexpr int kMaxPath = 224;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kMaxLegal = 96;   // most legal actions any state can have (MCTS children block size)
+  static constexpr int kFilterWords = 0;   // no per-lane history filter (see rules_go.cuh)
   static constexpr int kIlp = 2;      // lanes per thread in the streaming kernels
   static constexpr int kMinBlocks = 4;
   static constexpr bool kHasInfoState = false;

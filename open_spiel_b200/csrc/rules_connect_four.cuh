@@ -21,6 +21,7 @@ struct ConnectFourRules {
   static constexpr int kPlayers = 2;
   static constexpr int kMaxPath = 72;   // MCTS path stack (>= max_game_length + 2); 0 = no device MCTS
   static constexpr int kMaxLegal = 32;   // most legal actions any state can have (MCTS children block size)
+  static constexpr int kFilterWords = 0;   // no per-lane history filter (see rules_go.cuh)
   static constexpr int kIlp = 4;      // lanes per thread in the streaming kernels
   static constexpr int kMinBlocks = 6;   // <= 42 registers (capping k_apply at 32 registers to fit the 1M-lane grid in one wave spills and was measured 20 % slower)
   static constexpr bool kHasInfoState = false;
