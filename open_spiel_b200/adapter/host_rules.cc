@@ -4,6 +4,12 @@
 // contiguous, which is exactly the b2s_state_get blob layout).
 #include "host_rules.h"
 
+// The rule cores live in namespace b2s and define globals there (go's Zobrist table).  libb2s.so carries host-side shadow
+// symbols of the same names for its __device__ globals, and an executable that links both would interpose them (the
+// library's cudaMemcpyToSymbol would then be handed this file's array as the symbol).  The host build therefore compiles
+// the cores in a namespace of its own.
+#define b2s b2s_hostcore
+
 #include "../csrc/host_compat.h"   // host definitions of the device intrinsics; must precede the rule cores
 
 #include "../csrc/common.cuh"

@@ -185,6 +185,8 @@ int b2s_batch_create(int game_id, const b2s_params* params, int64_t capacity, in
   cudaError_t ce = cudaSetDevice(device);
   if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "cudaSetDevice"); }
   ops->device_init();
+  ce = cudaGetLastError();                       // e.g. go's Zobrist table upload (cudaMemcpyToSymbol)
+  if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "per-game device tables"); }
   size_t bytes = ops->chunk_bytes() * (size_t)ops->chunks() * (size_t)capacity;
   ce = cudaMalloc(&B->planes, bytes);
   if (ce != cudaSuccess) { delete B; return cuda_fail(ce, "cudaMalloc(state planes)"); }
@@ -312,13 +314,17 @@ static int step_host_impl(Batch* B, const void* actions_h, int action_bytes, uin
   // (stream hs2) — PCIe is full duplex, so the call costs about max(H2D, D2H) instead of their sum.
   cudaStream_t st = pipe.hs, st2 = pipe.hs2;
   const size_t W = (size_t)B->info.mask_words, P = (size_t)B->info.num_players, cb = B->ops->chunk_bytes();
+  const size_t ab = (size_t)action_bytes;
   static const int n_chunks = [] {                 // B2S_HOST_CHUNKS=1..8 overrides the default (tuning knob)
     const char* e = getenv("B2S_HOST_CHUNKS");
     int v = e ? atoi(e) : kHostChunksDefault;
     return v < 1 ? 1 : (v > kHostChunks ? kHostChunks : v);
   }();
-  const int64_t chunk = (n >= (1 << 18) && n_chunks > 1) ? ((n + n_chunks - 1) / n_chunks + 1023) / 1024 * 1024 : n;
-  const size_t ab = (size_t)action_bytes;
+  // two chunks overlap the upload + kernel of one half with the download of the other; that only pays when the copies
+  // are long compared with the per-copy launch cost (a few microseconds): below ~4 MiB of traffic the call runs as one chunk
+  const size_t bytes_per_lane = ab + (compact ? 1 : (term_or_status_h ? 1 : 0) + (rets_h ? sizeof(float) * P : 0)) + (mask_h ? sizeof(u32) * W : 0);
+  const bool split = n_chunks > 1 && n >= (1 << 18) && bytes_per_lane * (size_t)n >= (4u << 20);
+  const int64_t chunk = split ? ((n + n_chunks - 1) / n_chunks + 1023) / 1024 * 1024 : n;
   int c = 0, rc = 0;
   for (int64_t lo = 0; lo < n && !rc; lo += chunk, ++c) {
     const int64_t len = n - lo < chunk ? n - lo : chunk;
@@ -562,6 +568,7 @@ int b2s_mcts_search(void* roots_batch, int64_t n_trees, const b2s_mcts_config* c
   a.max_nodes = (int)cfg->max_nodes_per_tree; a.max_seconds = cfg->max_wall_clock_time;
   a.seed = cfg->seed; a.tree_offset = cfg->tree_index_offset; a.log_table = B->mcts_log;
   a.pool = B->mcts_pool; a.nodes_per_tree = per_tree; a.nodes_used = B->mcts_top; a.compact = compact;
+  { const char* t = getenv("B2S_MCTS_TUNING"); a.tuning = t ? atoi(t) : 0; }
   a.visits_out = visit_counts_d; a.reward_out = total_reward_d; a.outcome_out = outcome_p0_d;
   a.best_out = best_action_d; a.sims_out = sims_run_d; a.gc_out = cfg->gc_runs_d; a.err = B->err;
   const char* e = B->ops->mcts(B->ctx(), work, n_trees, a, st);

@@ -74,6 +74,7 @@ struct MctsArgs {
   unsigned long long nodes_per_tree;
   unsigned long long* nodes_used;   // [1] sum over trees of the arena high-water marks, for b2s_mcts_nodes_used
   int compact;                      // host-side: 16-byte nodes (StatsC) or 24-byte nodes (StatsW)
+  int tuning;                       // measurement switches (env B2S_MCTS_TUNING): 1 = no history filter, 2 = no float32 pre-selection
   int* visits_out;                  // [n][A]
   double* reward_out;               // [n][A]
   float* outcome_out;               // [n][A] (NaN = unproven), nullable
@@ -213,8 +214,10 @@ __global__ void __launch_bounds__(128, MINBLOCKS) k_mcts(Ctx rootctx, Ctx workct
   constexpr int kFW = R::kFilterWords > 0 ? R::kFilterWords : 1;
   u32 root_filter[kFW], filter[kFW];
   if constexpr (R::kFilterWords > 0) {
-    R::filter_build(root_filter, workctx, tree, root);
-    workctx.filter = filter;
+    if (!(P.tuning & 1)) {
+      R::filter_build(root_filter, workctx, tree, root);
+      workctx.filter = filter;
+    }
   }
   const double inv_rollouts = __ddiv_rn(1.0, (double)P.n_rollouts);
   const float inv_rollouts_f = (float)inv_rollouts, c_f = (float)P.uct_c;
@@ -291,9 +294,11 @@ __global__ void __launch_bounds__(128, MINBLOCKS) k_mcts(Ctx rootctx, Ctx workct
             if (best < __longlong_as_double(0x7ff0000000000000LL)) chosen = first + i;
             break;                                  // nothing later can exceed +infinity
           }
-          float margin;
-          float est = approx_value<NS>(ch, log_parent_f, cp_f, c_f, P.puct != 0, inv_rollouts_f, &margin);
-          if ((double)est + (double)margin < best) continue;
+          if (!(P.tuning & 2)) {
+            float margin;
+            float est = approx_value<NS>(ch, log_parent_f, cp_f, c_f, P.puct != 0, inv_rollouts_f, &margin);
+            if ((double)est + (double)margin < best) continue;
+          }
         }
         double v = exact_value<NS>(ch, log_parent, cp, P, inv_rollouts);
         if (v > best) { best = v; chosen = first + i; }

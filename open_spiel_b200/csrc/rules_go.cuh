@@ -153,6 +153,19 @@ struct GoRules {
       cur = nx;
     }
   }
+  // Does the connected component of `seed` inside `mask` touch `libs`?  Grows the component one step at a time like flood()
+  // but stops at the first liberty: most chains have one within a step or two, and the full chain is only needed when the
+  // answer is no (a capture).  *component receives the component when the answer is no (it is complete then).
+  __device__ static __forceinline__ bool flood_finds(B128 seed, B128 mask, B128 libs, const Cfg& c, B128* component) {
+    B128 cur = b_and(seed, mask);
+    while (true) {
+      B128 n4 = nb4(cur, c);
+      if (b_any(b_and(n4, libs))) return true;
+      B128 nx = b_and(b_or(cur, n4), mask);
+      if (nx.lo == cur.lo && nx.hi == cur.hi) { *component = cur; return false; }
+      cur = nx;
+    }
+  }
   __device__ static __forceinline__ u64 hash_of(B128 black, B128 white) {
     u64 h = 0;
     while (b_any(black)) { int p = b_ffs(black); black = b_andn(black, b_bit(p)); h ^= g_go_zobrist[0][p]; }
@@ -166,17 +179,16 @@ struct GoRules {
   }
   __device__ static __forceinline__ int cur_player(const S& s, const Cfg& c) { return terminal(s, c) ? kTerminalPlayerId : s.to_play; }
 
-  // Tromp-Taylor area score from black's side minus komi (go_board.cc:641-683).
+  // Tromp-Taylor area score from black's side minus komi (go_board.cc:641-683): an empty region counts for a colour iff it
+  // borders only that colour.  Instead of flooding the regions one by one, flood the empty points reachable from black
+  // stones and those reachable from white stones (two floods, the same work in every lane): a region bordering only black is
+  // exactly the set of empty points reachable from black and not from white.
   __device__ static __forceinline__ float score(const S& s, const Cfg& c) {
     int delta = b_popc(s.black) - b_popc(s.white);
     B128 empty = b_andn(c.board, b_or(s.black, s.white));
-    while (b_any(empty)) {
-      B128 region = flood(b_bit(b_ffs(empty)), empty, c);
-      B128 border = nb4(region, c);
-      bool rb = b_any(b_and(border, s.black)), rw = b_any(b_and(border, s.white));
-      if (rb && !rw) delta += b_popc(region);
-      else if (rw && !rb) delta -= b_popc(region);
-      empty = b_andn(empty, region);
+    if (b_any(empty)) {
+      B128 rb = flood(nb4(s.black, c), empty, c), rw = flood(nb4(s.white, c), empty, c);
+      delta += b_popc(b_andn(rb, rw)) - b_popc(b_andn(rw, rb));
     }
     return (float)delta - c.komi;
   }
@@ -231,9 +243,8 @@ struct GoRules {
   // Does the chain containing stone set `seed` (all of one colour `col`) have a liberty in `libs_allowed`?
   // Quick accept when a seed stone itself touches an allowed empty point; otherwise flood the chain.
   __device__ static __forceinline__ bool chain_has_liberty(B128 seed, B128 col, B128 libs_allowed, const Cfg& c) {
-    if (b_any(b_and(nb4(seed, c), libs_allowed))) return true;
-    B128 chain = flood(seed, col, c);
-    return b_any(b_and(nb4(chain, c), libs_allowed));
+    B128 chain;
+    return flood_finds(seed, col, libs_allowed, c, &chain);
   }
   __device__ static __forceinline__ bool legal_point(const S& s, const Cfg& c, int p) {
     B128 pb = b_bit(p);
@@ -250,10 +261,9 @@ struct GoRules {
     B128 todo = b_and(nbp, opp);
     while (b_any(todo)) {
       B128 q = b_bit(b_ffs(todo));
-      if (b_any(b_and(nb4(q, c), other))) { todo = b_andn(todo, q); continue; }
-      B128 chain = flood(q, opp, c);
-      if (!b_any(b_and(nb4(chain, c), other))) return true;
-      todo = b_andn(todo, chain);
+      B128 chain;
+      if (!flood_finds(q, opp, other, c, &chain)) return true;       // no liberty but p: playing p captures it
+      todo = b_andn(todo, q);                                          // (another stone of the same chain just repeats the short search)
     }
     return false;
   }
@@ -314,9 +324,9 @@ struct GoRules {
       B128 todo = b_and(nbp, opp), captured = {0, 0};
       while (b_any(todo)) {
         B128 q = b_bit(b_ffs(todo));
-        if (b_any(b_and(nb4(q, c), empty))) { todo = b_andn(todo, q); continue; }   // that stone still has a liberty
-        B128 chain = flood(q, opp, c);
-        if (!b_any(b_and(nb4(chain, c), empty))) captured = b_or(captured, chain);
+        B128 chain;
+        if (flood_finds(q, opp, empty, c, &chain)) { todo = b_andn(todo, q); continue; }   // the chain still has a liberty
+        captured = b_or(captured, chain);
         todo = b_andn(todo, chain);
       }
       int ncap = b_popc(captured);

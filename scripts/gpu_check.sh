@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.csv 2>&1
 nproc > gpurun_out/nproc.txt; lscpu | head -20 >> gpurun_out/nproc.txt
-echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 | tee gpurun_out/r02_pytest_gpu.log
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -25 | tee gpurun_out/r02_pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/r02_smoke.log
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 20 --warmup 3 2>&1 | tail -3 | tee gpurun_out/r02_bench_ref.json
 echo "== bench"; timeout 1500 python bench.py --steps 200 --warmup 10 2>&1 | tail -3 | tee gpurun_out/r02_bench.json
