@@ -61,14 +61,15 @@ __host__ __device__ __forceinline__ void philox4(u64 seed, u64 lane, u32 ply, u3
 // Unbiased uniform integer in [0, n) from the (seed, lane, ply) block: Lemire's multiply-shift with
 // rejection; the four words of the block are tried in order, then the block for stream+1, ...
 __host__ __device__ __forceinline__ u32 philox_uniform(u64 seed, u64 lane, u32 ply, u32 n) {
-  u32 thresh = (u32)(0u - n) % n;
+  // a word is rejected iff the low half of word * n is below (2^32 - n) mod n; that threshold is < n, so the modulo is only
+  // evaluated when the low half is below n (probability n / 2^32) — same accept / reject decisions, no division otherwise
   for (u32 stream = 0;; ++stream) {
     u32 r[4];
     philox4(seed, lane, ply, stream, r);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       u64 m = (u64)r[j] * n;
-      if ((u32)m >= thresh) return (u32)(m >> 32);
+      if ((u32)m >= n || (u32)m >= (u32)(0u - n) % n) return (u32)(m >> 32);
     }
   }
 }

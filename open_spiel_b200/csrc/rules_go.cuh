@@ -257,8 +257,9 @@ struct GoRules {
     // joins a friendly chain that keeps a liberty (one flood covers every friendly neighbour chain)
     B128 mine = b_and(nbp, own);
     if (b_any(mine) && chain_has_liberty(mine, own, other, c)) return true;
-    // captures an enemy chain whose only liberty is p
-    B128 todo = b_and(nbp, opp);
+    // captures an enemy chain whose only liberty is p; neighbours that touch another empty point themselves are safe at
+    // once (one whole-board neighbourhood instead of one per stone), the rest need the chain search
+    B128 todo = b_andn(b_and(nbp, opp), nb4(other, c));
     while (b_any(todo)) {
       B128 q = b_bit(b_ffs(todo));
       B128 chain;
@@ -320,8 +321,8 @@ struct GoRules {
       own = b_or(own, pb);
       empty = b_andn(empty, pb);
       h ^= g_go_zobrist[s.to_play][p];
-      // capture enemy chains left without liberties
-      B128 todo = b_and(nbp, opp), captured = {0, 0};
+      // capture enemy chains left without liberties; neighbours that touch an empty point themselves are safe at once
+      B128 todo = b_andn(b_and(nbp, opp), nb4(empty, c)), captured = {0, 0};
       while (b_any(todo)) {
         B128 q = b_bit(b_ffs(todo));
         B128 chain;
