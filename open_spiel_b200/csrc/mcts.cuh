@@ -24,11 +24,10 @@
 // free block).  The reference's `nodes_` accounting (+= children.capacity() on expansion, -= on collection) is kept
 // as a separate logical counter, so collections happen after exactly the same simulations as in the reference.
 //
-// Selection.  UCTValue is two FP64 divisions and a square root per child, and a 9x9 root has 82 children; the reference's
-// first-maximum scan is reproduced exactly but lazily: a float32 estimate with a proven error margin is computed for every
-// child, and the FP64 value only for children whose estimate could still exceed the best exact value found so far
-// (random child order -> about log n exact evaluations per scan).  A child is skipped only if estimate + margin <
-// best_exact, which implies exact < best_exact, so the chosen child is the one the reference's `>` scan picks.
+// Selection is the reference's first-maximum scan in FP64 (an unvisited child is +infinity, so the first unvisited child ends
+// the scan).  A float32 pre-selection with a proven error margin (FP64 only for children whose estimate could still win) was
+// built and measured in round 2: B200's FP64 rate makes it a wash at depth and 10 % slower on shallow trees
+// (profiles/r02_mcts_variants.jsonl), so it was removed.
 // Not implemented: chance nodes in the tree, Dirichlet noise, custom evaluators (the host adapters route those to the
 // stock MCTSBot).
 #pragma once
@@ -74,7 +73,7 @@ struct MctsArgs {
   unsigned long long nodes_per_tree;
   unsigned long long* nodes_used;   // [1] sum over trees of the arena high-water marks, for b2s_mcts_nodes_used
   int compact;                      // host-side: 16-byte nodes (StatsC) or 24-byte nodes (StatsW)
-  int tuning;                       // measurement switches (env B2S_MCTS_TUNING): 1 = no history filter, 2 = no float32 pre-selection
+  int tuning;                       // measurement switch (env B2S_MCTS_TUNING): 1 = no history filter
   int* visits_out;                  // [n][A]
   double* reward_out;               // [n][A]
   float* outcome_out;               // [n][A] (NaN = unproven), nullable
@@ -107,14 +106,12 @@ struct StatsC {
   __device__ static __forceinline__ void zero(Node& n) { n.reward = 0; }
   __device__ static __forceinline__ void add(Node& n, int player, const SimReturn& r) { n.reward += r.num[player]; }
   __device__ static __forceinline__ double total(const Node& n, double inv_rollouts) { return __dmul_rn((double)n.reward, inv_rollouts); }
-  __device__ static __forceinline__ float total_f(const Node& n, float inv_rollouts) { return (float)n.reward * inv_rollouts; }
 };
 struct StatsW {
   typedef MctsNodeW Node;
   __device__ static __forceinline__ void zero(Node& n) { n.reward = 0.0; n.pad = 0; }
   __device__ static __forceinline__ void add(Node& n, int player, const SimReturn& r) { n.reward = __dadd_rn(n.reward, r.val[player]); }
   __device__ static __forceinline__ double total(const Node& n, double) { return n.reward; }
-  __device__ static __forceinline__ float total_f(const Node& n, float) { return (float)n.reward; }
 };
 
 // UCTValue (mcts.cc:90-101) / PUCTValue (:103-112, uniform prior 1/|children| of RandomRolloutEvaluator::Prior :74-87; `cp` =
@@ -132,26 +129,6 @@ __device__ __forceinline__ double exact_value(const typename NS::Node& ch, doubl
   double u = __dsqrt_rn(__ddiv_rn(log_parent, n));
   return __dadd_rn(q, __dmul_rn(P.uct_c, u));
 }
-// float32 estimate of the same value and a bound on |estimate - exact|.  Every float operation below is IEEE round-to-nearest
-// (no fast-math): conversions of reward / visits / log / c (<= 2^-24 relative each), two divisions, one square root, one
-// multiplication, one addition — fewer than 12 half-ulp steps on terms of magnitude (|q| + c u); the margin takes 64
-// ulp (2^-18 relative) of that magnitude plus an absolute 1e-30, far above the accumulated rounding (and above the exact
-// side's 2^-50), so estimate + margin >= exact always holds.
-template <class NS>
-__device__ __forceinline__ float approx_value(const typename NS::Node& ch, float log_parent_f, float cp_f, float c_f, bool puct, float inv_rollouts_f, float* margin) {
-  float n = (float)ch.visits;
-  float q, e;
-  if (puct) {
-    q = ch.visits ? NS::total_f(ch, inv_rollouts_f) / n : 0.f;
-    e = cp_f / (n + 1.f);
-  } else {
-    q = NS::total_f(ch, inv_rollouts_f) / n;
-    e = c_f * sqrtf(log_parent_f / n);
-  }
-  *margin = (fabsf(q) + fabsf(e)) * 3.8146973e-6f + 1e-30f;      // 2^-18
-  return q + e;
-}
-
 // Children block allocator of one tree (thread-private): exact-size free list, else bump, else split a larger free block.
 template <class Node, int KMAX>
 struct TreeArena {
@@ -220,7 +197,6 @@ __global__ void __launch_bounds__(128, MINBLOCKS) k_mcts(Ctx rootctx, Ctx workct
     }
   }
   const double inv_rollouts = __ddiv_rn(1.0, (double)P.n_rollouts);
-  const float inv_rollouts_f = (float)inv_rollouts, c_f = (float)P.uct_c;
   u32 path[MAXPATH];
   unsigned char gc_iter[MAXPATH];                  // child cursor per stack level of the collector's depth-first walk
   u32 expansions = 0;
@@ -284,21 +260,13 @@ __global__ void __launch_bounds__(128, MINBLOCKS) k_mcts(Ctx rootctx, Ctx workct
       const u32 first = nd.first_child, pv = nd.visits;
       const double log_parent = P.puct ? 0.0 : P.log_table[pv];
       const double cp = P.puct ? __dmul_rn(__dmul_rn(P.uct_c, __ddiv_rn(1.0, (double)nch)), __dsqrt_rn((double)pv)) : 0.0;
-      const float log_parent_f = (float)log_parent, cp_f = (float)cp;
       double best = __longlong_as_double(0xfff0000000000000LL);
       u32 chosen = first;
       for (int i = 0; i < nch; ++i) {
         const Node ch = pool[first + i];
-        if (!meta_proven(ch.meta)) {
-          if (ch.visits == 0 && !P.puct) {          // +infinity: the first unvisited child wins unless an earlier value is +infinity too
-            if (best < __longlong_as_double(0x7ff0000000000000LL)) chosen = first + i;
-            break;                                  // nothing later can exceed +infinity
-          }
-          if (!(P.tuning & 2)) {
-            float margin;
-            float est = approx_value<NS>(ch, log_parent_f, cp_f, c_f, P.puct != 0, inv_rollouts_f, &margin);
-            if ((double)est + (double)margin < best) continue;
-          }
+        if (!meta_proven(ch.meta) && ch.visits == 0 && !P.puct) {   // +infinity: the first unvisited child wins (every earlier value is finite)
+          chosen = first + i;
+          break;                                                     // nothing later can exceed +infinity
         }
         double v = exact_value<NS>(ch, log_parent, cp, P, inv_rollouts);
         if (v > best) { best = v; chosen = first + i; }

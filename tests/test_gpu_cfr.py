@@ -106,7 +106,7 @@ def test_sharded_traversal_path_is_bit_identical():
         for t in tables:
             for f in ("regrets", "cum_policy", "cur_policy"):
                 assert np.array_equal(t[f], tr[f]), (plus, f)
-        assert np.abs(tr["regrets"]).max() > 1.0       # the tables are not trivially zero
+        assert np.abs(tr["regrets"]).max() > 0.1       # the tables are not trivially zero
 
 
 @pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not shipped")
