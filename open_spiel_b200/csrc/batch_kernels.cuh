@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kBlock) k_status(Ctx ctx, typename R::Cfg cfg,
       float r[R::kPlayers];
       R::returns(s[j], cfg, r);
       if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
-      else for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+      else { const int np = rule_num_players<R>(cfg); for (int p = 0; p < np; ++p) rets[i * np + p] = r[p]; }
     }
   }
 }
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kBlock) k_step_fused(Ctx ctx, typename R::Cfg 
       float r[R::kPlayers];
       R::returns(s[j], cfg, r);
       if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
-      else for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+      else { const int np = rule_num_players<R>(cfg); for (int p = 0; p < np; ++p) rets[i * np + p] = r[p]; }
     }
     if (mask) {
       u32 m[R::kMaskWords];
@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(kBlock) k_rollout(Ctx ctx, typename R::Cfg cfg
   if (rets) {
     float r[R::kPlayers];
     R::returns(s, cfg, r);
-    for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+    const int np = rule_num_players<R>(cfg);
+    for (int p = 0; p < np; ++p) rets[i * np + p] = r[p];
   }
 }
 
@@ -418,7 +419,8 @@ __global__ void __launch_bounds__(kBlock) k_traj_finish(Ctx ctx, typename R::Cfg
   if (rewards) {
     float r[R::kPlayers];
     R::returns(s, cfg, r);
-    for (int p = 0; p < R::kPlayers; ++p) rewards[i * R::kPlayers + p] = r[p];
+    const int np = rule_num_players<R>(cfg);
+    for (int p = 0; p < np; ++p) rewards[i * np + p] = r[p];
   }
 }
 

@@ -97,6 +97,15 @@ __device__ __forceinline__ bool apply_known_legal(S& s, int a, const Cfg& c, con
   return apply_known_legal_impl<R>(s, a, c, ctx, lane, 0);
 }
 
+// Number of players of a configured game: R::num_players(cfg) when the rule core has a run-time count (kuhn_poker), else the
+// compile-time R::kPlayers (which is always the size of the returns array a kernel keeps).
+template <class R, class Cfg>
+__device__ __forceinline__ auto rule_num_players_impl(const Cfg& c, int) -> decltype(R::num_players(c)) { return R::num_players(c); }
+template <class R, class Cfg>
+__device__ __forceinline__ int rule_num_players_impl(const Cfg&, long) { return R::kPlayers; }
+template <class R, class Cfg>
+__device__ __forceinline__ int rule_num_players(const Cfg& c) { return rule_num_players_impl<R>(c, 0); }
+
 // One playout step: choose a uniformly random legal action and apply it; returns the action.
 // Rule cores may expose a cheap candidate superset (R::num_candidates / R::candidate, e.g. go: empty non-ko points
 // + pass) together with R::play_candidate, which applies the candidate or reports it illegal: a uniformly drawn

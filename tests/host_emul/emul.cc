@@ -108,7 +108,7 @@ struct EmuT : Emu {
       term[i] = cp == kTerminalPlayerId ? 1 : 0;
       float r[R::kPlayers];
       R::returns(s, cfg, r);
-      for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+      for (int p = 0; p < info.num_players; ++p) rets[i * info.num_players + p] = r[p];
     }
   }
   int obs(int player, int which, float* out, long long n) override {     // k_obs: obs_pack, then obs_elem per element
@@ -141,7 +141,7 @@ struct EmuT : Emu {
       plies[i] = ply;
       float r[R::kPlayers];
       R::returns(s, cfg, r);
-      for (int p = 0; p < R::kPlayers; ++p) rets[i * R::kPlayers + p] = r[p];
+      for (int p = 0; p < info.num_players; ++p) rets[i * info.num_players + p] = r[p];
     }
   }
   // b2s_mcts_search: the argument block is filled as api.cu / GameOpsT<R>::mcts do, then the KERNEL BODY of mcts.cuh is

@@ -37,10 +37,12 @@ GAMES = [
     ("go(board_size=4,komi=0.5)", 256),
     ("go(board_size=2,komi=0.5)", 128),
     ("kuhn_poker", 512),
+    ("kuhn_poker(players=3)", 512),
+    ("kuhn_poker(players=5)", 256),
     ("leduc_poker", 1024),
     ("leduc_poker(starting_player=1)", 256),
 ]
-INFO_STATE = {"kuhn_poker", "leduc_poker", "leduc_poker(starting_player=1)"}
+INFO_STATE = {"kuhn_poker", "kuhn_poker(players=3)", "kuhn_poker(players=5)", "leduc_poker", "leduc_poker(starting_player=1)"}
 
 
 @pytest.mark.parametrize("game_string,lanes", GAMES, ids=[g for g, _ in GAMES])
