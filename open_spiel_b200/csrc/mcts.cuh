@@ -9,8 +9,9 @@
 // independent roots per GPU.  Random decisions are an explicit function of (seed, tree, simulation, position)
 // through Philox (common.cuh), the same function oracle/algorithms/mcts.cc uses, so trees match bit for bit:
 //   expansion #e:  Fisher-Yates over the ascending legal list, j = rng(key, e, i, 1, i+1) for i = n-1..1
-//   simulation #t, rollout #r, ply p:  k = rng(key, t, p + 4096 q, 2+r, C) over the C playout candidates
-//     (the legal actions; for go: empty non-ko points + pass), q = 0,1,.. until the candidate is legal
+//   simulation #t, rollout #r, ply p:  k = shared(key, t, p + 4096 q, 2+r, C) over the C playout candidates
+//     (the legal actions; for go: empty non-ko points + pass), q = 0,1,.. until the candidate is legal; shared(.., b, ..)
+//     is word (b & 3) of the Philox block of (t, b >> 2, 2+r) — four consecutive plies share one block (PlayoutRng)
 // UCT arithmetic is done with explicitly rounded double operations (no FMA contraction) and log(N_parent)
 // comes from a table the HOST fills with std::log, so values equal the CPU's to the last bit.
 //
@@ -96,6 +97,40 @@ __device__ __forceinline__ unsigned long long mcts_now_ns() {
 
 __device__ __forceinline__ u32 rng_uniform(u64 key, u32 a, u32 b, u32 c, u32 n) {
   return philox_uniform(key, (u64)a | ((u64)b << 32), c, n);
+}
+
+// Playout draws (oracle/algorithms/philox.h RngUniformShared): draw number b of simulation `sim`, rollout domain `dom`, uses
+// word (b & 3) of the Philox block keyed by (sim, b >> 2, dom), so the first tries of four consecutive plies cost one block
+// (the block is kept in registers; retries, b >= 4096, compute theirs).  A rejected word falls back to streams 4 s + (b & 3).
+struct PlayoutRng {
+  u64 key;
+  u32 sim, dom, id;
+  u32 blk[4];
+};
+__device__ __forceinline__ u32 playout_draw(PlayoutRng& g, u32 b, u32 n) {
+  const u32 id = b >> 2, wi = b & 3u;
+  const u64 lane = (u64)g.sim | ((u64)id << 32);
+  u32 w;
+  if (b < 4096u) {
+    if (id != g.id) { philox4(g.key, lane, g.dom, 0u, g.blk); g.id = id; }
+    w = wi == 0 ? g.blk[0] : (wi == 1 ? g.blk[1] : (wi == 2 ? g.blk[2] : g.blk[3]));
+  } else {
+    u32 t[4];
+    philox4(g.key, lane, g.dom, 0u, t);
+    w = wi == 0 ? t[0] : (wi == 1 ? t[1] : (wi == 2 ? t[2] : t[3]));
+  }
+  u64 m = (u64)w * n;
+  if ((u32)m >= n || (u32)m >= (u32)(0u - n) % n) return (u32)(m >> 32);
+  const u32 thresh = (u32)(0u - n) % n;
+  for (u32 s = 1;; ++s) {
+    u32 t[4];
+    philox4(g.key, lane, g.dom, 4u * s + wi, t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m = (u64)t[j] * n;
+      if ((u32)m >= thresh) return (u32)(m >> 32);
+    }
+  }
 }
 
 // ---- per-representation statistics -----------------------------------------------------------------------------
@@ -293,8 +328,10 @@ __global__ void __launch_bounds__(128, MINBLOCKS) k_mcts(Ctx rootctx, Ctx workct
       for (int ro = 0; ro < P.n_rollouts; ++ro) {
         typename R::S w = s;
         u32 ply = 0;
+        PlayoutRng rng;
+        rng.key = key; rng.sim = (u32)sim; rng.dom = 2u + (u32)ro; rng.id = 0xffffffffu;
+        auto draw = [&](u32 b, u32 n) { return playout_draw(rng, b, n); };
         while (!R::terminal(w, cfg) && (int)ply < P.max_plies) {
-          auto draw = [&](u32 b, u32 n) { return rng_uniform(key, (u32)sim, b, 2u + (u32)ro, n); };
           playout_step<R>(w, cfg, workctx, tree, P.mask_words, draw, ply);
           ++ply;
         }

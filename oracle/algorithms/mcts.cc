@@ -9,7 +9,8 @@
 // kernels consume the identical function, so the search trees can be compared bit for bit:
 //   * expansion #e of a tree: Fisher-Yates over the ascending legal-action list, for i = n-1..1:
 //       j = RngUniform(key, e, i, 1, i + 1); swap(list[i], list[j])          (replaces std::shuffle, mcts.cc:294)
-//   * simulation #t, rollout #r, rollout ply p: draw q = 0, 1, ...: k = RngUniform(key, t, p + 4096 q, 2 + r, C)
+//   * simulation #t, rollout #r, rollout ply p: draw q = 0, 1, ...: k = RngUniformShared(key, t, p + 4096 q, 2 + r, C)
+//       (word (b & 3) of the Philox block of (t, b >> 2, 2 + r): four consecutive plies share one block)
 //       over the C rollout candidates (State::RolloutCandidates, = the legal actions except for go); the first
 //       legal candidate is played — a uniform draw over the legal actions    (replaces absl::Uniform, mcts.cc:54)
 //   key = seed + tree_index * 0x9E3779B97F4A7C15.
@@ -122,7 +123,7 @@ struct Search {
           auto actions = ws->LegalActions();
           ws->ApplyAction(actions[AbslUniformBelow(eval_rng, actions.size())]);
         } else {
-          ws->ApplyAction(SampleRolloutAction(*ws, [&](uint32_t b, uint32_t n) { return RngUniform(key, sim, b, 2 + r, n); }, ply));
+          ws->ApplyAction(SampleRolloutAction(*ws, [&](uint32_t b, uint32_t n) { return RngUniformShared(key, sim, b, 2 + r, n); }, ply));
         }
         ++ply;
       }

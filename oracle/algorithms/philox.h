@@ -38,5 +38,24 @@ inline uint32_t RngUniform(uint64_t key, uint32_t a, uint32_t b, uint32_t c, uin
   return PhiloxUniform(key, (uint64_t)a | ((uint64_t)b << 32), c, n);
 }
 
+// Playout draws of one simulation share Philox blocks: draw number b uses word (b & 3) of the block keyed by
+// (a, b >> 2, c) — four consecutive plies, one block.  A rejected word (probability < n / 2^32) falls back to streams
+// 4 s + (b & 3), s = 1, 2, ..., of the same key, all four words in order.
+inline uint32_t RngUniformShared(uint64_t key, uint32_t a, uint32_t b, uint32_t c, uint32_t n) {
+  const uint64_t lane = (uint64_t)a | ((uint64_t)(b >> 2) << 32);
+  const uint32_t thresh = (uint32_t)(0u - n) % n;
+  uint32_t r[4];
+  Philox4(key, lane, c, 0, r);
+  uint64_t m = (uint64_t)r[b & 3] * n;
+  if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+  for (uint32_t s = 1;; ++s) {
+    Philox4(key, lane, c, 4 * s + (b & 3), r);
+    for (int j = 0; j < 4; ++j) {
+      m = (uint64_t)r[j] * n;
+      if ((uint32_t)m >= thresh) return (uint32_t)(m >> 32);
+    }
+  }
+}
+
 }  // namespace oracle
 #endif
