@@ -549,7 +549,14 @@ def run_gpu(args):
                    "graph_chains": 2,
                    "graph_chains_note": "the K steps are on K different batches (independent), captured as 2 parallel chains; one chain (each step ordered after the previous) is extras.apply_1_chain_*",
                    "parallelism": "independent shards x%d, no data-path collective" % world,
-                   "host_numa_cpus": numa_cpus},
+                   "host_numa_cpus": numa_cpus,
+                   # the loops that drive the step kernels (BASELINE configs[2..4]); full records under extras.loops
+                   "loops_summary": {"mcts_go9x9_sims_per_s": loops["mcts_go9x9"]["sims_per_s"],
+                                     "mcts_go9x9_deep_sims_per_s": loops["mcts_go9x9_deep"]["sims_per_s"],
+                                     "mcts_go9x9_deep_config": "%d trees x %d simulations per GPU" % (args.deep_trees, args.deep_sims),
+                                     "cfr_leduc_iters_per_s": loops["cfr_leduc"]["iters_per_s"],
+                                     "cfr_leduc_iters": loops["cfr_leduc"]["iters"],
+                                     "rollouts_breakthrough_games_per_s": loops["rollouts_breakthrough"]["games_per_s"]}},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_apply<ConnectFourRules,4>",
                      "bytes_per_step": BYTES_APPLY, "peak_source": peak_src,

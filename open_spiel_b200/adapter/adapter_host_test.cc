@@ -94,6 +94,9 @@ int main() {
       {"kuhn_poker(players=5)", 20, 20, 1},
       {"leduc_poker", 60, 100, 1},                                               // leduc_poker_test.cc:35
       {"leduc_poker(starting_player=1)", 30, 20, 1},
+      {"leduc_poker(players=3)", 40, 50, 1},                                     // leduc_poker_test.cc:36-46
+      {"leduc_poker(players=3,starting_player=2)", 20, 10, 1},
+      {"leduc_poker(players=4)", 20, 20, 1},
   };
   std::vector<std::shared_ptr<const Game>> stock;
   for (const Case& c : cases) stock.push_back(LoadGame(c.game));     // built by the stock factories: names not yet taken over
@@ -118,7 +121,7 @@ int main() {
     std::cout << "ok " << c.game << std::endl;
   }
   // parameter sets the packed layouts cannot hold are served by the stock game (the previous factory)
-  for (const char* g : {"go(board_size=19)", "kuhn_poker(players=6)", "leduc_poker(players=3)", "leduc_poker(suit_isomorphism=true)",
+  for (const char* g : {"go(board_size=19)", "kuhn_poker(players=6)", "leduc_poker(players=5)", "leduc_poker(suit_isomorphism=true)",
                         "hex(board_size=13)", "connect_four(rows=12,columns=12)"}) {
     std::shared_ptr<const Game> fb = LoadGame(g);
     SPIEL_CHECK_TRUE(dynamic_cast<const b200::B200Game*>(fb.get()) == nullptr);

@@ -426,11 +426,12 @@ std::string B200State::ToString() const {
     case B2S_LEDUC_POKER: {
       static const char* kNames[3] = {"Fold", "Call", "Raise"};
       const PokerView v = Poker();
+      const char* more = num_players_ > 2 ? " [...]" : "";
       s = "Round: " + std::to_string(v.round) + "\nPlayer: " + std::to_string(v.cur_player) + "\nPot: " + std::to_string(v.pot) +
-          "\nMoney (player_0 player_1):";
-      for (int p = 0; p < 2; ++p) s += " " + Num(v.money[p]);
-      s += "\nCards (public player_0 player_1): " + std::to_string(v.public_card) + " ";
-      for (int p = 0; p < 2; ++p) s += std::to_string(v.private_cards[p]) + " ";
+          "\nMoney (player_0 player_1" + more + "):";
+      for (int p = 0; p < num_players_; ++p) s += " " + Num(v.money[p]);
+      s += std::string("\nCards (public player_0 player_1") + more + "): " + std::to_string(v.public_card) + " ";
+      for (int p = 0; p < num_players_; ++p) s += std::to_string(v.private_cards[p]) + " ";
       s += "\nRound 1 sequence: ";
       for (size_t i = 0; i < v.round1.size(); ++i) { if (i) s += ", "; s += kNames[v.round1[i]]; }
       s += "\nRound 2 sequence: ";
@@ -468,7 +469,7 @@ B200State::PokerView B200State::Poker() const {
     v.private_cards.assign(num_players_, -1);
     for (int p = 0; p < num_players_ && p < (int)history_.size(); ++p) v.private_cards[p] = (int)history_[p].action;
     for (int i = num_players_; i < (int)history_.size(); ++i) v.round1.push_back((int)history_[i].action);
-    float obs[16];
+    float obs[32];
     rules().Tensor(blob_.data(), 0, 0, obs);                   // pot contributions are the last num_players_ entries
     const int off = rules().info().observation_tensor_size - num_players_;
     for (int p = 0; p < num_players_; ++p) v.ante.push_back((int)obs[off + p]);
@@ -481,18 +482,19 @@ B200State::PokerView B200State::Poker() const {
   v.round = d.round;
   v.cur_player = d.cur_player;
   v.public_card = d.public_card < 0 ? kInvalidCard : d.public_card;
-  for (int p = 0; p < 2; ++p) {
+  v.pot = 0;
+  for (int p = 0; p < num_players_; ++p) {
     v.private_cards.push_back(d.private_card[p] < 0 ? kInvalidCard : d.private_card[p]);
     v.ante.push_back(d.ante[p]);
+    v.pot += d.ante[p];
+    // pot_ / money_ (leduc_poker.cc:628-678, 702-706): antes leave the stacks for the pot; ResolveWinner pays the pot out
+    v.money.push_back(kStartingMoney - d.ante[p]);
   }
   v.round1 = d.round1; v.round2 = d.round2;
-  // pot_ / money_ (leduc_poker.cc:628-678, 702-706): antes leave the stacks for the pot; ResolveWinner pays the pot out
-  v.pot = d.ante[0] + d.ante[1];
-  for (int p = 0; p < 2; ++p) v.money.push_back(kStartingMoney - d.ante[p]);
   if (IsTerminal()) {
-    float ret[2];
+    float ret[8];
     rules().Returns(blob_.data(), ret);
-    for (int p = 0; p < 2; ++p) v.money[p] = kStartingMoney + (double)ret[p];      // Returns = money - starting money
+    for (int p = 0; p < num_players_; ++p) v.money[p] = kStartingMoney + (double)ret[p];      // Returns = money - starting money
     v.pot = 0;
   }
   return v;

@@ -20,6 +20,7 @@
 #include "../csrc/rules_go.cuh"
 #include "../csrc/rules_kuhn_poker.cuh"
 #include "../csrc/rules_leduc_poker.cuh"
+#include "../csrc/rules_leduc_poker_n.cuh"
 
 namespace b2s_host {
 namespace {
@@ -83,6 +84,21 @@ void decode(const LeducRules::S& s, const LeducRules::Cfg&, Decoded* d) {
   d->round1.clear(); d->round2.clear();
   for (int i = 0; i < s.r1len; ++i) d->round1.push_back((s.r1seq >> (2 * i)) & 3);
   for (int i = 0; i < s.r2len; ++i) d->round2.push_back((s.r2seq >> (2 * i)) & 3);
+}
+
+void decode(const LeducNRules::S& s, const LeducNRules::Cfg& c, Decoded* d) {
+  d->round = s.round2 ? 2 : 1;
+  d->cur_player = s.cur == LeducNRules::kChance ? -1 : s.cur;
+  d->public_card = s.pub == LeducNRules::kNone ? -1 : s.pub;
+  d->num_players = c.n;
+  for (int p = 0; p < c.n; ++p) {
+    d->private_card[p] = s.priv[p] == LeducNRules::kNone ? -1 : s.priv[p];
+    d->ante[p] = s.ante[p];
+    d->folded[p] = (s.folded >> p) & 1;
+  }
+  d->round1.clear(); d->round2.clear();
+  for (int i = 0; i < s.r1len; ++i) d->round1.push_back((int)((s.r1seq >> (2 * i)) & 3u));
+  for (int i = 0; i < s.r2len; ++i) d->round2.push_back((int)((s.r2seq >> (2 * i)) & 3u));
 }
 
 template <class R>
@@ -179,7 +195,7 @@ std::unique_ptr<Rules> Rules::Create(int game_id, const b2s_params& p, std::stri
     case B2S_HEX: return make<HexRules>(p, error);
     case B2S_GO: return make<GoRules>(p, error);
     case B2S_KUHN_POKER: return make<KuhnRules>(p, error);
-    case B2S_LEDUC_POKER: return make<LeducRules>(p, error);
+    case B2S_LEDUC_POKER: return p.players > 2 ? make<LeducNRules>(p, error) : make<LeducRules>(p, error);
   }
   if (error) *error = "unknown game id";
   return nullptr;

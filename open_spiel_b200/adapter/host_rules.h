@@ -38,8 +38,9 @@ struct Decoded {
   std::vector<int8_t> cells;
   int to_play = 0;          // go: colour to move even at terminal states; others: mover
   // leduc_poker (kInvalidCard = -10000 in the reference, reported here as -1)
-  int round = 0, cur_player = 0, public_card = -1, private_card[2] = {-1, -1};
-  int ante[2] = {0, 0}, folded[2] = {0, 0};
+  int num_players = 2;
+  int round = 0, cur_player = 0, public_card = -1, private_card[4] = {-1, -1, -1, -1};
+  int ante[4] = {0, 0, 0, 0}, folded[4] = {0, 0, 0, 0};
   std::vector<int> round1, round2;     // 0 fold, 1 call, 2 raise
 };
 

@@ -68,7 +68,7 @@ struct Batch {
   }
 };
 
-static GameOps* make_ops(int id) {
+static GameOps* make_ops(int id, const b2s_params* p) {
   switch (id) {
     case B2S_TIC_TAC_TOE: return make_ops_tic_tac_toe();
     case B2S_CONNECT_FOUR: return make_ops_connect_four();
@@ -76,7 +76,7 @@ static GameOps* make_ops(int id) {
     case B2S_HEX: return make_ops_hex();
     case B2S_GO: return make_ops_go();
     case B2S_KUHN_POKER: return make_ops_kuhn_poker();
-    case B2S_LEDUC_POKER: return make_ops_leduc_poker();
+    case B2S_LEDUC_POKER: return (p && p->players > 2) ? make_ops_leduc_poker_n() : make_ops_leduc_poker();
   }
   return nullptr;
 }
@@ -119,7 +119,7 @@ void b2s_params_default(b2s_params* p) {
 }
 
 int b2s_game_info_get(int game_id, const b2s_params* params, b2s_game_info* out) {
-  GameOps* ops = make_ops(game_id);
+  GameOps* ops = make_ops(game_id, params);
   if (!ops) return fail("unsupported game id");
   b2s_params p;
   if (params) p = *params; else b2s_params_default(&p);
@@ -171,7 +171,7 @@ int b2s_batch_create(int game_id, const b2s_params* params, int64_t capacity, in
   *out_batch = nullptr;
   if (capacity <= 0) return fail("capacity must be positive");
   if (b2s_device_count() <= 0) return fail("no CUDA device: the b2s device path has no CPU fallback");
-  GameOps* ops = make_ops(game_id);
+  GameOps* ops = make_ops(game_id, params);
   if (!ops) return fail("unsupported game id");
   b2s_params p;
   if (params) p = *params; else b2s_params_default(&p);

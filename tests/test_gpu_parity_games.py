@@ -40,9 +40,12 @@ GAMES = [
     ("kuhn_poker(players=3)", 512),
     ("kuhn_poker(players=5)", 256),
     ("leduc_poker", 1024),
+    ("leduc_poker(players=3)", 1024),
+    ("leduc_poker(players=4)", 256),
     ("leduc_poker(starting_player=1)", 256),
 ]
-INFO_STATE = {"kuhn_poker", "kuhn_poker(players=3)", "kuhn_poker(players=5)", "leduc_poker", "leduc_poker(starting_player=1)"}
+INFO_STATE = {"kuhn_poker", "kuhn_poker(players=3)", "kuhn_poker(players=5)", "leduc_poker", "leduc_poker(starting_player=1)",
+              "leduc_poker(players=3)", "leduc_poker(players=4)"}
 
 
 @pytest.mark.parametrize("game_string,lanes", GAMES, ids=[g for g, _ in GAMES])

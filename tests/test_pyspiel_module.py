@@ -42,8 +42,9 @@ def test_load_game_returns_the_dropins():
         g = pyspiel.load_game(s)
         assert g.is_b200(), s
     # parameter sets outside the packed layouts are served by the stock games (the previous factory)
-    assert pyspiel.load_game("kuhn_poker(players=3)").is_b200()          # 2..5 players fit the packed layout
-    for s in ["go(board_size=19)", "kuhn_poker(players=6)", "leduc_poker(players=3)", "hex(board_size=13)"]:
+    assert pyspiel.load_game("kuhn_poker(players=3)").is_b200()          # kuhn 2..5 / leduc 2..4 players fit the packed layouts
+    assert pyspiel.load_game("leduc_poker(players=3)").is_b200()
+    for s in ["go(board_size=19)", "kuhn_poker(players=6)", "leduc_poker(players=5)", "hex(board_size=13)"]:
         assert not pyspiel.load_game(s).is_b200(), s
     g = pyspiel.load_game("go", {"board_size": 9, "komi": 6.5})
     assert g.is_b200() and g.get_parameters()["komi"] == 6.5 and g.num_distinct_actions() == 82

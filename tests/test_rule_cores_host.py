@@ -117,7 +117,8 @@ GAMES = [
     ("go(board_size=9)", 12), ("go(board_size=5)", 32), ("go(board_size=3,komi=0.5)", 48), ("go(board_size=7,komi=4.5)", 16),
     ("go(board_size=5,max_game_length=30)", 24),
     ("kuhn_poker", 128), ("kuhn_poker(players=3)", 192), ("kuhn_poker(players=4)", 128), ("kuhn_poker(players=5)", 128),
-    ("leduc_poker", 128), ("leduc_poker(starting_player=1)", 64),
+    ("leduc_poker", 128), ("leduc_poker(starting_player=1)", 64), ("leduc_poker(players=3)", 256),
+    ("leduc_poker(players=3,starting_player=2)", 128), ("leduc_poker(players=4)", 128),
 ]
 
 
