@@ -46,16 +46,16 @@ extern "C" {
 int b2s_game_id(const char* short_name);
 enum {
   B2S_TIC_TAC_TOE = 0, B2S_CONNECT_FOUR = 1, B2S_BREAKTHROUGH = 2, B2S_HEX = 3, B2S_GO = 4,
-  B2S_KUHN_POKER = 5, B2S_LEDUC_POKER = 6, B2S_NUM_GAMES = 7
+  B2S_KUHN_POKER = 5, B2S_LEDUC_POKER = 6, B2S_MNK = 7, B2S_NUM_GAMES = 8
 };
 
 /* Game parameters (replaces GameParameters, open_spiel/game_parameters.h:31-120, for the seven
  * games).  Unset fields (< 0 / NaN) take the reference defaults. Names match the reference's
  * parameter_specification (e.g. connect_four.cc:50-54, go.cc:55-63, hex.cc:48-55). */
 typedef struct b2s_params {
-  int32_t rows;            /* connect_four, breakthrough; hex num_rows */
-  int32_t columns;         /* connect_four, breakthrough; hex num_cols */
-  int32_t x_in_row;        /* connect_four */
+  int32_t rows;            /* connect_four, breakthrough; hex num_rows; mnk n */
+  int32_t columns;         /* connect_four, breakthrough; hex num_cols; mnk m */
+  int32_t x_in_row;        /* connect_four; mnk k */
   int32_t egocentric_obs_tensor; /* connect_four */
   int32_t board_size;      /* hex, go */
   int32_t swap;            /* hex */

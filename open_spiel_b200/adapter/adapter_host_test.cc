@@ -61,6 +61,9 @@ static int LockStep(const Game& ours, const Game& stock, int games, std::mt19937
     }
     SPIEL_CHECK_TRUE(a->History() == b->History());
   }
+  // and again after play: the stock mnk records "k" on the first DoApplyAction (mnk.h:120-123), and so does the drop-in
+  SPIEL_CHECK_TRUE(ours.GetParameters() == stock.GetParameters());
+  SPIEL_CHECK_EQ(ours.ToString(), stock.ToString());
   return steps;
 }
 
@@ -88,6 +91,10 @@ int main() {
       {"go(board_size=5)", 10, 5, 1},
       {"go(board_size=3,max_game_length=30)", 20, 10, 1},
       {"go(board_size=2)", 20, 10, 1},
+      {"mnk", 6, 5, 1},                                                          // mnk_test.cc: RandomSimTest
+      {"mnk(m=3,n=3,k=3)", 60, 50, 1},
+      {"mnk(m=7,n=5,k=4)", 20, 20, 1},
+      {"mnk(m=15,n=2,k=6)", 10, 10, 0},
       {"kuhn_poker", 60, 100, 1},                                                // kuhn_poker_test.cc:31-32
       {"kuhn_poker(players=3)", 60, 50, 1},                                      // kuhn_poker_test.cc:33-38 (2..4 players)
       {"kuhn_poker(players=4)", 40, 50, 1},

@@ -11,6 +11,7 @@
 #include "open_spiel/games/hex/hex.h"
 #include "open_spiel/games/kuhn_poker/kuhn_poker.h"
 #include "open_spiel/games/leduc_poker/leduc_poker.h"
+#include "open_spiel/games/mnk/mnk.h"
 #include "open_spiel/games/tic_tac_toe/tic_tac_toe.h"
 
 namespace open_spiel {
@@ -64,6 +65,15 @@ std::shared_ptr<const Game> B200Game::Create(const GameType& type, const GamePar
     if (p.board_size < 1 || p.board_size > 19) return nullptr;
     p.max_game_length = g->ParameterValue<int>("max_game_length", p.board_size * p.board_size * 2);   // go.h:68-70
     g->komi_ = (float)p.komi;
+  } else if (name == "mnk") {
+    // read without recording: see TouchBoardParams() in the header
+    auto raw = [&](const char* key, int def) {
+      auto it = params.find(key);
+      return it == params.end() ? def : it->second.int_value();
+    };
+    p.columns = raw("m", 15);      // mnk.h:34-36
+    p.rows = raw("n", 15);
+    p.x_in_row = raw("k", 5);
   } else if (name == "kuhn_poker") {
     p.players = g->ParameterValue<int>("players");
   } else if (name == "leduc_poker") {
@@ -80,10 +90,12 @@ std::shared_ptr<const Game> B200Game::Create(const GameType& type, const GamePar
 }
 
 std::unique_ptr<State> B200Game::NewInitialState() const {
+  TouchBoardParams();            // MNKState's constructor sizes the board (mnk.cc:172-178)
   return std::unique_ptr<State>(new B200State(shared_from_this()));
 }
 
 std::vector<int> B200Game::ObservationTensorShape() const {
+  TouchBoardParams();
   std::vector<int> s;
   for (int d : info().obs_shape) if (d > 0) s.push_back(d);
   return s;
@@ -234,6 +246,11 @@ std::string B200Game::ActionToString(Player player, Action a) const {
       return std::string(player == 0 ? "x" : "o") + "(" + std::to_string(a / 3) + "," + std::to_string(a % 3) + ")";
     case B2S_CONNECT_FOUR:
       return std::string(player == 0 ? "x" : "o") + std::to_string(a);
+    case B2S_MNK: {               // mnk.cc:246-249
+      TouchBoardParams();
+      const int cols = gi.obs_shape[2];
+      return std::string(player == 0 ? "x" : "o") + "(" + std::to_string(a / cols) + "," + std::to_string(a % cols) + ")";
+    }
     case B2S_BREAKTHROUGH: {      // breakthrough.cc:196-217: from-cell, to-cell, '*' for captures
       const int rows = gi.obs_shape[1], cols = gi.obs_shape[2];
       const int cap = (int)(a & 1), dir = (int)((a >> 1) % 6), cell = (int)(a / 12);
@@ -310,6 +327,7 @@ std::vector<std::pair<Action, double>> B200State::ChanceOutcomes() const {
 }
 
 void B200State::DoApplyAction(Action action_id) {
+  bgame().TouchLineParam();
   const size_t sw = (rules().state_bytes() + sizeof(Word16) - 1) / sizeof(Word16);
   undo_.insert(undo_.end(), blob_.begin(), blob_.begin() + sw);
   if (!rules().Apply(blob_.data(), (int)action_id)) {
@@ -347,7 +365,18 @@ void B200State::InformationStateTensor(Player player, absl::Span<float> values) 
 std::unique_ptr<State> B200State::Clone() const { return std::unique_ptr<State>(new B200State(*this)); }
 
 void B200State::ToBatchLane(void* batch, int64_t lane) const { Check(b2s_state_set(batch, lane, blob_.data(), rules().blob_bytes())); }
-void B200State::FromBatchLane(void* batch, int64_t lane) { Check(b2s_state_get(batch, lane, blob_.data(), rules().blob_bytes())); }
+void B200State::FromBatchLane(void* batch, int64_t lane) {
+  Check(b2s_state_get(batch, lane, blob_.data(), rules().blob_bytes()));
+  undo_.clear();
+  if (bgame().gid() == B2S_KUHN_POKER) {      // the packed kuhn state is the action history: rebuild history_ from it
+    b2s_host::Decoded d;
+    rules().Decode(blob_.data(), &d);
+    history_.clear();
+    for (int p = 0; p < num_players_ && d.private_card[p] >= 0; ++p) history_.push_back({kChancePlayerId, d.private_card[p]});
+    for (size_t k = 0; k < d.round1.size(); ++k) history_.push_back({(Player)(k % num_players_), d.round1[k]});
+    move_number_ = (int)history_.size();
+  }
+}
 
 std::string B200State::ActionToString(Player player, Action action_id) const {
   // hex.cc:301 tests `StringRep() == StringRep::kStandard` on a value-initialised enum, not on the state's string_rep_,
@@ -369,6 +398,14 @@ std::string B200State::ToString() const {
         if (r < 2) s += "\n";
       }
       return s;
+    case B2S_MNK: {               // mnk.cc:193-205
+      const int rows = gi.obs_shape[1], cols = gi.obs_shape[2];
+      for (int r = 0; r < rows; ++r) {
+        for (int c = 0; c < cols; ++c) s += ".xo"[d.cells[r * cols + c]];
+        if (r < rows - 1) s += "\n";
+      }
+      return s;
+    }
     case B2S_CONNECT_FOUR: {
       const int rows = gi.obs_shape[1], cols = gi.obs_shape[2];
       for (int r = rows - 1; r >= 0; --r) {
@@ -513,6 +550,7 @@ std::shared_ptr<const Game> StockGame(const std::string& name, const GameParamet
   if (name == "go") return std::shared_ptr<const Game>(new go::GoGame(params));
   if (name == "kuhn_poker") return std::shared_ptr<const Game>(new kuhn_poker::KuhnGame(params));
   if (name == "leduc_poker") return std::shared_ptr<const Game>(new leduc_poker::LeducGame(params));
+  if (name == "mnk") return std::shared_ptr<const Game>(new mnk::MNKGame(params));
   SpielFatalError("b200: no stock game " + name);
 }
 }  // namespace
@@ -520,7 +558,8 @@ std::shared_ptr<const Game> StockGame(const std::string& name, const GameParamet
 void RegisterB200Games() {
   static std::once_flag once;
   std::call_once(once, [] {
-    for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker"}) {
+    for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk"}) {
+      if (!IsGameRegistered(name)) continue;                 // a build without that stock game
       GameType type;
       for (const GameType& t : GameRegisterer::RegisteredGames())
         if (t.short_name == name) type = t;                    // the stock registration's GameType, unchanged

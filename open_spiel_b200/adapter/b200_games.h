@@ -27,13 +27,13 @@ class B200Game : public Game {
   // nullptr when the parameters are not representable (the caller falls back to the stock factory)
   static std::shared_ptr<const Game> Create(const GameType& type, const GameParameters& params);
 
-  int NumDistinctActions() const override { return info().num_distinct_actions; }
+  int NumDistinctActions() const override { TouchBoardParams(); return info().num_distinct_actions; }
   std::unique_ptr<State> NewInitialState() const override;
   int NumPlayers() const override { return info().num_players; }
   double MinUtility() const override { return info().min_utility; }
   double MaxUtility() const override { return info().max_utility; }
   absl::optional<double> UtilitySum() const override { return 0; }
-  int MaxGameLength() const override { return info().max_game_length; }
+  int MaxGameLength() const override { TouchBoardParams(); return info().max_game_length; }
   int MaxChanceOutcomes() const override { return info().max_chance_outcomes; }
   std::vector<int> ObservationTensorShape() const override;
   std::vector<int> InformationStateTensorShape() const override;
@@ -50,6 +50,11 @@ class B200Game : public Game {
   const b2s_game_info& info() const { return rules_->info(); }
   const b2s_host::Rules& rules() const { return *rules_; }
   bool hex_explicit() const { return hex_explicit_; }
+  // The stock mnk reads its parameters only inside the methods that need them (mnk.h:120-123), and ParameterValue<>
+  // records a defaulted parameter on its first read: GetParameters() / ToString() / serialization therefore print
+  // "{m=15,n=15}" until the first move reads "k" (mnk.cc:167).  These two calls reproduce that from the same methods.
+  void TouchBoardParams() const { if (gid_ == B2S_MNK) { ParameterValue<int>("n"); ParameterValue<int>("m"); } }
+  void TouchLineParam() const { if (gid_ == B2S_MNK) ParameterValue<int>("k"); }
   float komi() const { return komi_; }
 
  private:
@@ -93,9 +98,9 @@ class B200State : public State {
   // The packed lane (b2s_state_get / b2s_state_set layout).
   const void* blob() const { return blob_.data(); }
   size_t blob_bytes() const { return bgame().rules().blob_bytes(); }
-  // Copies this state into lane `lane` of a b2s batch of the same game / from it (the history is not reconstructed
-  // by FromBatchLane: use it on states whose lanes were advanced by actions the caller also ApplyAction()s, or for
-  // read-only inspection of a device lane).
+  // Copies this state into lane `lane` of a b2s batch of the same game / from it.  FromBatchLane does not reconstruct
+  // history_ (except for kuhn_poker, whose packed state is the history): use it on states whose lanes were advanced by
+  // actions the caller also ApplyAction()s, or for read-only inspection of a device lane; UndoAction stops there.
   void ToBatchLane(void* batch, int64_t lane) const;
   void FromBatchLane(void* batch, int64_t lane);
 

@@ -21,6 +21,7 @@
 #include "../csrc/rules_kuhn_poker.cuh"
 #include "../csrc/rules_leduc_poker.cuh"
 #include "../csrc/rules_leduc_poker_n.cuh"
+#include "../csrc/rules_mnk.cuh"
 
 namespace b2s_host {
 namespace {
@@ -72,7 +73,22 @@ void decode(const GoRules::S& s, const GoRules::Cfg& c, Decoded* d) {
     }
   d->to_play = s.to_play;
 }
-void decode(const KuhnRules::S&, const KuhnRules::Cfg&, Decoded*) {}     // kuhn strings are functions of the history
+void decode(const MnkRules::S& s, const MnkRules::Cfg& c, Decoded* d) {
+  d->cells.assign((size_t)c.cells, 0);
+  for (int r = 0; r < c.rows; ++r)
+    for (int col = 0; col < c.cols; ++col) {
+      const int bit = r * MnkRules::kStride + col;
+      d->cells[(size_t)r * c.cols + col] = q_test(s.x, bit) ? 1 : (q_test(s.o, bit) ? 2 : 0);
+    }
+  d->to_play = MnkRules::mover(s);
+}
+void decode(const KuhnRules::S& s, const KuhnRules::Cfg& c, Decoded* d) {   // the packed kuhn state is its action history
+  d->num_players = c.n;
+  const int len = KuhnRules::len(s);
+  for (int p = 0; p < c.n; ++p) d->private_card[p] = p < len ? KuhnRules::card(s, p) : -1;
+  d->round1.clear();
+  for (int k = 0; k < KuhnRules::num_bet_actions(s, c); ++k) d->round1.push_back(KuhnRules::bet(s, k));
+}
 void decode(const LeducRules::S& s, const LeducRules::Cfg&, Decoded* d) {
   d->round = s.round2 ? 2 : 1;
   d->cur_player = s.cur == LeducRules::kChance ? -1 : s.cur;
@@ -195,6 +211,7 @@ std::unique_ptr<Rules> Rules::Create(int game_id, const b2s_params& p, std::stri
     case B2S_HEX: return make<HexRules>(p, error);
     case B2S_GO: return make<GoRules>(p, error);
     case B2S_KUHN_POKER: return make<KuhnRules>(p, error);
+    case B2S_MNK: return make<MnkRules>(p, error);
     case B2S_LEDUC_POKER: return p.players > 2 ? make<LeducNRules>(p, error) : make<LeducRules>(p, error);
   }
   if (error) *error = "unknown game id";

@@ -39,9 +39,10 @@ struct Decoded {
   int to_play = 0;          // go: colour to move even at terminal states; others: mover
   // leduc_poker (kInvalidCard = -10000 in the reference, reported here as -1)
   int num_players = 2;
-  int round = 0, cur_player = 0, public_card = -1, private_card[4] = {-1, -1, -1, -1};
+  int round = 0, cur_player = 0, public_card = -1, private_card[5] = {-1, -1, -1, -1, -1};
   int ante[4] = {0, 0, 0, 0}, folded[4] = {0, 0, 0, 0};
   std::vector<int> round1, round2;     // 0 fold, 1 call, 2 raise
+  // kuhn_poker: num_players, private_card[p] (-1 = not dealt yet) and round1 = the betting actions (0 pass, 1 bet) in order
 };
 
 class Rules {

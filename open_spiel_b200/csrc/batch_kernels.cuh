@@ -635,5 +635,6 @@ GameOps* make_ops_go();
 GameOps* make_ops_kuhn_poker();
 GameOps* make_ops_leduc_poker();
 GameOps* make_ops_leduc_poker_n();   // players = 3..4
+GameOps* make_ops_mnk();
 
 }  // namespace b2s

@@ -13,7 +13,7 @@ kChancePlayerId = -1      # spiel_globals.h:26-56
 kTerminalPlayerId = -4
 kInvalidAction = -1
 
-_NAMES = ["tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker"]
+_NAMES = ["tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk"]
 
 
 def registered_names():
@@ -61,6 +61,7 @@ _PARAM_FIELDS = {
     "kuhn_poker": {"players": "players"},
     "leduc_poker": {"players": "players", "starting_player": "starting_player"},
     "tic_tac_toe": {},
+    "mnk": {"m": "columns", "n": "rows", "k": "x_in_row"},
 }
 
 

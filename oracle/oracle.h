@@ -101,6 +101,7 @@ std::unique_ptr<Game> MakeHex(const Params&);
 std::unique_ptr<Game> MakeGo(const Params&);
 std::unique_ptr<Game> MakeKuhnPoker(const Params&);
 std::unique_ptr<Game> MakeLeducPoker(const Params&);
+std::unique_ptr<Game> MakeMnk(const Params&);
 
 }  // namespace oracle
 #endif  // B2S_ORACLE_H_

@@ -11,10 +11,10 @@ echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 
 echo "== bench"; timeout 1500 python bench.py --steps 200 --warmup 10 2>&1 | tail -3 | tee gpurun_out/r02_bench.json
 if [ "${1:-}" != "quick" ]; then
   echo "== ncu launches"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 2000 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 20 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 2000 --csv --log-file gpurun_out/r02_launches.csv \
+      python bench.py --steps 20 --warmup 3 --deep-trees 1024 --deep-sims 500 --cfr-iters 2000 > gpurun_out/r02_bench_under_ncu.log 2>&1
   echo "== ncu full (k_apply)"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_apply -s 60 -c 3 -f -o gpurun_out/prof_apply \
-      python bench.py --steps 20 --warmup 3 > gpurun_out/bench_under_ncu2.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_apply -s 60 -c 3 -f -o gpurun_out/r02_prof_apply \
+      python bench.py --steps 20 --warmup 3 --deep-trees 1024 --deep-sims 500 --cfr-iters 2000 > gpurun_out/r02_bench_under_ncu2.log 2>&1
   ls -la gpurun_out
 fi

@@ -22,7 +22,9 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
 
 # 1. launch list
-lp = os.path.join(GO, "launches.csv")
+lp = os.path.join(GO, tag + "_launches.csv")
+if not os.path.exists(lp):
+    lp = os.path.join(GO, "launches.csv")
 if os.path.exists(lp):
     rows = list(csv.reader(open(lp)))
     h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
@@ -37,7 +39,7 @@ if os.path.exists(lp):
                 pass
     tot = sum(sum(v) for v in d.values())
     with open(os.path.join(OUT, tag + "_launches_summary.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ python bench.py --steps 20 --warmup 3\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ python bench.py (see scripts/gpu_check.sh for the loop sizes of the profiled run)\n")
         f.write("# per-launch times are cold-cache and serialised: compare shares, not absolutes.\n")
         f.write("# the headline timed region contains ONLY k_apply launches (K of them in one CUDA graph);\n")
         f.write("# k_copy = untimed restore of the per-step batches, k_step_fused / k_legal_mask = the 'extras' timings.\n")
@@ -47,9 +49,11 @@ if os.path.exists(lp):
 
 # 2. full captures
 for rep in sorted(os.listdir(GO)):
-    if not rep.endswith(".ncu-rep"):
+    if not rep.endswith(".ncu-rep") or (rep.startswith("r0") and not rep.startswith(tag + "_")):
         continue
     name = rep[:-8]
+    if name.startswith(tag + "_"):
+        name = name[len(tag) + 1:]
     raw = subprocess.run(["ncu", "-i", os.path.join(GO, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     if len(rows) < 3:
@@ -79,8 +83,10 @@ for rep in sorted(os.listdir(GO)):
     print("wrote", name)
 
 # 3. bench lines / sweep
-for fn in ("bench.json", "bench_ref.json", "sweep.jsonl", "gpu.csv", "nproc.txt"):
-    p = os.path.join(GO, fn)
+for fn in ("bench.json", "bench_ref.json", "sweep.jsonl", "gpu.csv", "nproc.txt", "pytest_gpu.log", "smoke.log"):
+    p = os.path.join(GO, tag + "_" + fn)
+    if not os.path.exists(p):
+        p = os.path.join(GO, fn)
     if os.path.exists(p):
         with open(os.path.join(OUT, tag + "_" + fn), "w") as f:
             f.write(open(p).read())

@@ -36,6 +36,13 @@ GAMES = [
     ("go(board_size=3,komi=0.5)", 256),
     ("go(board_size=4,komi=0.5)", 256),
     ("go(board_size=2,komi=0.5)", 128),
+    ("mnk", 48),
+    ("mnk(m=3,n=3,k=3)", 512),
+    ("mnk(m=7,n=5,k=4)", 128),
+    ("mnk(m=15,n=15,k=3)", 64),
+    ("mnk(m=4,n=15,k=5)", 64),
+    ("mnk(m=5,n=5,k=7)", 64),
+    ("mnk(m=1,n=1,k=1)", 32),
     ("kuhn_poker", 512),
     ("kuhn_poker(players=3)", 512),
     ("kuhn_poker(players=5)", 256),
@@ -147,7 +154,7 @@ def test_rollout_matches_oracle_given_same_random_stream():
     """b2s_rollout = uniform-random playout; the oracle replays it with the same Philox words."""
     from philox_ref import philox_uniform
     for gs in ["connect_four", "tic_tac_toe", "breakthrough", "hex(board_size=5)", "go(board_size=5)", "kuhn_poker",
-               "leduc_poker"]:
+               "leduc_poker", "mnk(m=6,n=6,k=4)"]:
         game = b2.load_game(gs)
         n = 256
         b = game.new_batch(n)

@@ -117,6 +117,8 @@ GAMES = [
     ("go(board_size=9)", 12), ("go(board_size=5)", 32), ("go(board_size=3,komi=0.5)", 48), ("go(board_size=7,komi=4.5)", 16),
     ("go(board_size=5,max_game_length=30)", 24),
     ("kuhn_poker", 128), ("kuhn_poker(players=3)", 192), ("kuhn_poker(players=4)", 128), ("kuhn_poker(players=5)", 128),
+    ("mnk", 24), ("mnk(m=3,n=3,k=3)", 128), ("mnk(m=7,n=5,k=4)", 64), ("mnk(m=15,n=15,k=3)", 32), ("mnk(m=4,n=15,k=5)", 32),
+    ("mnk(m=1,n=1,k=1)", 8), ("mnk(m=5,n=5,k=7)", 32),
     ("leduc_poker", 128), ("leduc_poker(starting_player=1)", 64), ("leduc_poker(players=3)", 256),
     ("leduc_poker(players=3,starting_player=2)", 128), ("leduc_poker(players=4)", 128),
 ]
@@ -196,7 +198,7 @@ def test_rule_core_rejects_illegal_and_post_terminal_actions():
 
 
 @pytest.mark.parametrize("gs", ["connect_four", "tic_tac_toe", "breakthrough", "breakthrough(rows=6,columns=6)", "hex(board_size=5)",
-                                "go(board_size=5)", "go(board_size=9)", "kuhn_poker", "leduc_poker"])
+                                "go(board_size=5)", "go(board_size=9)", "kuhn_poker", "leduc_poker", "mnk(m=6,n=6,k=4)"])
 def test_playout_step_matches_oracle_given_same_random_stream(gs):
     """common.cuh playout_step (legal-mask draw; candidate rejection sampling for go and breakthrough) on the host vs the
     oracle replaying the same Philox words — the CPU twin of the GPU test of b2s_rollout."""
