@@ -91,6 +91,7 @@ int main() {
       {"go(board_size=5)", 10, 5, 1},
       {"go(board_size=3,max_game_length=30)", 20, 10, 1},
       {"go(board_size=2)", 20, 10, 1},
+      {"othello", 100, 60, 1},                                                   // othello_test.cc:30-34
       {"mnk", 6, 5, 1},                                                          // mnk_test.cc: RandomSimTest
       {"mnk(m=3,n=3,k=3)", 60, 50, 1},
       {"mnk(m=7,n=5,k=4)", 20, 20, 1},

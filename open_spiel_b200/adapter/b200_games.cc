@@ -12,6 +12,7 @@
 #include "open_spiel/games/kuhn_poker/kuhn_poker.h"
 #include "open_spiel/games/leduc_poker/leduc_poker.h"
 #include "open_spiel/games/mnk/mnk.h"
+#include "open_spiel/games/othello/othello.h"
 #include "open_spiel/games/tic_tac_toe/tic_tac_toe.h"
 
 namespace open_spiel {
@@ -246,6 +247,9 @@ std::string B200Game::ActionToString(Player player, Action a) const {
       return std::string(player == 0 ? "x" : "o") + "(" + std::to_string(a / 3) + "," + std::to_string(a % 3) + ")";
     case B2S_CONNECT_FOUR:
       return std::string(player == 0 ? "x" : "o") + std::to_string(a);
+    case B2S_OTHELLO:             // othello.cc:226-234, Move::ToString :120-122
+      if (a == 64) return "pass";
+      return std::string(1, "abcdefgh"[a % 8]) + std::to_string(1 + a / 8);
     case B2S_MNK: {               // mnk.cc:246-249
       TouchBoardParams();
       const int cols = gi.obs_shape[2];
@@ -398,6 +402,17 @@ std::string B200State::ToString() const {
         if (r < 2) s += "\n";
       }
       return s;
+    case B2S_OTHELLO: {           // othello.cc:245-260
+      const std::string cols = "  a b c d e f g h  ";
+      s = IsTerminal() ? std::string("Terminal State:\n") : std::string(d.to_play == 0 ? "Black (x)" : "White (o)") + " to play:\n";
+      s += cols + "\n";
+      for (int r = 0; r < 8; ++r) {
+        s += std::to_string(r + 1) + " ";
+        for (int col = 0; col < 8; ++col) { s += "-xo"[d.cells[r * 8 + col]]; s += ' '; }
+        s += std::to_string(r + 1) + "\n";
+      }
+      return s + cols;
+    }
     case B2S_MNK: {               // mnk.cc:193-205
       const int rows = gi.obs_shape[1], cols = gi.obs_shape[2];
       for (int r = 0; r < rows; ++r) {
@@ -551,6 +566,7 @@ std::shared_ptr<const Game> StockGame(const std::string& name, const GameParamet
   if (name == "kuhn_poker") return std::shared_ptr<const Game>(new kuhn_poker::KuhnGame(params));
   if (name == "leduc_poker") return std::shared_ptr<const Game>(new leduc_poker::LeducGame(params));
   if (name == "mnk") return std::shared_ptr<const Game>(new mnk::MNKGame(params));
+  if (name == "othello") return std::shared_ptr<const Game>(new othello::OthelloGame(params));
   SpielFatalError("b200: no stock game " + name);
 }
 }  // namespace
@@ -558,7 +574,7 @@ std::shared_ptr<const Game> StockGame(const std::string& name, const GameParamet
 void RegisterB200Games() {
   static std::once_flag once;
   std::call_once(once, [] {
-    for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk"}) {
+    for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk", "othello"}) {
       if (!IsGameRegistered(name)) continue;                 // a build without that stock game
       GameType type;
       for (const GameType& t : GameRegisterer::RegisteredGames())

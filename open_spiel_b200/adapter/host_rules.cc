@@ -22,6 +22,7 @@
 #include "../csrc/rules_leduc_poker.cuh"
 #include "../csrc/rules_leduc_poker_n.cuh"
 #include "../csrc/rules_mnk.cuh"
+#include "../csrc/rules_othello.cuh"
 
 namespace b2s_host {
 namespace {
@@ -82,6 +83,11 @@ void decode(const MnkRules::S& s, const MnkRules::Cfg& c, Decoded* d) {
     }
   d->to_play = MnkRules::mover(s);
 }
+void decode(const OthelloRules::S& s, const OthelloRules::Cfg&, Decoded* d) {
+  d->cells.assign(64, 0);
+  for (int c = 0; c < 64; ++c) d->cells[c] = ((s.b >> c) & 1ull) ? 1 : (((s.w >> c) & 1ull) ? 2 : 0);
+  d->to_play = s.mover;
+}
 void decode(const KuhnRules::S& s, const KuhnRules::Cfg& c, Decoded* d) {   // the packed kuhn state is its action history
   d->num_players = c.n;
   const int len = KuhnRules::len(s);
@@ -90,16 +96,18 @@ void decode(const KuhnRules::S& s, const KuhnRules::Cfg& c, Decoded* d) {   // t
   for (int k = 0; k < KuhnRules::num_bet_actions(s, c); ++k) d->round1.push_back(KuhnRules::bet(s, k));
 }
 void decode(const LeducRules::S& s, const LeducRules::Cfg&, Decoded* d) {
-  d->round = s.round2 ? 2 : 1;
-  d->cur_player = s.cur == LeducRules::kChance ? -1 : s.cur;
-  d->public_card = s.pub == LeducRules::kNone ? -1 : s.pub;
-  d->private_card[0] = s.priv0 == LeducRules::kNone ? -1 : s.priv0;
-  d->private_card[1] = s.priv1 == LeducRules::kNone ? -1 : s.priv1;
-  d->ante[0] = s.ante0; d->ante[1] = s.ante1;
-  d->folded[0] = s.folded0; d->folded[1] = s.folded1;
+  typedef LeducRules L;
+  d->round = L::round2(s) ? 2 : 1;
+  d->cur_player = L::cur(s) == L::kChance ? -1 : L::cur(s);
+  d->public_card = L::pub(s) == L::kNone ? -1 : L::pub(s);
+  for (int p = 0; p < 2; ++p) {
+    d->private_card[p] = L::priv_of(s, p) == L::kNone ? -1 : L::priv_of(s, p);
+    d->ante[p] = L::ante_of(s, p);
+    d->folded[p] = L::folded_of(s, p);
+  }
   d->round1.clear(); d->round2.clear();
-  for (int i = 0; i < s.r1len; ++i) d->round1.push_back((s.r1seq >> (2 * i)) & 3);
-  for (int i = 0; i < s.r2len; ++i) d->round2.push_back((s.r2seq >> (2 * i)) & 3);
+  for (int i = 0; i < L::seq_len(s, 0); ++i) d->round1.push_back((L::seq(s, 0) >> (2 * i)) & 3);
+  for (int i = 0; i < L::seq_len(s, 1); ++i) d->round2.push_back((L::seq(s, 1) >> (2 * i)) & 3);
 }
 
 void decode(const LeducNRules::S& s, const LeducNRules::Cfg& c, Decoded* d) {
@@ -212,6 +220,7 @@ std::unique_ptr<Rules> Rules::Create(int game_id, const b2s_params& p, std::stri
     case B2S_GO: return make<GoRules>(p, error);
     case B2S_KUHN_POKER: return make<KuhnRules>(p, error);
     case B2S_MNK: return make<MnkRules>(p, error);
+    case B2S_OTHELLO: return make<OthelloRules>(p, error);
     case B2S_LEDUC_POKER: return p.players > 2 ? make<LeducNRules>(p, error) : make<LeducRules>(p, error);
   }
   if (error) *error = "unknown game id";

@@ -35,6 +35,7 @@ struct Decoded {
   //   hex           [cell]                 0 empty, 1 black, 2 black-north, 3 black-south, 4 black-win,
   //                                        5 white, 6 white-west, 7 white-east, 8 white-win   (hex.h:68-78)
   //   go            [row*n+col], row 0 = "1"  0 empty, 1 black, 2 white
+  //   mnk, othello  [r*cols+c]             0 empty, 1 player 0 ("x"), 2 player 1 ("o")
   std::vector<int8_t> cells;
   int to_play = 0;          // go: colour to move even at terminal states; others: mover
   // leduc_poker (kInvalidCard = -10000 in the reference, reported here as -1)

@@ -636,5 +636,6 @@ GameOps* make_ops_kuhn_poker();
 GameOps* make_ops_leduc_poker();
 GameOps* make_ops_leduc_poker_n();   // players = 3..4
 GameOps* make_ops_mnk();
+GameOps* make_ops_othello();
 
 }  // namespace b2s

@@ -339,15 +339,35 @@ __device__ __forceinline__ u64 mc_child_hash(u64 h, int idx) { return h * 0x9E37
 
 // Sharding: the rank that owns reduction lanes [lane_begin, lane_begin + L) runs the traversals k with k mod 64 in
 // that range; thread t is traversal k = lane_begin + t mod L + 64 (t div L) and owns row t.  One GPU: L = 64, k = t.
+//
+// Where a traversal's deltas go (template LOG):
+//   false: row t of `rows` ([threads][E] doubles, dense, zero except for the cells this traversal touches);
+//   true:  a delta log, log[t][0 .. counts[t]) of {table entry, value} records (McLog).  A traversal touches an entry at most
+//          once (perfect recall: the information states on the paths of one traversal differ in the traverser's own
+//          actions), so a log holds the same numbers as the row's non-zero cells — a few dozen records instead of E cells.
+struct McLog {
+  int4* rec;      // [threads][cap]: {entry, 0, value bits lo, value bits hi}
+  int* counts;    // [threads]
+  int cap;        // records per traversal: an exact upper bound from the tree (mccfr_log_capacity)
+};
+__device__ __forceinline__ void mc_log_append(const McLog& lg, int t, int& cnt, int entry, double v, int* err) {
+  if (v == 0.0) return;                                  // the dense rows cannot tell a zero delta from an untouched cell either
+  if (cnt >= lg.cap) { atomicAdd(err, 1); return; }
+  const long long bits = __double_as_longlong(v);
+  lg.rec[(size_t)t * lg.cap + cnt++] = make_int4(entry, 0, (int)(u32)bits, (int)(u32)((u64)bits >> 32));
+}
+
+template <bool LOG>
 __global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u64 seed, int K, int lane_begin, int L, int n_threads,
-                                                   double* __restrict__ rows, int* __restrict__ err, int simple_average) {
+                                                   double* __restrict__ rows, McLog lg, int* __restrict__ err, int simple_average) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_threads) return;
   int k = lane_begin + t % L + 64 * (t / L);
-  if (k >= K) return;
+  if (k >= K) { if (LOG) lg.counts[t] = 0; return; }
   const int E = d.n_entries;
-  double* reg_row = rows + (size_t)t * E;
+  double* reg_row = LOG ? nullptr : rows + (size_t)t * E;
   double* avg_row = reg_row;
+  int cnt = 0;
   struct Frame { int node, a, n, off; double v; u64 h; double cv[kMcMaxActions], sig[kMcMaxActions]; };
   Frame st[kMcMaxDepth];
   int sp = 0, node = 0;
@@ -395,8 +415,12 @@ __global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u6
           sum = __dadd_rn(sum, sig[a]);
         }
         if (aidx < 0) { atomicAdd(err, 1); aidx = n - 1; }
-        if (simple_average && actor == ((p + 1) & 1))    // simple averaging at the next player's nodes (:176-183)
-          for (int a = 0; a < n; ++a) avg_row[off + a] = __dadd_rn(avg_row[off + a], sig[a]);
+        if (simple_average && actor == ((p + 1) & 1)) {  // simple averaging at the next player's nodes (:176-183)
+          for (int a = 0; a < n; ++a) {
+            if (LOG) mc_log_append(lg, t, cnt, off + a, sig[a], err);
+            else avg_row[off + a] = __dadd_rn(avg_row[off + a], sig[a]);
+          }
+        }
         h = mc_child_hash(h, aidx);
         node = fc + aidx;
         continue;
@@ -416,13 +440,16 @@ __global__ void __launch_bounds__(128) k_mccfr_es(CfrDev d, int p, u32 phase, u6
       f.v = __dadd_rn(f.v, __dmul_rn(f.sig[f.a], r));
       ++f.a;
       if (f.a < f.n) { node = d.first_child[f.node] + f.a; h = mc_child_hash(f.h, f.a); break; }
-      for (int a = 0; a < f.n; ++a)                      // regret += child value - node value (:168-172)
-        reg_row[f.off + a] = __dadd_rn(reg_row[f.off + a], __dsub_rn(f.cv[a], f.v));
+      for (int a = 0; a < f.n; ++a) {                    // regret += child value - node value (:168-172)
+        if (LOG) mc_log_append(lg, t, cnt, f.off + a, __dsub_rn(f.cv[a], f.v), err);
+        else reg_row[f.off + a] = __dadd_rn(reg_row[f.off + a], __dsub_rn(f.cv[a], f.v));
+      }
       r = f.v;
       --sp;
     }
-    if (done) return;
+    if (done) break;
   }
+  if (LOG) lg.counts[t] = cnt;
 }
 
 // tables += the sum of the K traversal rows, in a FIXED order so the result is reproducible (and restated by the
@@ -484,20 +511,69 @@ __global__ void __launch_bounds__(1024) k_mccfr_partial(CfrDev d, int K, int lan
   }
   partials[(size_t)(lane_begin + ql) * E + e] = acc;
 }
+// The same partial sums from delta logs.  The order is the dense kernels' — lane q adds the deltas of its traversals
+// k = q, q + 64, q + 128, ... one after the other, from 0.0 — so the result is bit-identical; what changes is the traffic:
+// the records of the K traversals (tens of bytes each) instead of K rows of E doubles.  One block per lane keeps that
+// lane's partial row in shared memory; the records of one traversal go to distinct entries and are added in parallel,
+// traversals are separated by a barrier.  The chain over a lane's K / 64 traversals is sequential by definition, so the
+// loads run kMcPrefetch traversals ahead of the adds (a register ring) to keep the chain at barrier + shared-memory speed.
+// `width` = entries per partial row (E, or 2E for outcome sampling: regret deltas then average-policy deltas).
+constexpr int kMcPrefetch = 8, kMcLogThreads = 256;
+__global__ void __launch_bounds__(kMcLogThreads) k_mccfr_partial_log(int K, int lane_begin, int L, McLog lg, int width, double* __restrict__ partials) {
+  extern __shared__ double mc_part[];
+  const int ql = blockIdx.x, q = lane_begin + ql, tid = threadIdx.x;
+  for (int e = tid; e < width; e += kMcLogThreads) mc_part[e] = 0.0;
+  __syncthreads();
+  const int nj = q < K ? (K - q + 63) / 64 : 0;          // traversal j of this lane is k = q + 64 j, held by thread row ql + L j
+  int n[kMcPrefetch];
+  int4 rec[kMcPrefetch];
+  auto fetch = [&](int j, int& nn, int4& r) {
+    nn = 0;
+    if (j < nj) {
+      const size_t row = (size_t)ql + (size_t)L * j;
+      nn = lg.counts[row];
+      if (tid < nn) r = lg.rec[row * lg.cap + tid];
+    }
+  };
+  auto add = [&](const int4& r) {
+    const double v = __longlong_as_double((long long)(((u64)(u32)r.w << 32) | (u32)r.z));
+    mc_part[r.x] = __dadd_rn(mc_part[r.x], v);
+  };
+#pragma unroll
+  for (int u = 0; u < kMcPrefetch; ++u) fetch(u, n[u], rec[u]);
+  for (int j0 = 0; j0 < nj; j0 += kMcPrefetch) {
+#pragma unroll
+    for (int u = 0; u < kMcPrefetch; ++u) {
+      const int j = j0 + u;
+      if (j < nj) {                                      // uniform over the block
+        if (tid < n[u]) add(rec[u]);
+        if (n[u] > kMcLogThreads) {
+          const size_t row = (size_t)ql + (size_t)L * j;
+          for (int i = tid + kMcLogThreads; i < n[u]; i += kMcLogThreads) add(lg.rec[row * lg.cap + i]);
+        }
+        __syncthreads();
+      }
+      fetch(j + kMcPrefetch, n[u], rec[u]);
+    }
+  }
+  for (int e = tid; e < width; e += kMcLogThreads) partials[(size_t)q * width + e] = mc_part[e];
+}
+
 // step 2 (after the lanes of all ranks have been gathered): the tree over the 64 lanes, then table += partial[0].
-__global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_combine(CfrDev d, int p, const double* __restrict__ partials) {
+// `partials` = [64][stride]; mode as in k_mccfr_apply (0: by the entry's player, 1: regrets, 2: cumulative policy).
+__global__ void __launch_bounds__(kMcLanes * kMcTile) k_mccfr_combine(CfrDev d, int p, const double* __restrict__ partials, int stride, int mode) {
   __shared__ double part[kMcLanes][kMcTile + 1];
   const int E = d.n_entries;
   const int ex = threadIdx.x, q = threadIdx.y;
   const int e = blockIdx.x * kMcTile + ex;
-  part[q][ex] = e < E ? partials[(size_t)q * E + e] : 0.0;
+  part[q][ex] = e < E ? partials[(size_t)q * stride + e] : 0.0;
   __syncthreads();
   for (int s = kMcLanes / 2; s >= 1; s >>= 1) {
     if (q < s) part[q][ex] = __dadd_rn(part[q][ex], part[q + s][ex]);
     __syncthreads();
   }
   if (q == 0 && e < E) {
-    double* dst = d.entry_player[e] == p ? d.regrets + e : d.cum_policy + e;
+    double* dst = mode == 0 ? (d.entry_player[e] == p ? d.regrets + e : d.cum_policy + e) : (mode == 1 ? d.regrets + e : d.cum_policy + e);
     *dst = __dadd_rn(*dst, part[0][ex]);
   }
 }
@@ -545,13 +621,15 @@ __device__ __forceinline__ double os_real(u64 seed, u64 h, u32 phase, u32 k, dou
   }
 }
 
+template <bool LOG>
 __global__ void __launch_bounds__(128) k_mccfr_os(CfrDev d, int p, u32 phase, u64 seed, int K, double epsilon, double* __restrict__ rows,
-                                                   int* __restrict__ err) {
+                                                   McLog lg, int* __restrict__ err) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   const int E = d.n_entries;
-  double* reg_row = rows + (size_t)k * 2 * E;
-  double* pol_row = reg_row + E;
+  double* reg_row = LOG ? nullptr : rows + (size_t)k * 2 * E;
+  double* pol_row = LOG ? nullptr : reg_row + E;
+  int cnt = 0;
   struct Frame { int off, n, sampled, actor; double my_reach, opp_reach, sample_reach, sample_prob; double sig[kMcMaxActions]; };
   Frame st[kMcMaxDepth];
   int sp = 0, node = 0;
@@ -614,12 +692,19 @@ __global__ void __launch_bounds__(128) k_mccfr_os(CfrDev d, int p, u32 phase, u6
       for (int a = 0; a < f.n; ++a) {
         const double cv = a == f.sampled ? cv_sampled : 0.0;
         const double cf_action_value = __ddiv_rn(__dmul_rn(cv, f.opp_reach), f.sample_reach);
-        reg_row[f.off + a] = __dsub_rn(cf_action_value, cf_value);
-        pol_row[f.off + a] = __ddiv_rn(__dmul_rn(f.my_reach, f.sig[a]), f.sample_reach);
+        const double dr = __dsub_rn(cf_action_value, cf_value), dp = __ddiv_rn(__dmul_rn(f.my_reach, f.sig[a]), f.sample_reach);
+        if (LOG) {
+          mc_log_append(lg, k, cnt, f.off + a, dr, err);
+          mc_log_append(lg, k, cnt, E + f.off + a, dp, err);
+        } else {
+          reg_row[f.off + a] = dr;
+          pol_row[f.off + a] = dp;
+        }
       }
     }
     value = value_estimate;
   }
+  if (LOG) lg.counts[k] = cnt;
 }
 
 struct CfrSolver {
@@ -629,7 +714,11 @@ struct CfrSolver {
   cudaGraphExec_t dist_graph = nullptr;
   int last_shard_player = 0;
   int mccfr_tables = 0;
-  double* mc_rows = nullptr; int mc_rows_k = 0;
+  double* mc_rows = nullptr; int mc_rows_k = 0;              // dense delta rows (B2S_MCCFR_DENSE=1, or tables too wide for the log path)
+  int4* mc_log = nullptr; int* mc_counts = nullptr;          // delta logs [mc_log_rows][mc_log_cap] + record counts
+  int mc_log_rows = 0, mc_log_cap = 0;
+  double* mc_partials = nullptr;                             // [64][2E] lane partial sums of the log path
+  int mc_cap_es = 0, mc_cap_os = 0;                          // most records one traversal / one episode can write (from the tree)
   int* mc_err = nullptr;
   int max_actions = 0;
   int device = 0;
@@ -649,6 +738,9 @@ struct CfrSolver {
     if (dist_stream) cudaStreamDestroy(dist_stream);
     for (void* p : allocs) cudaFree(p);
     if (mc_rows) cudaFree(mc_rows);
+    if (mc_log) cudaFree(mc_log);
+    if (mc_counts) cudaFree(mc_counts);
+    if (mc_partials) cudaFree(mc_partials);
     if (mc_err) cudaFree(mc_err);
   }
 };
@@ -852,6 +944,31 @@ int b2s_cfr_create(int game_id, const b2s_params* params, int flags, int device,
       mc[v] = make_int4(first_child[v], kind[v] == 2 ? S->is_off[infoset[v]] : -1,
                         (int)kind[v] | ((int)(actor[v] & 0xff) << 8) | ((int)nchild[v] << 16), 0);
     CK(upload(S, mc, &d.mc_node));
+    {
+      // Most delta records one sampled traversal can produce, exactly, from the tree (children follow their parents in the node
+      // order, so one backward sweep suffices).  External sampling (UpdateRegrets): the traverser's nodes explore every action and
+      // write one regret delta per action; the other player's nodes follow one action and write one average-policy delta per
+      // action; chance nodes follow one outcome.  Outcome sampling: one path, two deltas per action at the update player's nodes.
+      int cap_es = 0, cap_os = 0;
+      std::vector<int> es(N), os(N);
+      for (int pl = 0; pl < 2; ++pl) {
+        for (int v = N - 1; v >= 0; --v) {
+          int sum_es = 0, max_es = 0, max_os = 0;
+          for (int c = 0; c < nchild[v]; ++c) {
+            const int w = first_child[v] + c;
+            sum_es += es[w]; max_es = std::max(max_es, es[w]); max_os = std::max(max_os, os[w]);
+          }
+          if (kind[v] == 2) {
+            es[v] = nchild[v] + (actor[v] == pl ? sum_es : max_es);
+            os[v] = (actor[v] == pl ? 2 * nchild[v] : 0) + max_os;
+          } else {
+            es[v] = max_es; os[v] = max_os;                 // chance (one outcome followed) or terminal (no children)
+          }
+        }
+        cap_es = std::max(cap_es, es[0]); cap_os = std::max(cap_os, os[0]);
+      }
+      S->mc_cap_es = std::max(cap_es, 1); S->mc_cap_os = std::max(cap_os, 1);
+    }
     std::vector<signed char> entry_player(S->legal_actions.size(), 0);
     for (int i = 0; i < I; ++i)
       for (int k = S->is_off[i]; k < S->is_off[i + 1]; ++k) entry_player[k] = (signed char)S->is_player[i];
@@ -915,21 +1032,54 @@ int b2s_cfr_iterate(void* solver, int iters, void* stream) {
   return 0;
 }
 
-static int mccfr_prepare(CfrSolver* S, int rows_needed) {
+// Delta logs are used whenever one lane's partial row fits the shared memory of a block; B2S_MCCFR_DENSE=1 forces the dense
+// rows (kept for tables wider than that, and for the before / after measurement under profiles/).
+constexpr size_t kMcLogMaxShared = 200 * 1024;
+static bool mccfr_use_log(const CfrSolver* S, int width) {
+  static const bool dense = [] { const char* e = getenv("B2S_MCCFR_DENSE"); return e && atoi(e) != 0; }();
+  return !dense && sizeof(double) * (size_t)width <= kMcLogMaxShared;
+}
+static McLog mccfr_log(const CfrSolver* S) { return McLog{S->mc_log, S->mc_counts, S->mc_log_cap}; }
+
+// rows_needed: traversal threads of one launch; width: entries per row (E, or 2E for outcome sampling); cap: records per
+// traversal when the log path is taken
+static int mccfr_prepare(CfrSolver* S, int rows_needed, int width, int cap) {
   if (!S->mccfr_tables) return fail("mccfr: the solver was not created with B2S_CFR_MCCFR_TABLES");
   if (S->max_actions > kMcMaxActions || S->d.n_levels > kMcMaxDepth) return fail("mccfr: game tree too wide / deep for the device traversal");
   B2S_CU(cudaSetDevice(S->device));
   const int E = S->d.n_entries;
+  if (!S->mc_err) {
+    B2S_CU(cudaMalloc((void**)&S->mc_err, sizeof(int)));
+    B2S_CU(cudaMemset(S->mc_err, 0, sizeof(int)));
+  }
+  if (mccfr_use_log(S, width)) {
+    if (S->mc_log_rows < rows_needed || S->mc_log_cap < cap) {
+      if (S->mc_log) cudaFree(S->mc_log);
+      if (S->mc_counts) cudaFree(S->mc_counts);
+      const int rows = std::max(rows_needed, S->mc_log_rows), c = std::max(cap, S->mc_log_cap);
+      S->mc_log = nullptr; S->mc_counts = nullptr; S->mc_log_rows = 0;
+      B2S_CU(cudaMalloc((void**)&S->mc_log, sizeof(int4) * (size_t)rows * (size_t)c));
+      B2S_CU(cudaMalloc((void**)&S->mc_counts, sizeof(int) * (size_t)rows));
+      B2S_CU(cudaMemset(S->mc_counts, 0, sizeof(int) * (size_t)rows));
+      S->mc_log_rows = rows; S->mc_log_cap = c;
+    }
+    if (!S->mc_partials) {
+      B2S_CU(cudaMalloc((void**)&S->mc_partials, sizeof(double) * (size_t)kMcLanes * 2 * (size_t)E));
+      static bool attr = false;
+      if (!attr) {
+        B2S_CU(cudaFuncSetAttribute(k_mccfr_partial_log, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMcLogMaxShared));
+        attr = true;
+      }
+    }
+    return 0;
+  }
+  rows_needed *= width / E;                              // dense rows are allocated in units of E doubles
   if (S->mc_rows_k < rows_needed) {
     if (S->mc_rows) cudaFree(S->mc_rows);
     S->mc_rows = nullptr; S->mc_rows_k = 0;
     B2S_CU(cudaMalloc((void**)&S->mc_rows, sizeof(double) * (size_t)E * (size_t)rows_needed));
     B2S_CU(cudaMemset(S->mc_rows, 0, sizeof(double) * (size_t)E * (size_t)rows_needed));
     S->mc_rows_k = rows_needed;
-  }
-  if (!S->mc_err) {
-    B2S_CU(cudaMalloc((void**)&S->mc_err, sizeof(int)));
-    B2S_CU(cudaMemset(S->mc_err, 0, sizeof(int)));
   }
   return 0;
 }
@@ -942,11 +1092,16 @@ int b2s_mccfr_traverse_lanes(void* solver, int player, int traversals_per_update
   if (lane_begin < 0 || lane_end > kMcLanes || lane_begin >= lane_end) return fail("mccfr: lane range must lie within [0, 64)");
   const int K = traversals_per_update, L = lane_end - lane_begin, E = S->d.n_entries;
   const int n_threads = L * ((K + 63) / 64);
-  if (int r = mccfr_prepare(S, n_threads)) return r;
+  if (int r = mccfr_prepare(S, n_threads, E, S->mc_cap_es)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned phase = (unsigned)(S->iteration * 2 + player);
-  k_mccfr_es<<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, S->mc_rows, S->mc_err, 1);
-  k_mccfr_partial<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, K, lane_begin, L, S->mc_rows, partials_d);
+  if (mccfr_use_log(S, E)) {
+    k_mccfr_es<true><<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, nullptr, mccfr_log(S), S->mc_err, 1);
+    k_mccfr_partial_log<<<L, kMcLogThreads, sizeof(double) * (size_t)E, st>>>(K, lane_begin, L, mccfr_log(S), E, partials_d);
+  } else {
+    k_mccfr_es<false><<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, S->mc_rows, McLog{}, S->mc_err, 1);
+    k_mccfr_partial<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, K, lane_begin, L, S->mc_rows, partials_d);
+  }
   g_launches += 2;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "k_mccfr launch");
@@ -957,10 +1112,10 @@ int b2s_mccfr_apply_partials(void* solver, int player, const double* partials_d,
   if (!solver || !partials_d) return fail("mccfr: null argument");
   CfrSolver* S = (CfrSolver*)solver;
   if (player < 0 || player > 1) return fail("mccfr: bad player");
-  if (int r = mccfr_prepare(S, 1)) return r;
+  if (int r = mccfr_prepare(S, 1, S->d.n_entries, S->mc_cap_es)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   const int E = S->d.n_entries;
-  k_mccfr_combine<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, player, partials_d);
+  k_mccfr_combine<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, player, partials_d, E, 0);
   ++g_launches;
   if (player == 1) ++S->iteration;
   int bad = 0;
@@ -984,16 +1139,26 @@ int b2s_mccfr_external_iterate_ex(void* solver, int iters, int traversals_per_up
   if (!solver) return fail("mccfr: null solver");
   CfrSolver* S = (CfrSolver*)solver;
   if (iters < 0 || traversals_per_update < 1) return fail("mccfr: iters >= 0 and traversals_per_update >= 1 required");
-  if (int r = mccfr_prepare(S, traversals_per_update)) return r;
+  if (int r = mccfr_prepare(S, traversals_per_update, S->d.n_entries, S->mc_cap_es)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   const int K = traversals_per_update, E = S->d.n_entries;
   const int full = (flags & B2S_MCCFR_FULL_AVERAGE) ? 1 : 0;
+  const bool use_log = mccfr_use_log(S, E);
+  const dim3 ablock(kMcTile, kMcLanes);
+  const unsigned agrid = (unsigned)((E + kMcTile - 1) / kMcTile);
   for (int it = 0; it < iters; ++it) {
     for (int p = 0; p < 2; ++p) {
       unsigned phase = (unsigned)(S->iteration * 2 + p);
-      k_mccfr_es<<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, 0, kMcLanes, K, S->mc_rows, S->mc_err, full ? 0 : 1);
-      k_mccfr_apply<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, p, K, S->mc_rows, E, 0);
-      g_launches += 2;
+      if (use_log) {
+        k_mccfr_es<true><<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, 0, kMcLanes, K, nullptr, mccfr_log(S), S->mc_err, full ? 0 : 1);
+        k_mccfr_partial_log<<<kMcLanes, kMcLogThreads, sizeof(double) * (size_t)E, st>>>(K, 0, kMcLanes, mccfr_log(S), E, S->mc_partials);
+        k_mccfr_combine<<<agrid, ablock, 0, st>>>(S->d, p, S->mc_partials, E, 0);
+        g_launches += 3;
+      } else {
+        k_mccfr_es<false><<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, 0, kMcLanes, K, S->mc_rows, McLog{}, S->mc_err, full ? 0 : 1);
+        k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows, E, 0);
+        g_launches += 2;
+      }
     }
     if (full) { k_mccfr_full_average<<<1, 1024, 0, st>>>(S->d); ++g_launches; }     // RunIteration, external_sampling_mccfr.cc:76-79
     ++S->iteration;
@@ -1010,18 +1175,27 @@ int b2s_mccfr_outcome_iterate(void* solver, int iters, int trajectories_per_upda
   CfrSolver* S = (CfrSolver*)solver;
   if (iters < 0 || trajectories_per_update < 1) return fail("mccfr: iters >= 0 and trajectories_per_update >= 1 required");
   if (!(epsilon >= 0.0 && epsilon <= 1.0)) return fail("mccfr: epsilon must lie in [0, 1]");
-  if (int r = mccfr_prepare(S, 2 * trajectories_per_update)) return r;       // rows are [K][2E]
+  if (int r = mccfr_prepare(S, trajectories_per_update, 2 * S->d.n_entries, S->mc_cap_os)) return r;       // rows are [K][2E]
   cudaStream_t st = (cudaStream_t)stream;
   const int K = trajectories_per_update, E = S->d.n_entries;
   const dim3 ablock(kMcTile, kMcLanes);
   const unsigned agrid = (unsigned)((E + kMcTile - 1) / kMcTile);
+  const bool use_log = mccfr_use_log(S, 2 * E);
   for (int it = 0; it < iters; ++it) {
     for (int p = 0; p < 2; ++p) {
       unsigned phase = (unsigned)(S->iteration * 2 + p);
-      k_mccfr_os<<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, epsilon, S->mc_rows, S->mc_err);
-      k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows, 2 * E, 1);
-      k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows + E, 2 * E, 2);
-      g_launches += 3;
+      if (use_log) {
+        k_mccfr_os<true><<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, epsilon, nullptr, mccfr_log(S), S->mc_err);
+        k_mccfr_partial_log<<<kMcLanes, kMcLogThreads, sizeof(double) * 2 * (size_t)E, st>>>(K, 0, kMcLanes, mccfr_log(S), 2 * E, S->mc_partials);
+        k_mccfr_combine<<<agrid, ablock, 0, st>>>(S->d, p, S->mc_partials, 2 * E, 1);
+        k_mccfr_combine<<<agrid, ablock, 0, st>>>(S->d, p, S->mc_partials + E, 2 * E, 2);
+        g_launches += 4;
+      } else {
+        k_mccfr_os<false><<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, epsilon, S->mc_rows, McLog{}, S->mc_err);
+        k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows, 2 * E, 1);
+        k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows + E, 2 * E, 2);
+        g_launches += 3;
+      }
     }
     ++S->iteration;
   }

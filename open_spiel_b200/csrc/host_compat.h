@@ -27,6 +27,13 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
   unsigned long long v = ((unsigned long long)hi << 32) | lo;
   return (unsigned)(v >> (sh & 31));
 }
+// PRMT: result byte i = byte (selector nibble i) of the 8 bytes {x, y}; selector values 0-7 only (no sign replication)
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+  const unsigned long long v = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffull) << (8 * i);
+  return r;
+}
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline long long atomicMin(long long* p, long long v) { long long o = *p; if (v < o) *p = v; return o; }

@@ -88,6 +88,64 @@ struct BreakthroughRules {
     r[0] = w == 0 ? 1.f : w == 1 ? -1.f : 0.f;
     r[1] = w == 1 ? 1.f : w == 0 ? -1.f : 0.f;
   }
+  // Legal-action mask, bit-parallel.  Action id = (cell * 6 + dir) * 2 + capture with dir = mover * 3 + o, o = 0 / 1 / 2 for
+  // the left / straight / right forward neighbour (breakthrough.cc:163-208, 289-337): every cell owns a 12-bit group, of
+  // which the mover can set five bits (2o + capture, + 6 for player 1).  The five move kinds are computed for all cells at
+  // once as bitboards of FROM cells; what remains is a bit permutation, byte t of each bitboard (cells 8t..8t+7) -> mask
+  // words 3t..3t+2 at stride 12.  Multiplying a byte by a sum of 2^(11 j) puts bit j of its j-th copy at position 12 j
+  // (copies are 11 apart, a byte is 8 wide: no carries), so a byte spreads with two 64-bit multiplies and two masks:
+  //   cells 0..4 of the byte -> bits 12 j + k (j <= 4) of the 96-bit group triple, held in `lo`
+  //   cells 5..7             -> bits 60 + k, 72 + k, 84 + k, held in `hi` relative to bit 32
+  // No loop over pieces, no indexed local array: straight-line code, identical for every lane of a warp.
+#ifndef B2S_BREAKTHROUGH_LEGAL_LOOP
+  template <int K>
+  __device__ static __forceinline__ void spread(u64 board, int t, u64& lo, u64& hi) {
+    constexpr u64 kMulLo = (1ull | 1ull << 11 | 1ull << 22 | 1ull << 33 | 1ull << 44) << K;
+    constexpr u64 kBitLo = (1ull | 1ull << 12 | 1ull << 24 | 1ull << 36 | 1ull << 48) << K;
+    constexpr u64 kMulHi = (1ull << 23 | 1ull << 34 | 1ull << 45) << K;
+    constexpr u64 kBitHi = (1ull << 28 | 1ull << 40 | 1ull << 52) << K;
+    const u32 byte = __byte_perm((u32)(board >> (32 * (t >> 2))), 0u, 0x4440u | (u32)(t & 3));      // byte t, one PRMT
+    lo |= mul_byte(byte, kMulLo) & kBitLo;
+    hi |= mul_byte(byte, kMulHi) & kBitHi;
+  }
+  // byte * k for a byte < 256 and a 64-bit constant: one widening multiply-add per half (a plain u64 * u64 costs twice that)
+  __device__ static __forceinline__ u64 mul_byte(u32 byte, u64 k) {
+    return (u64)byte * (u32)k + ((u64)(byte * (u32)(k >> 32)) << 32);
+  }
+  __device__ static __forceinline__ void legal_nonterminal(const S& s, const Cfg& c, u32* m) {
+    const u64 white = s.w & c.board;
+    const u64 mine = s.mover == 0 ? s.b : white, theirs = s.mover == 0 ? white : s.b;
+    const u64 empty = ~(s.b | white) & c.board;
+    // target sets shifted back onto the FROM cell; player 0 moves up the board (r + 1), player 1 down (r - 1);
+    // 2 <= cols <= 32, so every shift count is in 1..33
+    u64 e_l, e_s, e_r, t_l, t_r;                 // empty / enemy target at the left, straight, right forward neighbour
+    if (s.mover == 0) {
+      e_l = empty >> (c.cols - 1); e_s = empty >> c.cols; e_r = empty >> (c.cols + 1);
+      t_l = theirs >> (c.cols - 1); t_r = theirs >> (c.cols + 1);
+    } else {
+      e_l = empty << (c.cols + 1); e_s = empty << c.cols; e_r = empty << (c.cols - 1);
+      t_l = theirs << (c.cols + 1); t_r = theirs << (c.cols - 1);
+    }
+    const u64 from_l = mine & c.not_col0, from_r = mine & c.not_collast;
+    const u64 p0 = from_l & e_l, c0 = from_l & t_l, p1 = mine & e_s, p2 = from_r & e_r, c2 = from_r & t_r;
+    const int sh = 6 * s.mover;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      u64 lo = 0, hi = 0;
+      spread<0>(p0, t, lo, hi);
+      spread<1>(c0, t, lo, hi);
+      spread<2>(p1, t, lo, hi);
+      spread<4>(p2, t, lo, hi);
+      spread<5>(c2, t, lo, hi);
+      lo <<= sh; hi <<= sh;                    // player 1's directions are 3..5: six bits further up in every group
+      m[3 * t] = (u32)lo;
+      m[3 * t + 1] = (u32)(lo >> 32) | (u32)hi;
+      m[3 * t + 2] = (u32)(hi >> 32);
+    }
+  }
+#else
+  // the first version (a loop over the mover's pieces setting bits in an indexed local array), kept for the before / after
+  // measurement under profiles/ (scripts/r02_item9.sh builds a second library with -DB2S_BREAKTHROUGH_LEGAL_LOOP)
   __device__ static __forceinline__ void legal_nonterminal(const S& s, const Cfg& c, u32* m) {
     for (int i = 0; i < kMaskWords; ++i) m[i] = 0;
     u64 white = s.w & c.board;
@@ -112,6 +170,7 @@ struct BreakthroughRules {
       }
     }
   }
+#endif
   __device__ static __forceinline__ void legal(const S& s, const Cfg& c, u32* m) {
     if (terminal(s, c)) { for (int i = 0; i < kMaskWords; ++i) m[i] = 0; return; }
     legal_nonterminal(s, c, m);

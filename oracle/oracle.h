@@ -102,6 +102,7 @@ std::unique_ptr<Game> MakeGo(const Params&);
 std::unique_ptr<Game> MakeKuhnPoker(const Params&);
 std::unique_ptr<Game> MakeLeducPoker(const Params&);
 std::unique_ptr<Game> MakeMnk(const Params&);
+std::unique_ptr<Game> MakeOthello(const Params&);
 
 }  // namespace oracle
 #endif  // B2S_ORACLE_H_

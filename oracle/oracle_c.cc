@@ -14,6 +14,7 @@ std::unique_ptr<Game> LoadGame(const std::string& name, const Params& p) {
   if (name == "kuhn_poker") return MakeKuhnPoker(p);
   if (name == "leduc_poker") return MakeLeducPoker(p);
   if (name == "mnk") return MakeMnk(p);
+  if (name == "othello") return MakeOthello(p);
   return nullptr;
 }
 }  // namespace oracle

@@ -7,6 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import bench  # noqa: E402
 import open_spiel_b200 as b2  # noqa: E402
 
@@ -18,9 +19,14 @@ game = b2.load_game(gs)
 if gs == "connect_four":
     _, snap, actions = bench.build_workload(torch, game, n, dev, seed=1)
 else:
+    import sweep_games                                   # mid-game states + one legal action per lane, as the sweep builds them
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5)
     snap = game.new_batch(n)
-    snap.rollout(seed=1, n=n)      # any states
-    actions = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    for _ in range(dict(sweep_games.GAMES)[gs]):
+        snap.apply_actions(sweep_games.random_legal(snap.legal_actions_mask_words(), gen))
+    actions = sweep_games.random_legal(snap.legal_actions_mask_words(), gen)
+    snap.check_errors()
 work = game.new_batch(n)
 mask = torch.empty((n, game._info.mask_words), dtype=torch.int32, device=dev)
 term = torch.empty((n,), dtype=torch.uint8, device=dev)

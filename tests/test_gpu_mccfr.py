@@ -136,3 +136,39 @@ def test_outcome_sampling_converges():
     t = b2.OutcomeSamplingMCCFRSolver(b2.load_game("leduc_poker"), seed=4, trajectories_per_update=4096)
     t.run_iteration(100)
     assert t.nash_conv() < 2.0
+
+
+_DENSE_SCRIPT = r"""
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import open_spiel_b200 as b2
+out = []
+for gs, K in (("kuhn_poker", 64), ("leduc_poker", 1), ("leduc_poker", 777), ("leduc_poker", 4096)):
+    es = b2.ExternalSamplingMCCFRSolver(b2.load_game(gs), seed=11, traversals_per_update=K)
+    es.run_iteration(3)
+    fa = b2.ExternalSamplingMCCFRSolver(b2.load_game(gs), seed=12, traversals_per_update=K, full_average=True)
+    fa.run_iteration(2)
+    osm = b2.OutcomeSamplingMCCFRSolver(b2.load_game(gs), seed=13, trajectories_per_update=K)
+    osm.run_iteration(3)
+    for s in (es, fa, osm):
+        t = s.table()
+        out.append(hashlib.sha256(t["regrets"].tobytes() + t["cum_policy"].tobytes()).hexdigest())
+print(" ".join(out))
+"""
+
+
+def test_delta_log_path_equals_dense_rows_bitwise():
+    """The sparse delta-log update (default) and the dense-row update (B2S_MCCFR_DENSE=1) add the same numbers in the same order:
+    regret and average-policy tables hash-identical for external sampling (simple and full averaging) and outcome sampling."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runs = []
+    for dense in ("0", "1"):
+        env = dict(os.environ, B2S_MCCFR_DENSE=dense)
+        r = subprocess.run([sys.executable, "-c", _DENSE_SCRIPT, root], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs.append(r.stdout.strip().split())
+    assert len(runs[0]) == 12 and runs[0] == runs[1]

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 GAMES = [("tic_tac_toe", 128), ("connect_four", 128), ("breakthrough", 64), ("hex", 32), ("hex(board_size=4,swap=True)", 64),
          ("go(board_size=9)", 32), ("go(board_size=5)", 64), ("kuhn_poker", 128), ("leduc_poker", 256),
-         ("mnk", 16), ("mnk(m=5,n=4,k=3)", 64)]
+         ("mnk", 16), ("mnk(m=5,n=4,k=3)", 64), ("othello", 64)]
 
 
 @pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not shipped")
@@ -26,7 +26,7 @@ def test_device_equals_unmodified_reference(gs, lanes):
 
 @pytest.mark.parametrize("gs,n", [("go(board_size=9)", 1 << 17), ("hex", 1 << 18), ("breakthrough", 1 << 20),
                                   ("tic_tac_toe", 1 << 20), ("leduc_poker", 1 << 20), ("kuhn_poker", 1 << 20),
-                                  ("mnk", 1 << 17)])
+                                  ("mnk", 1 << 17), ("othello", 1 << 18)])
 def test_full_size_rollout_properties(gs, n):
     game = b2.load_game(gs)
     b = game.new_batch(n)
