@@ -91,6 +91,9 @@ int main() {
       {"go(board_size=5)", 10, 5, 1},
       {"go(board_size=3,max_game_length=30)", 20, 10, 1},
       {"go(board_size=2)", 20, 10, 1},
+      {"y(board_size=9)", 100, 60, 1},                                           // y_test.cc: RandomSimTest on sizes up to 11
+      {"y(board_size=11)", 30, 30, 1},
+      {"y(board_size=3)", 60, 60, 1},
       {"othello", 100, 60, 1},                                                   // othello_test.cc:30-34
       {"mnk", 6, 5, 1},                                                          // mnk_test.cc: RandomSimTest
       {"mnk(m=3,n=3,k=3)", 60, 50, 1},
@@ -130,7 +133,8 @@ int main() {
   }
   // parameter sets the packed layouts cannot hold are served by the stock game (the previous factory)
   for (const char* g : {"go(board_size=19)", "kuhn_poker(players=6)", "leduc_poker(players=5)", "leduc_poker(suit_isomorphism=true)",
-                        "hex(board_size=13)", "connect_four(rows=12,columns=12)"}) {
+                        "hex(board_size=13)", "connect_four(rows=12,columns=12)", "y", "y(board_size=9,ansi_color_output=true)",
+                        "mnk(m=16,n=4,k=3)"}) {
     std::shared_ptr<const Game> fb = LoadGame(g);
     SPIEL_CHECK_TRUE(dynamic_cast<const b200::B200Game*>(fb.get()) == nullptr);
     testing::RandomSimTest(*fb, 1);

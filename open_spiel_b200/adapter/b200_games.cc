@@ -13,6 +13,11 @@
 #include "open_spiel/games/leduc_poker/leduc_poker.h"
 #include "open_spiel/games/mnk/mnk.h"
 #include "open_spiel/games/othello/othello.h"
+// y.h defines the free function CalcXY without `inline` (y.h:57-64), so a second translation unit that includes it collides
+// with y.o at link time; the name is redirected for this include (the function body is the header's own).
+#define CalcXY CalcXY_b200_adapter
+#include "open_spiel/games/y/y.h"
+#undef CalcXY
 #include "open_spiel/games/tic_tac_toe/tic_tac_toe.h"
 
 namespace open_spiel {
@@ -75,6 +80,9 @@ std::shared_ptr<const Game> B200Game::Create(const GameType& type, const GamePar
     p.columns = raw("m", 15);      // mnk.h:34-36
     p.rows = raw("n", 15);
     p.x_in_row = raw("k", 5);
+  } else if (name == "y") {
+    p.board_size = g->ParameterValue<int>("board_size");              // y.cc:331-334
+    if (g->ParameterValue<bool>("ansi_color_output")) return nullptr;  // escape sequences in ToString: the stock class prints them
   } else if (name == "kuhn_poker") {
     p.players = g->ParameterValue<int>("players");
   } else if (name == "leduc_poker") {
@@ -247,6 +255,10 @@ std::string B200Game::ActionToString(Player player, Action a) const {
       return std::string(player == 0 ? "x" : "o") + "(" + std::to_string(a / 3) + "," + std::to_string(a % 3) + ")";
     case B2S_CONNECT_FOUR:
       return std::string(player == 0 ? "x" : "o") + std::to_string(a);
+    case B2S_Y: {                 // y.cc:143-145, Move::ToString :110-114
+      const int n = gi.obs_shape[1];
+      return std::string(1, (char)('a' + a % n)) + std::to_string(a / n + 1);
+    }
     case B2S_OTHELLO:             // othello.cc:226-234, Move::ToString :120-122
       if (a == 64) return "pass";
       return std::string(1, "abcdefgh"[a % 8]) + std::to_string(1 + a / 8);
@@ -402,6 +414,27 @@ std::string B200State::ToString() const {
         if (r < 2) s += "\n";
       }
       return s;
+    case B2S_Y: {                 // y.cc:147-212 (ansi_color_output = false)
+      const int n = gi.obs_shape[1];
+      s = " ";
+      for (int x = 0; x < n; ++x) { s += ' '; s += (char)('a' + x); }
+      s += '\n';
+      for (int y = 0; y < n; ++y) {
+        s += std::string(y + ((y + 1) < 10), ' ');
+        s += std::to_string(y + 1);
+        bool found_last = false;
+        for (int x = 0; x < n - y; ++x) {
+          const int xy = x + y * n;
+          if (found_last) { s += ']'; found_last = false; }
+          else if (d.last_move == xy) { s += '['; found_last = true; }
+          else s += ' ';
+          s += ".O@"[d.cells[xy]];
+        }
+        if (found_last) s += ']';
+        s += '\n';
+      }
+      return s;
+    }
     case B2S_OTHELLO: {           // othello.cc:245-260
       const std::string cols = "  a b c d e f g h  ";
       s = IsTerminal() ? std::string("Terminal State:\n") : std::string(d.to_play == 0 ? "Black (x)" : "White (o)") + " to play:\n";
@@ -567,6 +600,7 @@ std::shared_ptr<const Game> StockGame(const std::string& name, const GameParamet
   if (name == "leduc_poker") return std::shared_ptr<const Game>(new leduc_poker::LeducGame(params));
   if (name == "mnk") return std::shared_ptr<const Game>(new mnk::MNKGame(params));
   if (name == "othello") return std::shared_ptr<const Game>(new othello::OthelloGame(params));
+  if (name == "y") return std::shared_ptr<const Game>(new y_game::YGame(params));
   SpielFatalError("b200: no stock game " + name);
 }
 }  // namespace
@@ -574,7 +608,7 @@ std::shared_ptr<const Game> StockGame(const std::string& name, const GameParamet
 void RegisterB200Games() {
   static std::once_flag once;
   std::call_once(once, [] {
-    for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk", "othello"}) {
+    for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk", "othello", "y"}) {
       if (!IsGameRegistered(name)) continue;                 // a build without that stock game
       GameType type;
       for (const GameType& t : GameRegisterer::RegisteredGames())

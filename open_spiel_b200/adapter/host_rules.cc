@@ -23,6 +23,7 @@
 #include "../csrc/rules_leduc_poker_n.cuh"
 #include "../csrc/rules_mnk.cuh"
 #include "../csrc/rules_othello.cuh"
+#include "../csrc/rules_y.cuh"
 
 namespace b2s_host {
 namespace {
@@ -87,6 +88,12 @@ void decode(const OthelloRules::S& s, const OthelloRules::Cfg&, Decoded* d) {
   d->cells.assign(64, 0);
   for (int c = 0; c < 64; ++c) d->cells[c] = ((s.b >> c) & 1ull) ? 1 : (((s.w >> c) & 1ull) ? 2 : 0);
   d->to_play = s.mover;
+}
+void decode(const YRules::S& s, const YRules::Cfg& c, Decoded* d) {
+  d->cells.assign((size_t)c.cells, 0);
+  for (int cell = 0; cell < c.cells; ++cell) d->cells[cell] = b_test(s.p1, cell) ? 1 : (b_test(s.p2, cell) ? 2 : 0);
+  d->to_play = s.mover;
+  d->last_move = s.last == YRules::kNoMove ? -1 : s.last;
 }
 void decode(const KuhnRules::S& s, const KuhnRules::Cfg& c, Decoded* d) {   // the packed kuhn state is its action history
   d->num_players = c.n;
@@ -221,6 +228,7 @@ std::unique_ptr<Rules> Rules::Create(int game_id, const b2s_params& p, std::stri
     case B2S_KUHN_POKER: return make<KuhnRules>(p, error);
     case B2S_MNK: return make<MnkRules>(p, error);
     case B2S_OTHELLO: return make<OthelloRules>(p, error);
+    case B2S_Y: return make<YRules>(p, error);
     case B2S_LEDUC_POKER: return p.players > 2 ? make<LeducNRules>(p, error) : make<LeducRules>(p, error);
   }
   if (error) *error = "unknown game id";

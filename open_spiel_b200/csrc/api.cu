@@ -78,6 +78,7 @@ static GameOps* make_ops(int id, const b2s_params* p) {
     case B2S_KUHN_POKER: return make_ops_kuhn_poker();
     case B2S_MNK: return make_ops_mnk();
     case B2S_OTHELLO: return make_ops_othello();
+    case B2S_Y: return make_ops_y();
     case B2S_LEDUC_POKER: return (p && p->players > 2) ? make_ops_leduc_poker_n() : make_ops_leduc_poker();
   }
   return nullptr;
@@ -108,7 +109,7 @@ int64_t b2s_launch_count(void) { return g_launches; }
 
 int b2s_game_id(const char* name) {
   static const char* names[B2S_NUM_GAMES] = {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go",
-                                             "kuhn_poker", "leduc_poker", "mnk", "othello"};
+                                             "kuhn_poker", "leduc_poker", "mnk", "othello", "y"};
   if (!name) return -1;
   for (int i = 0; i < B2S_NUM_GAMES; ++i) if (!strcmp(name, names[i])) return i;
   return -1;

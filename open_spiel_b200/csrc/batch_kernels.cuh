@@ -637,5 +637,6 @@ GameOps* make_ops_leduc_poker();
 GameOps* make_ops_leduc_poker_n();   // players = 3..4
 GameOps* make_ops_mnk();
 GameOps* make_ops_othello();
+GameOps* make_ops_y();
 
 }  // namespace b2s

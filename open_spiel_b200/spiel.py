@@ -13,7 +13,7 @@ kChancePlayerId = -1      # spiel_globals.h:26-56
 kTerminalPlayerId = -4
 kInvalidAction = -1
 
-_NAMES = ["tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk", "othello"]
+_NAMES = ["tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk", "othello", "y"]
 
 
 def registered_names():
@@ -63,6 +63,7 @@ _PARAM_FIELDS = {
     "tic_tac_toe": {},
     "mnk": {"m": "columns", "n": "rows", "k": "x_in_row"},
     "othello": {},
+    "y": {"board_size": "board_size"},
 }
 
 

@@ -15,6 +15,7 @@ std::unique_ptr<Game> LoadGame(const std::string& name, const Params& p) {
   if (name == "leduc_poker") return MakeLeducPoker(p);
   if (name == "mnk") return MakeMnk(p);
   if (name == "othello") return MakeOthello(p);
+  if (name == "y") return MakeY(p);
   return nullptr;
 }
 }  // namespace oracle

@@ -117,6 +117,7 @@ GAMES = [
     ("go(board_size=9)", 12), ("go(board_size=5)", 32), ("go(board_size=3,komi=0.5)", 48), ("go(board_size=7,komi=4.5)", 16),
     ("go(board_size=5,max_game_length=30)", 24),
     ("kuhn_poker", 128), ("kuhn_poker(players=3)", 192), ("kuhn_poker(players=4)", 128), ("kuhn_poker(players=5)", 128),
+    ("y(board_size=9)", 128), ("y(board_size=11)", 64), ("y(board_size=1)", 8), ("y(board_size=2)", 32), ("y(board_size=4)", 128),
     ("othello", 96), ("mnk", 24), ("mnk(m=3,n=3,k=3)", 128), ("mnk(m=7,n=5,k=4)", 64), ("mnk(m=15,n=15,k=3)", 32), ("mnk(m=4,n=15,k=5)", 32),
     ("mnk(m=1,n=1,k=1)", 8), ("mnk(m=5,n=5,k=7)", 32),
     ("leduc_poker", 128), ("leduc_poker(starting_player=1)", 64), ("leduc_poker(players=3)", 256),
@@ -198,7 +199,7 @@ def test_rule_core_rejects_illegal_and_post_terminal_actions():
 
 
 @pytest.mark.parametrize("gs", ["connect_four", "tic_tac_toe", "breakthrough", "breakthrough(rows=6,columns=6)", "hex(board_size=5)",
-                                "go(board_size=5)", "go(board_size=9)", "kuhn_poker", "leduc_poker", "mnk(m=6,n=6,k=4)", "othello"])
+                                "go(board_size=5)", "go(board_size=9)", "kuhn_poker", "leduc_poker", "mnk(m=6,n=6,k=4)", "othello", "y(board_size=7)"])
 def test_playout_step_matches_oracle_given_same_random_stream(gs):
     """common.cuh playout_step (legal-mask draw; candidate rejection sampling for go and breakthrough) on the host vs the
     oracle replaying the same Philox words — the CPU twin of the GPU test of b2s_rollout."""
@@ -240,6 +241,8 @@ MCTS_CASES = [("tic_tac_toe", 16, 3, 300, 2, True, False), ("connect_four", 12, 
               ("breakthrough(rows=5,columns=4)", 4, 3, 800, 1, False, False, 250),
               # next-tier games: pass moves in the tree (othello), wide boards (mnk)
               ("othello", 8, 30, 120, 1, True, False), ("othello", 6, 56, 400, 1, True, True), ("othello", 4, 10, 900, 1, False, False, 300),
+              ("y(board_size=5)", 8, 4, 300, 1, True, False), ("y(board_size=9)", 6, 12, 100, 1, True, True),
+              ("y(board_size=4)", 6, 2, 1200, 1, True, False, 300),
               ("mnk(m=5,n=5,k=4)", 8, 6, 200, 1, True, False), ("mnk", 4, 10, 60, 1, True, True),
               ("mnk(m=4,n=4,k=3)", 6, 2, 1200, 2, True, False, 350)]
 
