@@ -71,6 +71,40 @@ __global__ void __launch_bounds__(kBlock, R::kMinBlocks) k_apply(Ctx ctx, typena
   }
 }
 
+// Coalesced store of multi-word legal masks.  A warp owns 32 consecutive lanes, whose mask words are one contiguous range of
+// the output, but written lane by lane (mask[i * W + w] in a loop over w) every store instruction scatters over 32 sectors —
+// for breakthrough (W = 24) that, not the mask arithmetic, was the kernel's limit (ncu, profiles/r02_item9: 2 % of DRAM
+// bandwidth, 15 % SM busy, 40 us for 262k lanes).  The warp stages its 32 x W words in shared memory (row stride odd: no
+// bank conflicts) and writes the range with fully coalesced 128-byte stores.  Every lane of the warp must call (active =
+// false for lanes past n); W <= MAXW.  `first` = lane index of the warp's lane 0, `n` = lanes in the batch.
+template <int MAXW>
+struct MaskStage {
+  static constexpr int kRow = MAXW | 1;
+  u32 w[kBlock / 32][32 * kRow];
+};
+template <int MAXW>
+__device__ __forceinline__ void store_masks_coalesced(u32* __restrict__ mask, long long first, long long n, bool active, int W,
+                                                      const u32* m, MaskStage<MAXW>& stage) {
+  const int lane = threadIdx.x & 31;
+  u32* st = stage.w[threadIdx.x >> 5];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < MAXW; ++k) if (k < W) st[lane * MaskStage<MAXW>::kRow + k] = m[k];
+  }
+  __syncwarp();
+  const long long left = n - first;
+  const int total = (int)(left < 32 ? left : 32) * W;       // words this warp owns
+  int q = lane / W, r = lane - q * W;                        // flat word index f = q * W + r, advanced by 32 per iteration
+  const int dq = 32 / W, dr = 32 - dq * W;
+  u32* out = mask + first * W;
+  for (int f = lane; f < total; f += 32) {
+    out[f] = st[q * MaskStage<MAXW>::kRow + r];
+    q += dq; r += dr;
+    if (r >= W) { r -= W; ++q; }
+  }
+  __syncwarp();
+}
+
 template <class R, int ILP>
 __global__ void __launch_bounds__(kBlock) k_legal_mask(Ctx ctx, typename R::Cfg cfg, u32* __restrict__ mask, int mask_words, long long n) {
   long long base = (long long)blockIdx.x * (kBlock * ILP) + threadIdx.x;
@@ -80,16 +114,16 @@ __global__ void __launch_bounds__(kBlock) k_legal_mask(Ctx ctx, typename R::Cfg 
     long long i = base + (long long)j * kBlock;
     if (i < n) R::load(s[j], ctx, i);
   }
+  __shared__ MaskStage<R::kMaskWords == 1 ? 0 : R::kMaskWords> stage;
 #pragma unroll
   for (int j = 0; j < ILP; ++j) {
     long long i = base + (long long)j * kBlock;
-    if (i >= n) continue;
     u32 m[R::kMaskWords];
-    R::legal(s[j], cfg, m);
+    if (i < n) R::legal(s[j], cfg, m);
     if (R::kMaskWords == 1) {
-      mask[i] = m[0];
+      if (i < n) mask[i] = m[0];
     } else {
-      for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+      store_masks_coalesced(mask, i - (threadIdx.x & 31), n, i < n, mask_words, m, stage);
     }
   }
 }
@@ -154,28 +188,33 @@ __global__ void __launch_bounds__(kBlock) k_step_fused(Ctx ctx, typename R::Cfg 
     if (i < n) { a[j] = __ldg(actions + i); R::load(s[j], ctx, i); }
   }
   pdl_launch_dependents();
+  __shared__ MaskStage<R::kMaskWords == 1 ? 0 : R::kMaskWords> stage;
 #pragma unroll
   for (int j = 0; j < ILP; ++j) {
     long long i = base + (long long)j * kBlock;
-    if (i >= n) continue;
-    if (a[j] != -1) {
-      if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) flag_error(ctx.err, ctx.lane0 + i);
-      else R::store(s[j], ctx, i);
+    const bool live = i < n;
+    u32 m[R::kMaskWords];
+    if (live) {
+      if (a[j] != -1) {
+        if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) flag_error(ctx.err, ctx.lane0 + i);
+        else R::store(s[j], ctx, i);
+      }
+      bool t = R::terminal(s[j], cfg);
+      if (term) term[i] = t ? 1 : 0;
+      if (rets) {
+        float r[R::kPlayers];
+        R::returns(s[j], cfg, r);
+        if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
+        else { const int np = rule_num_players<R>(cfg); for (int p = 0; p < np; ++p) rets[i * np + p] = r[p]; }
+      }
+      if (mask) {
+        if (t) { for (int w = 0; w < R::kMaskWords; ++w) m[w] = 0; }
+        else R::legal_nonterminal(s[j], cfg, m);
+      }
     }
-    bool t = R::terminal(s[j], cfg);
-    if (term) term[i] = t ? 1 : 0;
-    if (rets) {
-      float r[R::kPlayers];
-      R::returns(s[j], cfg, r);
-      if (R::kPlayers == 2) reinterpret_cast<float2*>(rets)[i] = make_float2(r[0], r[1]);
-      else { const int np = rule_num_players<R>(cfg); for (int p = 0; p < np; ++p) rets[i * np + p] = r[p]; }
-    }
-    if (mask) {
-      u32 m[R::kMaskWords];
-      if (t) { for (int w = 0; w < R::kMaskWords; ++w) m[w] = 0; }
-      else R::legal_nonterminal(s[j], cfg, m);
-      if (R::kMaskWords == 1) mask[i] = m[0];
-      else for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+    if (mask) {                                            // uniform over the grid
+      if (R::kMaskWords == 1) { if (live) mask[i] = m[0]; }
+      else store_masks_coalesced(mask, i - (threadIdx.x & 31), n, live, mask_words, m, stage);
     }
   }
 }
@@ -205,30 +244,33 @@ __global__ void __launch_bounds__(kBlock) k_step_compact(Ctx ctx, typename R::Cf
     }
   }
   pdl_launch_dependents();
+  __shared__ MaskStage<R::kMaskWords == 1 ? 0 : R::kMaskWords> stage;
 #pragma unroll
   for (int j = 0; j < ILP; ++j) {
     long long i = base + (long long)j * kBlock;
-    if (i >= n) continue;
-    if (a[j] != -1) {
-      if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) flag_error(ctx.err, ctx.lane0 + i);
-      else R::store(s[j], ctx, i);
-    }
-    bool t = R::terminal(s[j], cfg);
+    const bool live = i < n;
     u32 m[R::kMaskWords];
-    unsigned st = 0;
-    if (t) {
-      float r[R::kPlayers];
-      R::returns(s[j], cfg, r);
-      st = 0x80u | (r[0] > 0.f ? 1u : (r[0] < 0.f ? 2u : 0u));
-      for (int w = 0; w < R::kMaskWords; ++w) m[w] = 0;
-    } else if (small_mask || mask) {
-      R::legal_nonterminal(s[j], cfg, m);
-      if (small_mask) st = m[0] & 0x7Fu;
+    if (live) {
+      if (a[j] != -1) {
+        if (R::terminal(s[j], cfg) || !R::apply(s[j], a[j], cfg, ctx, i)) flag_error(ctx.err, ctx.lane0 + i);
+        else R::store(s[j], ctx, i);
+      }
+      bool t = R::terminal(s[j], cfg);
+      unsigned st = 0;
+      if (t) {
+        float r[R::kPlayers];
+        R::returns(s[j], cfg, r);
+        st = 0x80u | (r[0] > 0.f ? 1u : (r[0] < 0.f ? 2u : 0u));
+        for (int w = 0; w < R::kMaskWords; ++w) m[w] = 0;
+      } else if (small_mask || mask) {
+        R::legal_nonterminal(s[j], cfg, m);
+        if (small_mask) st = m[0] & 0x7Fu;
+      }
+      status[i] = (unsigned char)st;
     }
-    status[i] = (unsigned char)st;
-    if (mask) {
-      if (R::kMaskWords == 1) mask[i] = m[0];
-      else for (int w = 0; w < mask_words; ++w) mask[i * mask_words + w] = m[w];
+    if (mask) {                                            // uniform over the grid
+      if (R::kMaskWords == 1) { if (live) mask[i] = m[0]; }
+      else store_masks_coalesced(mask, i - (threadIdx.x & 31), n, live, mask_words, m, stage);
     }
   }
 }
@@ -370,37 +412,41 @@ struct TrajStepOut {          // row t of the time-major outputs; any pointer ma
 template <class R>
 __global__ void __launch_bounds__(kBlock) k_traj_step(Ctx ctx, typename R::Cfg cfg, u64 seed, long long lane_offset, int t, int mask_words, int num_actions, TrajStepOut o, long long n) {
   long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= n) return;
+  const bool live = i < n;
+  __shared__ MaskStage<R::kMaskWords == 1 ? 0 : R::kMaskWords> stage;
   typename R::S s;
-  R::load(s, ctx, i);
   u32 m[R::kMaskWords];
   int a = 0, pl = 0;
   unsigned char valid = 0, nit = 0;
-  if (R::terminal(s, cfg)) {
-    // padding as BatchedTrajectory::ResizeFields (trajectories.cc:62-96): legal mask all ones, everything else 0
-    for (int w = 0; w < R::kMaskWords; ++w) {
-      int bits = num_actions - 32 * w;
-      m[w] = bits >= 32 ? 0xffffffffu : (bits > 0 ? (1u << bits) - 1u : 0u);
+  if (live) {
+    R::load(s, ctx, i);
+    if (R::terminal(s, cfg)) {
+      // padding as BatchedTrajectory::ResizeFields (trajectories.cc:62-96): legal mask all ones, everything else 0
+      for (int w = 0; w < R::kMaskWords; ++w) {
+        int bits = num_actions - 32 * w;
+        m[w] = bits >= 32 ? 0xffffffffu : (bits > 0 ? (1u << bits) - 1u : 0u);
+      }
+    } else {
+      const u64 g = (u64)(i + lane_offset);
+      const u32 b0 = 64u * (u32)(t + 1);
+      R::legal_nonterminal(s, cfg, m);
+      int cnt = 0;
+      for (int w = 0; w < mask_words; ++w) cnt += __popc(m[w]);
+      a = nth_set_bit(m, mask_words, (int)philox_uniform(seed, g, b0, (u32)cnt));
+      pl = R::cur_player(s, cfg);
+      valid = 1;
+      apply_known_legal<R>(s, a, cfg, ctx, i);
+      traj_resolve_chance<R>(s, cfg, ctx, i, seed, g, mask_words, b0);
+      nit = R::terminal(s, cfg) ? 1 : 0;
+      R::store(s, ctx, i);
+      if (nit && o.lengths) o.lengths[i] = t + 1;
     }
-  } else {
-    const u64 g = (u64)(i + lane_offset);
-    const u32 b0 = 64u * (u32)(t + 1);
-    R::legal_nonterminal(s, cfg, m);
-    int cnt = 0;
-    for (int w = 0; w < mask_words; ++w) cnt += __popc(m[w]);
-    a = nth_set_bit(m, mask_words, (int)philox_uniform(seed, g, b0, (u32)cnt));
-    pl = R::cur_player(s, cfg);
-    valid = 1;
-    apply_known_legal<R>(s, a, cfg, ctx, i);
-    traj_resolve_chance<R>(s, cfg, ctx, i, seed, g, mask_words, b0);
-    nit = R::terminal(s, cfg) ? 1 : 0;
-    R::store(s, ctx, i);
-    if (nit && o.lengths) o.lengths[i] = t + 1;
   }
-  if (o.mask) {
-    if (R::kMaskWords == 1) o.mask[i] = m[0];
-    else for (int w = 0; w < mask_words; ++w) o.mask[i * mask_words + w] = m[w];
+  if (o.mask) {                                            // uniform over the grid
+    if (R::kMaskWords == 1) { if (live) o.mask[i] = m[0]; }
+    else store_masks_coalesced(o.mask, i - (threadIdx.x & 31), n, live, mask_words, m, stage);
   }
+  if (!live) return;
   if (o.actions) o.actions[i] = a;
   if (o.players) o.players[i] = (signed char)pl;
   if (o.valid) o.valid[i] = valid;

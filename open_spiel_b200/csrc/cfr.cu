@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(1024) k_mccfr_partial(CfrDev d, int K, int lan
 // traversals are separated by a barrier.  The chain over a lane's K / 64 traversals is sequential by definition, so the
 // loads run kMcPrefetch traversals ahead of the adds (a register ring) to keep the chain at barrier + shared-memory speed.
 // `width` = entries per partial row (E, or 2E for outcome sampling: regret deltas then average-policy deltas).
-constexpr int kMcPrefetch = 8, kMcLogThreads = 256;
+constexpr int kMcPrefetch = 16, kMcLogThreads = 256;
 __global__ void __launch_bounds__(kMcLogThreads) k_mccfr_partial_log(int K, int lane_begin, int L, McLog lg, int width, double* __restrict__ partials) {
   extern __shared__ double mc_part[];
   const int ql = blockIdx.x, q = lane_begin + ql, tid = threadIdx.x;
@@ -527,12 +527,14 @@ __global__ void __launch_bounds__(kMcLogThreads) k_mccfr_partial_log(int K, int 
   const int nj = q < K ? (K - q + 63) / 64 : 0;          // traversal j of this lane is k = q + 64 j, held by thread row ql + L j
   int n[kMcPrefetch];
   int4 rec[kMcPrefetch];
+  // the record is loaded whether or not slot `tid` is in use (validity is decided at the add, from the count): a load that
+  // waited for the count would stall the in-order warp for a full memory latency per traversal and undo the prefetch
   auto fetch = [&](int j, int& nn, int4& r) {
     nn = 0;
     if (j < nj) {
       const size_t row = (size_t)ql + (size_t)L * j;
       nn = lg.counts[row];
-      if (tid < nn) r = lg.rec[row * lg.cap + tid];
+      if (tid < lg.cap) r = lg.rec[row * lg.cap + tid];
     }
   };
   auto add = [&](const int4& r) {
@@ -557,6 +559,21 @@ __global__ void __launch_bounds__(kMcLogThreads) k_mccfr_partial_log(int K, int 
     }
   }
   for (int e = tid; e < width; e += kMcLogThreads) partials[(size_t)q * width + e] = mc_part[e];
+}
+
+// Log -> dense rows: one thread per record slot.  The traversal kernels are latency chains (a few thousand threads walking a
+// tree); letting them also read-modify-write their dense delta rows costs them a third of their time (k_mccfr_es 119 -> 74 us
+// at K = 16,384 on leduc, profiles/r02_item9_summary.md), whereas scattering the same records from a kernel of its own is a
+// few microseconds of fully parallel stores.  Entries are distinct within a traversal and the rows are zero between phases
+// (k_mccfr_apply re-zeroes what it reads), so a plain store reproduces the dense path's cell exactly.
+__global__ void __launch_bounds__(256) k_mccfr_scatter(McLog lg, long long slots, int stride, double* __restrict__ rows) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= slots) return;
+  const long long t = g / lg.cap;
+  const int j = (int)(g - t * lg.cap);
+  if (j >= lg.counts[t]) return;
+  const int4 r = lg.rec[g];
+  rows[(size_t)t * stride + r.x] = __longlong_as_double((long long)(((u64)(u32)r.w << 32) | (u32)r.z));
 }
 
 // step 2 (after the lanes of all ranks have been gathered): the tree over the 64 lanes, then table += partial[0].
@@ -1032,12 +1049,33 @@ int b2s_cfr_iterate(void* solver, int iters, void* stream) {
   return 0;
 }
 
-// Delta logs are used whenever one lane's partial row fits the shared memory of a block; B2S_MCCFR_DENSE=1 forces the dense
-// rows (kept for tables wider than that, and for the before / after measurement under profiles/).
+// How the K traversals' deltas reach the tables (all three add the same numbers in the same order; the GPU suite compares them
+// bit for bit):
+//   kMcScatter (default)  traversals write delta logs, k_mccfr_scatter expands them into the dense [K][width] rows, k_mccfr_apply
+//                         streams the rows (coalesced, at HBM speed) — the fastest when the rows fit comfortably in HBM;
+//   kMcLanes64            traversals write delta logs, k_mccfr_partial_log adds them lane by lane in shared memory: no [K][width]
+//                         buffer at all (memory O(K x records) instead of O(K x table)), but each lane's K / 64 traversals are a
+//                         sequential chain — chosen when the dense rows would exceed kMcDenseMaxBytes (or B2S_MCCFR_MODE=lanes);
+//   kMcDense              round 1's path: the traversals read-modify-write their dense rows themselves (B2S_MCCFR_MODE=dense, or
+//                         B2S_MCCFR_DENSE=1; kept for the before / after measurement, and when a partial row does not fit shared memory).
+enum McMode { kMcScatter = 0, kMcLanes64 = 1, kMcDense = 2 };
 constexpr size_t kMcLogMaxShared = 200 * 1024;
-static bool mccfr_use_log(const CfrSolver* S, int width) {
-  static const bool dense = [] { const char* e = getenv("B2S_MCCFR_DENSE"); return e && atoi(e) != 0; }();
-  return !dense && sizeof(double) * (size_t)width <= kMcLogMaxShared;
+constexpr size_t kMcDenseMaxBytes = (size_t)8 << 30;
+static McMode mccfr_mode(const CfrSolver*, int rows, int width) {
+  static const int forced = [] {
+    if (const char* d = getenv("B2S_MCCFR_DENSE")) if (atoi(d) != 0) return (int)kMcDense;
+    const char* e = getenv("B2S_MCCFR_MODE");
+    if (!e) return -1;
+    if (!strcmp(e, "dense")) return (int)kMcDense;
+    if (!strcmp(e, "lanes")) return (int)kMcLanes64;
+    if (!strcmp(e, "scatter")) return (int)kMcScatter;
+    return -1;
+  }();
+  const bool lanes_fit = sizeof(double) * (size_t)width <= kMcLogMaxShared;
+  if (forced == kMcLanes64 && lanes_fit) return kMcLanes64;
+  if (forced == kMcDense || forced == kMcScatter) return (McMode)forced;
+  const size_t dense_bytes = sizeof(double) * (size_t)width * (size_t)rows;
+  return (dense_bytes > kMcDenseMaxBytes && lanes_fit) ? kMcLanes64 : kMcScatter;
 }
 static McLog mccfr_log(const CfrSolver* S) { return McLog{S->mc_log, S->mc_counts, S->mc_log_cap}; }
 
@@ -1052,7 +1090,8 @@ static int mccfr_prepare(CfrSolver* S, int rows_needed, int width, int cap) {
     B2S_CU(cudaMalloc((void**)&S->mc_err, sizeof(int)));
     B2S_CU(cudaMemset(S->mc_err, 0, sizeof(int)));
   }
-  if (mccfr_use_log(S, width)) {
+  const McMode mode = mccfr_mode(S, rows_needed, width);
+  if (mode != kMcDense) {
     if (S->mc_log_rows < rows_needed || S->mc_log_cap < cap) {
       if (S->mc_log) cudaFree(S->mc_log);
       if (S->mc_counts) cudaFree(S->mc_counts);
@@ -1063,7 +1102,7 @@ static int mccfr_prepare(CfrSolver* S, int rows_needed, int width, int cap) {
       B2S_CU(cudaMemset(S->mc_counts, 0, sizeof(int) * (size_t)rows));
       S->mc_log_rows = rows; S->mc_log_cap = c;
     }
-    if (!S->mc_partials) {
+    if (mode == kMcLanes64 && !S->mc_partials) {
       B2S_CU(cudaMalloc((void**)&S->mc_partials, sizeof(double) * (size_t)kMcLanes * 2 * (size_t)E));
       static bool attr = false;
       if (!attr) {
@@ -1071,7 +1110,7 @@ static int mccfr_prepare(CfrSolver* S, int rows_needed, int width, int cap) {
         attr = true;
       }
     }
-    return 0;
+    if (mode == kMcLanes64) return 0;
   }
   rows_needed *= width / E;                              // dense rows are allocated in units of E doubles
   if (S->mc_rows_k < rows_needed) {
@@ -1095,11 +1134,19 @@ int b2s_mccfr_traverse_lanes(void* solver, int player, int traversals_per_update
   if (int r = mccfr_prepare(S, n_threads, E, S->mc_cap_es)) return r;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned phase = (unsigned)(S->iteration * 2 + player);
-  if (mccfr_use_log(S, E)) {
+  const McMode mode = mccfr_mode(S, n_threads, E);
+  if (mode == kMcLanes64) {
     k_mccfr_es<true><<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, nullptr, mccfr_log(S), S->mc_err, 1);
     k_mccfr_partial_log<<<L, kMcLogThreads, sizeof(double) * (size_t)E, st>>>(K, lane_begin, L, mccfr_log(S), E, partials_d);
   } else {
-    k_mccfr_es<false><<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, S->mc_rows, McLog{}, S->mc_err, 1);
+    if (mode == kMcScatter) {
+      const long long slots = (long long)n_threads * S->mc_log_cap;
+      k_mccfr_es<true><<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, nullptr, mccfr_log(S), S->mc_err, 1);
+      k_mccfr_scatter<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(mccfr_log(S), slots, E, S->mc_rows);
+      ++g_launches;
+    } else {
+      k_mccfr_es<false><<<(n_threads + 127) / 128, 128, 0, st>>>(S->d, player, phase, seed, K, lane_begin, L, n_threads, S->mc_rows, McLog{}, S->mc_err, 1);
+    }
     k_mccfr_partial<<<(E + kMcTile - 1) / kMcTile, dim3(kMcTile, kMcLanes), 0, st>>>(S->d, K, lane_begin, L, S->mc_rows, partials_d);
   }
   g_launches += 2;
@@ -1143,16 +1190,22 @@ int b2s_mccfr_external_iterate_ex(void* solver, int iters, int traversals_per_up
   cudaStream_t st = (cudaStream_t)stream;
   const int K = traversals_per_update, E = S->d.n_entries;
   const int full = (flags & B2S_MCCFR_FULL_AVERAGE) ? 1 : 0;
-  const bool use_log = mccfr_use_log(S, E);
+  const McMode mode = mccfr_mode(S, K, E);
   const dim3 ablock(kMcTile, kMcLanes);
   const unsigned agrid = (unsigned)((E + kMcTile - 1) / kMcTile);
+  const long long slots = (long long)K * S->mc_log_cap;
   for (int it = 0; it < iters; ++it) {
     for (int p = 0; p < 2; ++p) {
       unsigned phase = (unsigned)(S->iteration * 2 + p);
-      if (use_log) {
+      if (mode == kMcLanes64) {
         k_mccfr_es<true><<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, 0, kMcLanes, K, nullptr, mccfr_log(S), S->mc_err, full ? 0 : 1);
         k_mccfr_partial_log<<<kMcLanes, kMcLogThreads, sizeof(double) * (size_t)E, st>>>(K, 0, kMcLanes, mccfr_log(S), E, S->mc_partials);
         k_mccfr_combine<<<agrid, ablock, 0, st>>>(S->d, p, S->mc_partials, E, 0);
+        g_launches += 3;
+      } else if (mode == kMcScatter) {
+        k_mccfr_es<true><<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, 0, kMcLanes, K, nullptr, mccfr_log(S), S->mc_err, full ? 0 : 1);
+        k_mccfr_scatter<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(mccfr_log(S), slots, E, S->mc_rows);
+        k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows, E, 0);
         g_launches += 3;
       } else {
         k_mccfr_es<false><<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, 0, kMcLanes, K, S->mc_rows, McLog{}, S->mc_err, full ? 0 : 1);
@@ -1180,11 +1233,18 @@ int b2s_mccfr_outcome_iterate(void* solver, int iters, int trajectories_per_upda
   const int K = trajectories_per_update, E = S->d.n_entries;
   const dim3 ablock(kMcTile, kMcLanes);
   const unsigned agrid = (unsigned)((E + kMcTile - 1) / kMcTile);
-  const bool use_log = mccfr_use_log(S, 2 * E);
+  const McMode mode = mccfr_mode(S, K, 2 * E);
+  const long long slots = (long long)K * S->mc_log_cap;
   for (int it = 0; it < iters; ++it) {
     for (int p = 0; p < 2; ++p) {
       unsigned phase = (unsigned)(S->iteration * 2 + p);
-      if (use_log) {
+      if (mode == kMcScatter) {
+        k_mccfr_os<true><<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, epsilon, nullptr, mccfr_log(S), S->mc_err);
+        k_mccfr_scatter<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(mccfr_log(S), slots, 2 * E, S->mc_rows);
+        k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows, 2 * E, 1);
+        k_mccfr_apply<<<agrid, ablock, 0, st>>>(S->d, p, K, S->mc_rows + E, 2 * E, 2);
+        g_launches += 4;
+      } else if (mode == kMcLanes64) {
         k_mccfr_os<true><<<(K + 127) / 128, 128, 0, st>>>(S->d, p, phase, seed, K, epsilon, nullptr, mccfr_log(S), S->mc_err);
         k_mccfr_partial_log<<<kMcLanes, kMcLogThreads, sizeof(double) * 2 * (size_t)E, st>>>(K, 0, kMcLanes, mccfr_log(S), 2 * E, S->mc_partials);
         k_mccfr_combine<<<agrid, ablock, 0, st>>>(S->d, p, S->mc_partials, 2 * E, 1);

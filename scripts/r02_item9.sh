@@ -44,3 +44,11 @@ P
 ncu --set full --clock-control none --import-source on -k regex:"k_mccfr_(partial_log|combine|es)" -s 6 -c 3 -o gpurun_out/r02_prof_mccfr_log python /tmp/mc1.py > /dev/null 2>&1
 B2S_MCCFR_DENSE=1 ncu --set full --clock-control none --import-source on -k regex:"k_mccfr_(apply|es)" -s 4 -c 2 -o gpurun_out/r02_prof_mccfr_dense python /tmp/mc1.py > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep
+echo "== bench at the driver's K (20 steps, 5 warm-up)"
+timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 2> gpurun_out/r02_bench_k20.err | tail -1 > gpurun_out/r02_bench_k20.json
+python - <<'P'
+import json
+d = json.load(open("gpurun_out/r02_bench_k20.json"))
+print(d["value"], d["ms_per_step"], d["roofline"]["frac"], d["roofline"].get("frac_events_around_graph"), d["config"].get("events_in_graph"), d["e2e"]["value"])
+P
+tail -2 gpurun_out/r02_bench_k20.err

@@ -68,7 +68,7 @@ for rep in sorted(os.listdir(GO)):
         out.append(rec)
     with open(os.path.join(OUT, "%s_%s_ncu_raw.json" % (tag, name)), "w") as f:
         json.dump(out, f, indent=1)
-    if "apply" in name:
+    if name == "prof_apply":
         def num(rec, key):
             v, u = rec[key].split(" ")[0], rec[key].split(" ")[1] if " " in rec[key] else ""
             x = float(v.replace(",", ""))
@@ -83,7 +83,7 @@ for rep in sorted(os.listdir(GO)):
     print("wrote", name)
 
 # 3. bench lines / sweep
-for fn in ("bench.json", "bench_ref.json", "sweep.jsonl", "gpu.csv", "nproc.txt", "pytest_gpu.log", "smoke.log"):
+for fn in ("bench.json", "bench_ref.json", "gpu.csv", "nproc.txt", "pytest_gpu.log", "smoke.log"):
     p = os.path.join(GO, tag + "_" + fn)
     if not os.path.exists(p):
         p = os.path.join(GO, fn)

@@ -159,16 +159,19 @@ print(" ".join(out))
 
 
 def test_delta_log_path_equals_dense_rows_bitwise():
-    """The sparse delta-log update (default) and the dense-row update (B2S_MCCFR_DENSE=1) add the same numbers in the same order:
-    regret and average-policy tables hash-identical for external sampling (simple and full averaging) and outcome sampling."""
+    """The three table-update paths add the same numbers in the same order — delta logs scattered into dense rows (default),
+    delta logs added lane by lane in shared memory (B2S_MCCFR_MODE=lanes), dense rows written by the traversals themselves
+    (B2S_MCCFR_MODE=dense, round 1): regret and average-policy tables hash-identical for external sampling (simple and full
+    averaging) and outcome sampling."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     runs = []
-    for dense in ("0", "1"):
-        env = dict(os.environ, B2S_MCCFR_DENSE=dense)
+    for mode in ("scatter", "lanes", "dense"):
+        env = dict(os.environ, B2S_MCCFR_MODE=mode)
+        env.pop("B2S_MCCFR_DENSE", None)
         r = subprocess.run([sys.executable, "-c", _DENSE_SCRIPT, root], capture_output=True, text=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         runs.append(r.stdout.strip().split())
-    assert len(runs[0]) == 12 and runs[0] == runs[1]
+    assert len(runs[0]) == 12 and runs[0] == runs[1] == runs[2]
