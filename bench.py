@@ -359,8 +359,8 @@ def run_gpu(args):
         """K synchronous host-buffer calls after W warm-up calls, wall clock around them; best of `reps` passes (like the
         device-resident figure), max over ranks."""
         restore()
-        for w_ in works:                      # allocate every batch's staging buffers outside the timed region
-            call(w_, 0)
+        for w_ in works:                      # outside the timed region: every batch allocates its staging buffers and captures
+            call(w_, n)                       # the pipeline graph for these host buffers (first call on a batch)
         best = None
         for _ in range(reps):
             restore()
@@ -579,7 +579,11 @@ def run_gpu(args):
                          "host_cores": cores},
         "e2e": {"value": world * n / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n,
                 "ms_per_step": ms_e2e, "timing": "wall clock around K synchronous calls after W warm-up calls, best of 3 passes, max over ranks",
+                "host_step_graph_replays": int(L.b2s_host_graph_launches()),
                 "call": "b2s_step_fused_host_compact (pinned host uint8 actions in; one status byte per lane out: terminal, outcome, next legal mask)",
+                "zero_copy_steps": int(L.b2s_host_zero_copy_steps()),
+                "path": "the step kernel reads the action bytes from the pinned host buffer and writes the status bytes back itself over PCIe (no DMA copies)"
+                        if L.b2s_host_zero_copy_steps() > 0 else "cudaMemcpyAsync H2D, kernel, cudaMemcpyAsync D2H",
                 "consistent_with_float_entry": e2e_consistent},
         "gpu_launches": K,
         "extras": {"apply_1_chain_steps_per_s": world * n / (ms_apply_s1 / K / 1e3), "apply_1_chain_ms": ms_apply_s1 / K,

@@ -144,7 +144,16 @@ int b2s_step_fused_host(void* batch, const int32_t* actions_h, uint32_t* mask_wo
  * connect_four lane.  Ordering of both *_host entry points: they run on library-owned BLOCKING streams, i.e. after work
  * already enqueued on the legacy default stream (stream = NULL) for this device and before later NULL-stream work; work the
  * caller has in flight on other streams must be synchronised by the caller first.  Both return after the results are in
- * the host buffers. */
+ * the host buffers.
+ * With PINNED host buffers and n >= 65536 the upload -> kernel -> download pipeline is captured once per (batch, buffers, n)
+ * into a CUDA graph and replayed with one launch per call instead of five driver calls per chunk; up to 4 graphs are kept
+ * per batch, least recently used evicted.  A buffer must
+ * stay pinned for as long as it is used with the batch.  B2S_HOST_GRAPH=0 keeps the plain stream path, which pageable
+ * buffers and small batches always take.  b2s_host_graph_launches() counts the graph replays of this process.
+ * Byte-wide entry without mask words, pinned + device-mapped buffers (cudaHostAlloc / cudaHostRegister under unified
+ * addressing — what torch's pin_memory() gives), both 16-byte aligned: no copy at all — the step kernel reads the action
+ * bytes from host memory and writes the status bytes back itself (B2S_HOST_ZEROCOPY=0 disables; b2s_host_zero_copy_steps()
+ * counts). */
 int b2s_step_fused_host_compact(void* batch, const void* actions_h, int action_bytes, uint8_t* status_h,
                                 uint32_t* mask_words_h, int64_t n);
 
@@ -355,6 +364,8 @@ int  b2s_bind_host_to_device(int device, int* n_cpus);
 
 /* Launch accounting: number of kernels this library has launched in this process. */
 int64_t b2s_launch_count(void);
+int64_t b2s_host_graph_launches(void);
+int64_t b2s_host_zero_copy_steps(void);
 
 const char* b2s_last_error(void);
 const char* b2s_version(void);

@@ -120,6 +120,8 @@ SIGNATURES = {
     "b2s_stream_synchronize": (C.c_int, [C.c_int, _VP]),
     "b2s_device_count": (C.c_int, []),
     "b2s_launch_count": (_I64, []),
+    "b2s_host_graph_launches": (_I64, []),
+    "b2s_host_zero_copy_steps": (_I64, []),
     "b2s_last_error": (C.c_char_p, []),
     "b2s_version": (C.c_char_p, []),
 }

@@ -46,12 +46,21 @@ struct Batch {
   // staging for the *_host entry points
   int* act_d = nullptr; u32* mask_d = nullptr; unsigned char* term_d = nullptr; float* rets_d = nullptr;
   bool host_ready = false;                       // b2s_step_fused_host staging buffers allocated
+  // b2s_step_fused_host*: instantiated CUDA graphs of the chunked upload -> kernel -> download pipeline, one per
+  // (host buffers, lane count, entry point) the batch has been stepped with (step_host_impl)
+  struct HostGraph {
+    const void* actions; void* mask; void* term; void* rets; long long n; int action_bytes, compact;
+    cudaGraphExec_t exec; unsigned long long stamp;
+  };
+  std::vector<HostGraph> host_graphs;
+  unsigned long long host_graph_clock = 0;
   // MCTS scratch (b2s_mcts_search): work lanes, log table, node arena
   void* mcts_work = nullptr; u64* mcts_hist = nullptr; long long mcts_work_cap = 0;
   double* mcts_log = nullptr; int mcts_log_n = 0;
   void* mcts_pool = nullptr; unsigned long long mcts_pool_bytes = 0; unsigned long long* mcts_top = nullptr;
   Ctx ctx() const { Ctx c; c.planes = planes; c.cap = cap; c.hist = hist; c.err = err; return c; }
   ~Batch() {
+    for (auto& g : host_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (planes) cudaFree(planes);
     if (hist) cudaFree(hist);
     if (err) cudaFree(err);
@@ -106,6 +115,9 @@ extern "C" {
 const char* b2s_last_error(void) { return g_err.c_str(); }
 const char* b2s_version(void) { return "b2s 0.1 (sm_100a)"; }
 int64_t b2s_launch_count(void) { return g_launches; }
+static int64_t g_host_graph_launches = 0, g_host_zero_copy_steps = 0;
+int64_t b2s_host_graph_launches(void) { return g_host_graph_launches; }
+int64_t b2s_host_zero_copy_steps(void) { return g_host_zero_copy_steps; }
 
 int b2s_game_id(const char* name) {
   static const char* names[B2S_NUM_GAMES] = {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go",
@@ -290,6 +302,47 @@ int b2s_step_fused(void* batch, const int32_t* actions_d, uint32_t* mask_d, uint
 
 // Shared body of the *_host step entry points.  compact = 0: int32 actions in, mask words / terminal / float returns out
 // (b2s_step_fused_host); compact = 1: `action_bytes`-wide actions in, one status byte (+ optional mask words) out.
+constexpr size_t kHostGraphsPerBatch = 4;
+
+// Chunked and double-streamed: the upload + kernel of chunk c+1 (stream hs) overlaps the download of chunk c (stream hs2) —
+// PCIe is full duplex, so the step costs about max(H2D, D2H) instead of their sum.  join: hs finally waits for hs2 (needed
+// when the sequence is being captured into a graph: every forked stream must rejoin the origin).
+static int enqueue_host_step(Batch* B, HostPipe& pipe, const void* actions_h, int action_bytes, uint32_t* mask_h, uint8_t* term_or_status_h,
+                             float* rets_h, int64_t n, int compact, int n_chunks, bool join) {
+  cudaStream_t st = pipe.hs, st2 = pipe.hs2;
+  const size_t W = (size_t)B->info.mask_words, P = (size_t)B->info.num_players, cb = B->ops->chunk_bytes();
+  const size_t ab = (size_t)action_bytes;
+  const int64_t chunk = n_chunks > 1 ? ((n + n_chunks - 1) / n_chunks + 1023) / 1024 * 1024 : n;
+  int c = 0, rc = 0;
+  cudaError_t e = cudaSuccess;
+  for (int64_t lo = 0; lo < n && !rc; lo += chunk, ++c) {
+    const int64_t len = n - lo < chunk ? n - lo : chunk;
+    Ctx v = B->ctx();
+    v.planes = (char*)v.planes + (size_t)lo * cb;
+    if (v.hist) v.hist += lo;
+    v.lane0 = lo;
+    char* act_d = (char*)B->act_d + (size_t)lo * ab;
+    e = cudaMemcpyAsync(act_d, (const char*)actions_h + (size_t)lo * ab, ab * len, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "step_host: upload"); break; }
+    if (compact)
+      B->ops->step_compact(v, act_d, action_bytes, B->term_d + lo, mask_h ? B->mask_d + lo * W : nullptr, len, st);
+    else
+      B->ops->step_fused(v, (const int*)act_d, mask_h ? B->mask_d + lo * W : nullptr, term_or_status_h ? B->term_d + lo : nullptr,
+                         rets_h ? B->rets_d + lo * P : nullptr, len, st);
+    if ((rc = post())) break;
+    cudaEvent_t ev = pipe.ev[c % kHostChunks];
+    if ((e = cudaEventRecord(ev, st)) != cudaSuccess || (e = cudaStreamWaitEvent(st2, ev, 0)) != cudaSuccess) { rc = cuda_fail(e, "step_host: event"); break; }
+    if (mask_h && (e = cudaMemcpyAsync(mask_h + lo * W, B->mask_d + lo * W, sizeof(u32) * W * len, cudaMemcpyDeviceToHost, st2)) != cudaSuccess) { rc = cuda_fail(e, "step_host: download"); break; }
+    if (term_or_status_h && (e = cudaMemcpyAsync(term_or_status_h + lo, B->term_d + lo, len, cudaMemcpyDeviceToHost, st2)) != cudaSuccess) { rc = cuda_fail(e, "step_host: download"); break; }
+    if (rets_h && (e = cudaMemcpyAsync(rets_h + lo * P, B->rets_d + lo * P, sizeof(float) * P * len, cudaMemcpyDeviceToHost, st2)) != cudaSuccess) { rc = cuda_fail(e, "step_host: download"); break; }
+  }
+  if (join && c > 0) {
+    cudaEvent_t ev = pipe.ev[c % kHostChunks];
+    if ((e = cudaEventRecord(ev, st2)) != cudaSuccess || (e = cudaStreamWaitEvent(st, ev, 0)) != cudaSuccess) { if (!rc) rc = cuda_fail(e, "step_host: join"); }
+  }
+  return rc;
+}
+
 static int step_host_impl(Batch* B, const void* actions_h, int action_bytes, uint32_t* mask_h, uint8_t* term_or_status_h,
                           float* rets_h, int64_t n, int compact) {
   // The two streams and the chunk events are shared by all batches of a device (a fresh stream / event costs tens of
@@ -313,43 +366,103 @@ static int step_host_impl(Batch* B, const void* actions_h, int action_bytes, uin
     CU(cudaMalloc((void**)&B->rets_d, sizeof(float) * (size_t)B->info.num_players * B->cap));
     B->host_ready = true;                        // only once every staging buffer exists
   }
-  // Chunked and double-streamed: the upload + kernel of chunk c+1 (stream hs) overlaps the download of chunk c
-  // (stream hs2) — PCIe is full duplex, so the call costs about max(H2D, D2H) instead of their sum.
   cudaStream_t st = pipe.hs, st2 = pipe.hs2;
-  const size_t W = (size_t)B->info.mask_words, P = (size_t)B->info.num_players, cb = B->ops->chunk_bytes();
-  const size_t ab = (size_t)action_bytes;
-  static const int n_chunks = [] {                 // B2S_HOST_CHUNKS=1..8 overrides the default (tuning knob)
+  const size_t W = (size_t)B->info.mask_words, P = (size_t)B->info.num_players;
+  const size_t bytes_per_lane = (size_t)action_bytes + (compact ? 1 : (term_or_status_h ? 1 : 0) + (rets_h ? sizeof(float) * P : 0)) + (mask_h ? sizeof(u32) * W : 0);
+  static const int env_chunks = [] {               // B2S_HOST_CHUNKS=1..8 overrides the defaults (tuning knob)
     const char* e = getenv("B2S_HOST_CHUNKS");
-    int v = e ? atoi(e) : kHostChunksDefault;
-    return v < 1 ? 1 : (v > kHostChunks ? kHostChunks : v);
+    int v = e ? atoi(e) : 0;
+    return v < 1 ? 0 : (v > kHostChunks ? kHostChunks : v);
   }();
+  static const bool graphs_on = [] { const char* e = getenv("B2S_HOST_GRAPH"); return !e || atoi(e) != 0; }();
+
   // two chunks overlap the upload + kernel of one half with the download of the other; that only pays when the copies
-  // are long compared with the per-copy launch cost (a few microseconds): below ~4 MiB of traffic the call runs as one chunk
-  const size_t bytes_per_lane = ab + (compact ? 1 : (term_or_status_h ? 1 : 0) + (rets_h ? sizeof(float) * P : 0)) + (mask_h ? sizeof(u32) * W : 0);
-  const bool split = n_chunks > 1 && n >= (1 << 18) && bytes_per_lane * (size_t)n >= (4u << 20);
-  const int64_t chunk = split ? ((n + n_chunks - 1) / n_chunks + 1023) / 1024 * 1024 : n;
-  int c = 0, rc = 0;
-  for (int64_t lo = 0; lo < n && !rc; lo += chunk, ++c) {
-    const int64_t len = n - lo < chunk ? n - lo : chunk;
-    Ctx v = B->ctx();
-    v.planes = (char*)v.planes + (size_t)lo * cb;
-    if (v.hist) v.hist += lo;
-    v.lane0 = lo;
-    char* act_d = (char*)B->act_d + (size_t)lo * ab;
-    cudaError_t e = cudaMemcpyAsync(act_d, (const char*)actions_h + (size_t)lo * ab, ab * len, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { rc = cuda_fail(e, "step_host: upload"); break; }
-    if (compact)
-      B->ops->step_compact(v, act_d, action_bytes, B->term_d + lo, mask_h ? B->mask_d + lo * W : nullptr, len, st);
-    else
-      B->ops->step_fused(v, (const int*)act_d, mask_h ? B->mask_d + lo * W : nullptr, term_or_status_h ? B->term_d + lo : nullptr,
-                         rets_h ? B->rets_d + lo * P : nullptr, len, st);
-    if ((rc = post())) break;
-    cudaEvent_t ev = pipe.ev[c % kHostChunks];
-    if ((e = cudaEventRecord(ev, st)) != cudaSuccess || (e = cudaStreamWaitEvent(st2, ev, 0)) != cudaSuccess) { rc = cuda_fail(e, "step_host: event"); break; }
-    if (mask_h && (e = cudaMemcpyAsync(mask_h + lo * W, B->mask_d + lo * W, sizeof(u32) * W * len, cudaMemcpyDeviceToHost, st2)) != cudaSuccess) { rc = cuda_fail(e, "step_host: download"); break; }
-    if (term_or_status_h && (e = cudaMemcpyAsync(term_or_status_h + lo, B->term_d + lo, len, cudaMemcpyDeviceToHost, st2)) != cudaSuccess) { rc = cuda_fail(e, "step_host: download"); break; }
-    if (rets_h && (e = cudaMemcpyAsync(rets_h + lo * P, B->rets_d + lo * P, sizeof(float) * P * len, cudaMemcpyDeviceToHost, st2)) != cudaSuccess) { rc = cuda_fail(e, "step_host: download"); break; }
+  // are long compared with the fixed cost of a copy (~10-15 us of DMA set-up each, measured with the copies as graph nodes
+  // too: scripts/r02_e2e_graph.py): below ~4 MiB of traffic the call runs as one chunk
+  const int n_chunks = env_chunks ? env_chunks : kHostChunksDefault;
+  const bool split = n_chunks > 1 && n >= (1 << 18) && (env_chunks || bytes_per_lane * (size_t)n >= (4u << 20));
+  const int chunks = split ? n_chunks : 1;
+
+  // ---- zero-copy path (byte-wide entry, pinned + device-mapped buffers): no DMA copies at all, see k_step_compact_zc ----------
+  static const bool zero_copy_on = [] { const char* e = getenv("B2S_HOST_ZEROCOPY"); return !e || atoi(e) != 0; }();
+  if (zero_copy_on && compact && action_bytes == 1 && !mask_h && n >= (1 << 12) &&
+      ((uintptr_t)actions_h & 15) == 0 && ((uintptr_t)term_or_status_h & 15) == 0) {
+    void *a_dev = nullptr, *s_dev = nullptr;
+    cudaPointerAttributes pa, ps;
+    if (cudaPointerGetAttributes(&pa, actions_h) == cudaSuccess && cudaPointerGetAttributes(&ps, term_or_status_h) == cudaSuccess &&
+        pa.type == cudaMemoryTypeHost && ps.type == cudaMemoryTypeHost && pa.devicePointer && ps.devicePointer) {
+      a_dev = pa.devicePointer; s_dev = ps.devicePointer;
+      B->ops->step_compact_zero_copy(B->ctx(), (const unsigned char*)a_dev, (unsigned char*)s_dev, n, st);
+      int rc = post();
+      cudaError_t e1 = cudaStreamSynchronize(st);
+      ++g_host_zero_copy_steps;
+      if (rc) return rc;
+      if (e1 != cudaSuccess) return cuda_fail(e1, "step_host: synchronize");
+      return 0;
+    }
+    cudaGetLastError();
   }
+
+  // ---- graph path: the pipeline is ONE cudaGraphLaunch -----------------------------------------------------------------
+  // RL loops step the same batch with the same pinned buffers every time, so the upload -> kernel -> download sequence is
+  // captured once per (batch, buffers, n) and replayed: one driver call instead of five per chunk.  Measured at 1M
+  // connect_four lanes (profiles/r02_e2e_graph.txt): byte-wide entry 95.7 -> 92.7 us, float entry 468 -> 345 us (its 2-chunk
+  // overlap no longer pays ten driver calls).  Pageable buffers (a captured copy must be a real DMA) and small batches take
+  // the plain stream path below.
+  static bool graphs_broken = false;            // a capture / instantiate failure turns the graph path off for the process
+  if (graphs_on && !graphs_broken && n >= (1 << 16)) {
+    auto pinned = [](const void* p) {
+      if (!p) return true;
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+      return a.type == cudaMemoryTypeHost;
+    };
+    if (pinned(actions_h) && pinned(mask_h) && pinned(term_or_status_h) && pinned(rets_h)) {
+      Batch::HostGraph* hit = nullptr;
+      for (auto& g : B->host_graphs)
+        if (g.actions == actions_h && g.mask == mask_h && g.term == term_or_status_h && g.rets == rets_h && g.n == n &&
+            g.action_bytes == action_bytes && g.compact == compact) { hit = &g; break; }
+      if (!hit) {
+        cudaGraph_t graph = nullptr;
+        Batch::HostGraph g{actions_h, mask_h, term_or_status_h, rets_h, n, action_bytes, compact, nullptr, 0};
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+          const int rc = enqueue_host_step(B, pipe, actions_h, action_bytes, mask_h, term_or_status_h, rets_h, n, compact, chunks, /*join=*/true);
+          e = cudaStreamEndCapture(st, &graph);
+          if (rc && e == cudaSuccess) e = cudaErrorUnknown;
+        }
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) {                    // not capturable here: fall back to the plain stream path, for good
+          cudaGetLastError();
+          graphs_broken = true;
+          goto stream_path;
+        }
+        if (B->host_graphs.size() >= kHostGraphsPerBatch) {                    // evict the least recently used
+          size_t lru = 0;
+          for (size_t i = 1; i < B->host_graphs.size(); ++i) if (B->host_graphs[i].stamp < B->host_graphs[lru].stamp) lru = i;
+          cudaGraphExecDestroy(B->host_graphs[lru].exec);
+          B->host_graphs[lru] = g;
+          hit = &B->host_graphs[lru];
+        } else {
+          B->host_graphs.push_back(g);
+          hit = &B->host_graphs.back();
+        }
+      }
+      hit->stamp = ++B->host_graph_clock;
+      cudaError_t e = cudaGraphLaunch(hit->exec, st);
+      g_launches += 1;
+      g_host_graph_launches += 1;
+      cudaError_t e1 = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return cuda_fail(e, "step_host: graph launch");
+      if (e1 != cudaSuccess) return cuda_fail(e1, "step_host: synchronize");
+      return 0;
+    }
+  }
+
+stream_path:
+  // ---- stream path ------------------------------------------------------------------------------------------------------
+  int rc = enqueue_host_step(B, pipe, actions_h, action_bytes, mask_h, term_or_status_h, rets_h, n, compact, chunks, /*join=*/false);
   // always drain both streams, error or not: no copy into a caller's host buffer may stay in flight after the call
   cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(st2);
   if (rc) return rc;

@@ -400,6 +400,62 @@ __global__ void __launch_bounds__(kBlock) k_traj_begin(Ctx ctx, typename R::Cfg 
   R::store(s, ctx, i);
 }
 
+// Zero-copy form of k_step_compact for pinned, device-mapped host buffers (b2s_step_fused_host_compact): the kernel reads the
+// action bytes straight from host memory and writes the status bytes straight back, so a step is ONE launch and the bytes
+// cross PCIe under the kernel's own load / store parallelism — no DMA-engine copies, whose fixed set-up (~10-15 us each way)
+// is most of a 1M-lane step whose payload is 1 MiB each way.  PCIe wants large requests: a block moves its kBlock * ILP
+// action bytes with 16-byte loads into shared memory (one 64-thread slice of the block, 1 KiB contiguous per block), works
+// from there, and writes its status bytes back the same way.  `actions` / `status` are device-visible addresses of the host
+// buffers, 16-byte aligned.
+template <class R, int ILP>
+__global__ void __launch_bounds__(kBlock) k_step_compact_zc(Ctx ctx, typename R::Cfg cfg, const unsigned char* __restrict__ actions,
+                                                            unsigned char* __restrict__ status, int small_mask, long long n) {
+  __shared__ __align__(16) unsigned char act_s[kBlock * ILP];
+  __shared__ __align__(16) unsigned char st_s[kBlock * ILP];
+  const long long b0 = (long long)blockIdx.x * (kBlock * ILP);
+  const long long left = n - b0;
+  const int here = (int)(left < kBlock * ILP ? left : kBlock * ILP);       // lanes of this block
+  const int vec = threadIdx.x * 16;
+  if (vec < here) {
+    if (vec + 16 <= here) *reinterpret_cast<uint4*>(act_s + vec) = *reinterpret_cast<const uint4*>(actions + b0 + vec);
+    else for (int k = vec; k < here; ++k) act_s[k] = actions[b0 + k];
+  }
+  long long base = b0 + threadIdx.x;
+  typename R::S s[ILP];
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    if (i < n) R::load(s[j], ctx, i);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < ILP; ++j) {
+    long long i = base + (long long)j * kBlock;
+    if (i >= n) continue;
+    const unsigned raw = act_s[threadIdx.x + j * kBlock];
+    if (raw != 0xFFu) {
+      if (R::terminal(s[j], cfg) || !R::apply(s[j], (int)raw, cfg, ctx, i)) flag_error(ctx.err, ctx.lane0 + i);
+      else R::store(s[j], ctx, i);
+    }
+    unsigned st = 0;
+    if (R::terminal(s[j], cfg)) {
+      float r[R::kPlayers];
+      R::returns(s[j], cfg, r);
+      st = 0x80u | (r[0] > 0.f ? 1u : (r[0] < 0.f ? 2u : 0u));
+    } else if (small_mask) {
+      u32 m[R::kMaskWords];
+      R::legal_nonterminal(s[j], cfg, m);
+      st = m[0] & 0x7Fu;
+    }
+    st_s[threadIdx.x + j * kBlock] = (unsigned char)st;
+  }
+  __syncthreads();
+  if (vec < here) {
+    if (vec + 16 <= here) *reinterpret_cast<uint4*>(status + b0 + vec) = *reinterpret_cast<const uint4*>(st_s + vec);
+    else for (int k = vec; k < here; ++k) status[b0 + k] = st_s[k];
+  }
+}
+
 struct TrajStepOut {          // row t of the time-major outputs; any pointer may be null
   u32* mask;                  // [n][mask_words]
   int* actions;               // [n]
@@ -527,6 +583,8 @@ struct GameOps {
   virtual const char* obs(const Ctx&, int player, int which, int zero_terminal, float* out, long long n, cudaStream_t) = 0;
   virtual void step_fused(const Ctx&, const int* a, u32* m, unsigned char* term, float* rets, long long n, cudaStream_t) = 0;
   virtual void step_compact(const Ctx&, const void* a, int action_bytes, unsigned char* status, u32* m, long long n, cudaStream_t) = 0;
+  // uint8 actions and status bytes in device-mapped HOST memory, no mask words (k_step_compact_zc)
+  virtual void step_compact_zero_copy(const Ctx&, const unsigned char* a_host, unsigned char* status_host, long long n, cudaStream_t) = 0;
   virtual void rollout(const Ctx&, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t) = 0;
   virtual void broadcast(const Ctx& dst, long long dst0, long long count, const Ctx& src, long long srclane, cudaStream_t) = 0;
   virtual void copy(const Ctx& dst, long long dst0, const Ctx& src, long long src0, long long count, cudaStream_t) = 0;
@@ -610,6 +668,11 @@ struct GameOpsT : GameOps {
     else
       launch_pdl(k_step_compact<R, R::kIlp, int>, grid_for(n, R::kIlp), st, c, cfg, (const int*)a, status, m, info.mask_words, small_mask, n);
     ++g_launches;
+  }
+  void step_compact_zero_copy(const Ctx& c, const unsigned char* a_host, unsigned char* status_host, long long n, cudaStream_t st) override {
+    if (n <= 0) return;
+    const int small_mask = info.num_distinct_actions <= 7 ? 1 : 0;
+    k_step_compact_zc<R, R::kIlp><<<grid_for(n, R::kIlp), kBlock, 0, st>>>(c, cfg, a_host, status_host, small_mask, n); ++g_launches;
   }
   void rollout(const Ctx& c, u64 seed, long long lane_offset, float* rets, int* plies, long long n, cudaStream_t st) override {
     if (n <= 0) return;

@@ -235,3 +235,50 @@ def test_host_buffer_step_equals_device_step_across_chunks():
         c.step_host(acts_h, mask_h, term_h, rets_h)
     cnt, first = c.error_count()
     assert cnt >= 1 and first == bad_lane
+
+
+def test_host_step_graph_replay_equals_stream_path():
+    """With pinned buffers and n >= 65536 b2s_step_fused_host replays a captured CUDA graph of its chunked upload -> kernel ->
+    download pipeline, and the byte-wide entry reads / writes the pinned buffers from the kernel itself (zero copy); pageable
+    buffers take the plain stream path.  Same inputs, same outputs, call after call."""
+    from open_spiel_b200 import _lib
+    n = (1 << 17) + 333
+    game = b2.load_game("connect_four")
+    a, b, c = game.new_batch(n), game.new_batch(n), game.new_batch(n)
+    g = torch.Generator(device="cpu").manual_seed(11)
+    pin = lambda t: t.pin_memory()   # noqa: E731
+    acts_p, acts_u = pin(torch.empty((n,), dtype=torch.int32)), torch.empty((n,), dtype=torch.int32)
+    acts8_p = pin(torch.empty((n,), dtype=torch.uint8))
+    mask_p, term_p, rets_p = pin(torch.empty((n, 1), dtype=torch.int32)), pin(torch.empty((n,), dtype=torch.uint8)), pin(torch.empty((n, 2), dtype=torch.float32))
+    mask_u, term_u, rets_u = torch.empty((n, 1), dtype=torch.int32), torch.empty((n,), dtype=torch.uint8), torch.empty((n, 2), dtype=torch.float32)
+    status_p = pin(torch.empty((n,), dtype=torch.uint8))
+    before, zc_before = _lib.lib().b2s_host_graph_launches(), _lib.lib().b2s_host_zero_copy_steps()
+    for ply in range(10):
+        acts = torch.randint(0, 7, (n,), generator=g, dtype=torch.int32)
+        acts_p.copy_(acts); acts_u.copy_(acts); acts8_p.copy_(acts.to(torch.uint8))
+        a.step_host(acts_p, mask_p, term_p, rets_p)                 # pinned: graph
+        b.step_host(acts_u, mask_u, term_u, rets_u)                 # pageable: streams
+        c.step_host_compact(acts8_p, status_p)                      # pinned, byte-wide: zero copy
+        assert torch.equal(mask_p, mask_u) and torch.equal(term_p, term_u) and torch.equal(rets_p, rets_u)
+        t = term_u.bool()
+        assert torch.equal(status_p >> 7, term_u)
+        assert torch.equal((status_p & 0x7F)[~t], mask_u[:, 0].to(torch.uint8)[~t])
+    assert a.error_count()[0] == b.error_count()[0] == c.error_count()[0]
+    replays = _lib.lib().b2s_host_graph_launches() - before
+    zero_copy = _lib.lib().b2s_host_zero_copy_steps() - zc_before
+    print("host-step graph replays:", replays, "zero-copy steps:", zero_copy)
+    assert replays in (0, 10)          # 0 only when the capture is not supported on this driver (the library then stays on the stream path)
+    assert zero_copy in (0, 10)        # 0 only when pinned memory is not device-mapped here
+    # ragged sizes and the no-op byte through the zero-copy kernel, against the device-buffer step
+    for m in (4096 + 5, 70001):
+        d, e = game.new_batch(m), game.new_batch(m)
+        a8 = torch.randint(0, 7, (m,), generator=g, dtype=torch.int32)
+        a8[::7] = -1                                              # untouched lanes
+        a8_p = pin(torch.where(a8 < 0, torch.full_like(a8, 255), a8).to(torch.uint8))
+        st_p = pin(torch.zeros((m,), dtype=torch.uint8))
+        mk, tm, _ = d.step(a8.to(d._dev))
+        e.step_host_compact(a8_p, st_p)
+        assert torch.equal(st_p >> 7, tm.cpu())
+        live = ~tm.cpu().bool()
+        assert torch.equal((st_p & 0x7F)[live], mk.cpu()[:, 0].to(torch.uint8)[live])
+        assert d.error_count()[0] == e.error_count()[0]
