@@ -8,7 +8,8 @@ nproc > gpurun_out/nproc.txt; lscpu | head -20 >> gpurun_out/nproc.txt
 echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -25 | tee gpurun_out/r02_pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/r02_smoke.log
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 20 --warmup 3 2>&1 | tail -3 | tee gpurun_out/r02_bench_ref.json
-echo "== bench"; timeout 1500 python bench.py --steps 200 --warmup 10 2>&1 | tail -3 | tee gpurun_out/r02_bench.json
+echo "== bench (driver's command)"; timeout 1500 python bench.py --gpus 1 --steps 20 --warmup 5 2>&1 | tail -1 | tee gpurun_out/r02_bench_k20.json | cut -c1-600
+echo "== bench"; timeout 1500 python bench.py --steps 200 --warmup 10 2>&1 | tail -3 | tee gpurun_out/r02_bench.json | cut -c1-2500
 if [ "${1:-}" != "quick" ]; then
   echo "== ncu launches"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 2000 --csv --log-file gpurun_out/r02_launches.csv \

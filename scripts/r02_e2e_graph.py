@@ -33,12 +33,15 @@ for name, call in (("compact", lambda b: b.step_host_compact(a8, status)), ("flo
                 call(b)
         best = min(best, (time.perf_counter() - t0) / 40)
     out[name] = best
-print("zero_copy=%s graph=%s chunks=%s  compact %.1f us (%.3e steps/s)  float %.1f us (%.3e steps/s)  replays %d" % (
-    os.environ.get("B2S_HOST_ZEROCOPY", "1"), os.environ.get("B2S_HOST_GRAPH", "1"), os.environ.get("B2S_HOST_CHUNKS", "default"), out["compact"] * 1e6, n / out["compact"],
+print("zero_copy=%s (blocks/SM %s) graph=%s chunks=%s  compact %.1f us (%.3e steps/s)  float %.1f us (%.3e steps/s)  replays %d" % (
+    os.environ.get("B2S_HOST_ZEROCOPY", "1"), os.environ.get("B2S_ZC_BLOCKS_PER_SM", "-"), os.environ.get("B2S_HOST_GRAPH", "1"), os.environ.get("B2S_HOST_CHUNKS", "default"), out["compact"] * 1e6, n / out["compact"],
     out["float"] * 1e6, n / out["float"], _lib.lib().b2s_host_graph_launches()) + "  zero-copy steps %d" % _lib.lib().b2s_host_zero_copy_steps())
 '''
-for zc, graph, chunks in (("0", "0", None), ("0", "1", "1"), ("0", "1", None), ("1", "1", None)):
+for zc, graph, chunks, per_sm in (("0", "0", None, None), ("0", "1", None, None), ("1", "1", None, "1"), ("1", "1", None, "2"), ("1", "1", None, "4"),
+                                  ("1", "1", None, "8")):
     env = dict(os.environ, B2S_HOST_GRAPH=graph, B2S_HOST_ZEROCOPY=zc)
+    if per_sm:
+        env["B2S_ZC_BLOCKS_PER_SM"] = per_sm
     env.pop("B2S_HOST_CHUNKS", None)
     if chunks:
         env["B2S_HOST_CHUNKS"] = chunks
