@@ -58,6 +58,13 @@ CASES = [
     ("go(board_size=3)", 32, 14, 100, 4, False),
     # n_rollouts not a power of two: 24-byte nodes, the reference's double accumulator
     ("connect_four", 24, 6, 200, 5, True),
+    # next-tier games: pass moves inside the tree (othello), the three-edge flood (y), 256-bit boards (mnk)
+    ("othello", 32, 30, 150, 1, True),
+    ("othello", 24, 56, 300, 1, True),
+    ("y(board_size=5)", 32, 4, 300, 1, True),
+    ("y(board_size=9)", 24, 12, 120, 2, False),
+    ("mnk(m=5,n=5,k=4)", 32, 6, 200, 1, True),
+    ("mnk", 8, 10, 60, 1, True),
 ]
 
 # node budget + garbage collection (MCTSBot max_memory_mb -> max_nodes_, mcts.cc:205-231, 441-482): game, trees, prefix, sims,
@@ -69,6 +76,8 @@ GC_CASES = [
     ("go(board_size=5)", 16, 6, 1200, 1, True, 600),
     ("breakthrough(rows=5,columns=4)", 16, 3, 1500, 1, False, 250),
     ("go(board_size=9)", 8, 20, 600, 1, True, 3000),
+    ("othello", 16, 10, 1200, 1, False, 300),
+    ("mnk(m=4,n=4,k=3)", 16, 2, 1500, 2, True, 350),
 ]
 
 
