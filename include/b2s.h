@@ -46,7 +46,7 @@ extern "C" {
 int b2s_game_id(const char* short_name);
 enum {
   B2S_TIC_TAC_TOE = 0, B2S_CONNECT_FOUR = 1, B2S_BREAKTHROUGH = 2, B2S_HEX = 3, B2S_GO = 4,
-  B2S_KUHN_POKER = 5, B2S_LEDUC_POKER = 6, B2S_MNK = 7, B2S_OTHELLO = 8, B2S_Y = 9, B2S_NUM_GAMES = 10
+  B2S_KUHN_POKER = 5, B2S_LEDUC_POKER = 6, B2S_MNK = 7, B2S_OTHELLO = 8, B2S_Y = 9, B2S_HAVANNAH = 10, B2S_NUM_GAMES = 11
 };
 
 /* Game parameters (replaces GameParameters, open_spiel/game_parameters.h:31-120, for the seven

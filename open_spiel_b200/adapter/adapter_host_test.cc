@@ -91,6 +91,10 @@ int main() {
       {"go(board_size=5)", 10, 5, 1},
       {"go(board_size=3,max_game_length=30)", 20, 10, 1},
       {"go(board_size=2)", 20, 10, 1},
+      {"havannah", 20, 10, 1},                                                   // havannah_test.cc: RandomSimTest on sizes 3..8, with / without swap
+      {"havannah(board_size=4)", 100, 100, 1},
+      {"havannah(board_size=4,swap=true)", 100, 100, 1},
+      {"havannah(board_size=3,swap=true)", 60, 60, 1},
       {"y(board_size=9)", 100, 60, 1},                                           // y_test.cc: RandomSimTest on sizes up to 11
       {"y(board_size=11)", 30, 30, 1},
       {"y(board_size=3)", 60, 60, 1},
@@ -133,7 +137,7 @@ int main() {
   }
   // parameter sets the packed layouts cannot hold are served by the stock game (the previous factory)
   for (const char* g : {"go(board_size=19)", "kuhn_poker(players=6)", "leduc_poker(players=5)", "leduc_poker(suit_isomorphism=true)",
-                        "hex(board_size=13)", "connect_four(rows=12,columns=12)", "y", "y(board_size=9,ansi_color_output=true)",
+                        "hex(board_size=13)", "connect_four(rows=12,columns=12)", "y", "y(board_size=9,ansi_color_output=true)", "havannah(board_size=9)", "havannah(board_size=4,ansi_color_output=true)",
                         "mnk(m=16,n=4,k=3)"}) {
     std::shared_ptr<const Game> fb = LoadGame(g);
     SPIEL_CHECK_TRUE(dynamic_cast<const b200::B200Game*>(fb.get()) == nullptr);

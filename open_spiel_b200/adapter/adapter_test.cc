@@ -83,7 +83,7 @@ static void CfrTests() {
 // the host rule core on every observable, and one device ApplyAction must produce the blob the host produces.
 static void LaneBridgeTests(std::mt19937* rng) {
   for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex(board_size=7,swap=true)", "go(board_size=9)",
-                           "go(board_size=5)", "kuhn_poker", "kuhn_poker(players=4)", "leduc_poker", "leduc_poker(players=3)", "mnk", "mnk(m=6,n=5,k=4)", "othello", "y(board_size=9)"}) {
+                           "go(board_size=5)", "kuhn_poker", "kuhn_poker(players=4)", "leduc_poker", "leduc_poker(players=3)", "mnk", "mnk(m=6,n=5,k=4)", "othello", "y(board_size=9)", "havannah(board_size=4,swap=true)", "havannah"}) {
     std::shared_ptr<const Game> game = LoadGame(name);
     const auto* bg = dynamic_cast<const b200::B200Game*>(game.get());
     SPIEL_CHECK_TRUE(bg != nullptr);

@@ -18,6 +18,7 @@
 #define CalcXY CalcXY_b200_adapter
 #include "open_spiel/games/y/y.h"
 #undef CalcXY
+#include "open_spiel/games/havannah/havannah.h"
 #include "open_spiel/games/tic_tac_toe/tic_tac_toe.h"
 
 namespace open_spiel {
@@ -80,6 +81,10 @@ std::shared_ptr<const Game> B200Game::Create(const GameType& type, const GamePar
     p.columns = raw("m", 15);      // mnk.h:34-36
     p.rows = raw("n", 15);
     p.x_in_row = raw("k", 5);
+  } else if (name == "havannah") {
+    p.board_size = g->ParameterValue<int>("board_size");              // havannah.cc:425-429
+    if (g->ParameterValue<bool>("ansi_color_output")) return nullptr;  // escape sequences in ToString: the stock class prints them
+    p.swap = g->ParameterValue<bool>("swap") ? 1 : 0;
   } else if (name == "y") {
     p.board_size = g->ParameterValue<int>("board_size");              // y.cc:331-334
     if (g->ParameterValue<bool>("ansi_color_output")) return nullptr;  // escape sequences in ToString: the stock class prints them
@@ -255,6 +260,10 @@ std::string B200Game::ActionToString(Player player, Action a) const {
       return std::string(player == 0 ? "x" : "o") + "(" + std::to_string(a / 3) + "," + std::to_string(a % 3) + ")";
     case B2S_CONNECT_FOUR:
       return std::string(player == 0 ? "x" : "o") + std::to_string(a);
+    case B2S_HAVANNAH: {          // havannah.cc:203-206, Move::ToString :160-164
+      const int d = gi.obs_shape[1];
+      return std::string(1, (char)('a' + a % d)) + std::to_string(a / d + 1);
+    }
     case B2S_Y: {                 // y.cc:143-145, Move::ToString :110-114
       const int n = gi.obs_shape[1];
       return std::string(1, (char)('a' + a % n)) + std::to_string(a / n + 1);
@@ -414,6 +423,29 @@ std::string B200State::ToString() const {
         if (r < 2) s += "\n";
       }
       return s;
+    case B2S_HAVANNAH: {          // havannah.cc:212-279 (ansi_color_output = false)
+      const int dd = gi.obs_shape[1], size = (dd + 1) / 2;
+      s = std::string(size + 3, ' ');
+      for (int x = 0; x < size; ++x) { s += ' '; s += (char)('a' + x); }
+      s += '\n';
+      for (int y = 0; y < dd; ++y) {
+        s += std::string(std::abs(size - 1 - y) + 1 + ((y + 1) < 10), ' ');
+        s += std::to_string(y + 1);
+        bool found_last = false;
+        const int start_x = y < size ? 0 : y - size + 1, end_x = y < size ? size + y : dd;
+        for (int x = start_x; x < end_x; ++x) {
+          const int xy = x + y * dd;
+          if (found_last) { s += ']'; found_last = false; }
+          else if (d.last_move == xy) { s += '['; found_last = true; }
+          else s += ' ';
+          s += ".O@"[d.cells[xy]];
+        }
+        if (found_last) s += ']';
+        if (y < size - 1) { s += ' '; s += (char)('a' + size + y); }
+        s += '\n';
+      }
+      return s;
+    }
     case B2S_Y: {                 // y.cc:147-212 (ansi_color_output = false)
       const int n = gi.obs_shape[1];
       s = " ";
@@ -601,6 +633,7 @@ std::shared_ptr<const Game> StockGame(const std::string& name, const GameParamet
   if (name == "mnk") return std::shared_ptr<const Game>(new mnk::MNKGame(params));
   if (name == "othello") return std::shared_ptr<const Game>(new othello::OthelloGame(params));
   if (name == "y") return std::shared_ptr<const Game>(new y_game::YGame(params));
+  if (name == "havannah") return std::shared_ptr<const Game>(new havannah::HavannahGame(params));
   SpielFatalError("b200: no stock game " + name);
 }
 }  // namespace
@@ -608,7 +641,7 @@ std::shared_ptr<const Game> StockGame(const std::string& name, const GameParamet
 void RegisterB200Games() {
   static std::once_flag once;
   std::call_once(once, [] {
-    for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk", "othello", "y"}) {
+    for (const char* name : {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk", "othello", "y", "havannah"}) {
       if (!IsGameRegistered(name)) continue;                 // a build without that stock game
       GameType type;
       for (const GameType& t : GameRegisterer::RegisteredGames())

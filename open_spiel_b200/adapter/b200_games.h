@@ -116,7 +116,7 @@ class B200State : public State {
 };
 
 // Registers the B200 implementations over the stock registrations of tic_tac_toe, connect_four, breakthrough, hex, go,
-// kuhn_poker and leduc_poker (call once, after static initialisation).  Idempotent.
+// kuhn_poker, leduc_poker, mnk, othello, y and havannah (call once, after static initialisation).  Idempotent.
 void RegisterB200Games();
 
 }  // namespace b200

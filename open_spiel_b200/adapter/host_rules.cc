@@ -24,6 +24,7 @@
 #include "../csrc/rules_mnk.cuh"
 #include "../csrc/rules_othello.cuh"
 #include "../csrc/rules_y.cuh"
+#include "../csrc/rules_havannah.cuh"
 
 namespace b2s_host {
 namespace {
@@ -94,6 +95,12 @@ void decode(const YRules::S& s, const YRules::Cfg& c, Decoded* d) {
   for (int cell = 0; cell < c.cells; ++cell) d->cells[cell] = b_test(s.p1, cell) ? 1 : (b_test(s.p2, cell) ? 2 : 0);
   d->to_play = s.mover;
   d->last_move = s.last == YRules::kNoMove ? -1 : s.last;
+}
+void decode(const HavannahRules::S& s, const HavannahRules::Cfg& c, Decoded* d) {
+  d->cells.assign((size_t)c.cells, 0);
+  for (int cell = 0; cell < c.cells; ++cell) d->cells[cell] = q_test(s.p1, cell) ? 1 : (q_test(s.p2, cell) ? 2 : 0);
+  d->to_play = s.mover;
+  d->last_move = s.last == HavannahRules::kNoMove ? -1 : s.last;
 }
 void decode(const KuhnRules::S& s, const KuhnRules::Cfg& c, Decoded* d) {   // the packed kuhn state is its action history
   d->num_players = c.n;
@@ -229,6 +236,7 @@ std::unique_ptr<Rules> Rules::Create(int game_id, const b2s_params& p, std::stri
     case B2S_MNK: return make<MnkRules>(p, error);
     case B2S_OTHELLO: return make<OthelloRules>(p, error);
     case B2S_Y: return make<YRules>(p, error);
+    case B2S_HAVANNAH: return make<HavannahRules>(p, error);
     case B2S_LEDUC_POKER: return p.players > 2 ? make<LeducNRules>(p, error) : make<LeducRules>(p, error);
   }
   if (error) *error = "unknown game id";

@@ -37,9 +37,10 @@ struct Decoded {
   //   go            [row*n+col], row 0 = "1"  0 empty, 1 black, 2 white
   //   mnk, othello  [r*cols+c]             0 empty, 1 player 0 ("x"), 2 player 1 ("o")
   //   y             [x + y*board_size]     0 empty (or off the triangle), 1 player 0 ("O"), 2 player 1 ("@")
+  //   havannah      [x + y*diameter]       0 empty (or off the hexagon), 1 player 0 ("O"), 2 player 1 ("@")
   std::vector<int8_t> cells;
   int to_play = 0;          // go: colour to move even at terminal states; others: mover
-  int last_move = -1;       // y: the cell of the last stone (-1: none), which ToString brackets
+  int last_move = -1;       // y, havannah: the cell of the last stone (-1: none), which ToString brackets
   // leduc_poker (kInvalidCard = -10000 in the reference, reported here as -1)
   int num_players = 2;
   int round = 0, cur_player = 0, public_card = -1, private_card[5] = {-1, -1, -1, -1, -1};

@@ -88,6 +88,7 @@ static GameOps* make_ops(int id, const b2s_params* p) {
     case B2S_MNK: return make_ops_mnk();
     case B2S_OTHELLO: return make_ops_othello();
     case B2S_Y: return make_ops_y();
+    case B2S_HAVANNAH: return make_ops_havannah();
     case B2S_LEDUC_POKER: return (p && p->players > 2) ? make_ops_leduc_poker_n() : make_ops_leduc_poker();
   }
   return nullptr;
@@ -121,7 +122,7 @@ int64_t b2s_host_zero_copy_steps(void) { return g_host_zero_copy_steps; }
 
 int b2s_game_id(const char* name) {
   static const char* names[B2S_NUM_GAMES] = {"tic_tac_toe", "connect_four", "breakthrough", "hex", "go",
-                                             "kuhn_poker", "leduc_poker", "mnk", "othello", "y"};
+                                             "kuhn_poker", "leduc_poker", "mnk", "othello", "y", "havannah"};
   if (!name) return -1;
   for (int i = 0; i < B2S_NUM_GAMES; ++i) if (!strcmp(name, names[i])) return i;
   return -1;

@@ -747,5 +747,6 @@ GameOps* make_ops_leduc_poker_n();   // players = 3..4
 GameOps* make_ops_mnk();
 GameOps* make_ops_othello();
 GameOps* make_ops_y();
+GameOps* make_ops_havannah();
 
 }  // namespace b2s

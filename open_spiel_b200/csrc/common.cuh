@@ -166,4 +166,31 @@ __device__ __forceinline__ int b_select(B128 a, int k) {
 }
 __device__ __forceinline__ int b_ffs(B128 a) { return a.lo ? __ffsll((long long)a.lo) - 1 : 64 + __ffsll((long long)a.hi) - 1; }
 
+// ---- 256-bit bitboards (mnk: 15 rows x 16-bit stride; havannah: up to 15 x 15 cells) ---------------------------------
+struct B256 {
+  u64 w[4];
+};
+__host__ __device__ __forceinline__ B256 q_and(B256 a, B256 b) { return {{a.w[0] & b.w[0], a.w[1] & b.w[1], a.w[2] & b.w[2], a.w[3] & b.w[3]}}; }
+__host__ __device__ __forceinline__ B256 q_or(B256 a, B256 b) { return {{a.w[0] | b.w[0], a.w[1] | b.w[1], a.w[2] | b.w[2], a.w[3] | b.w[3]}}; }
+__host__ __device__ __forceinline__ B256 q_andn(B256 a, B256 b) { return {{a.w[0] & ~b.w[0], a.w[1] & ~b.w[1], a.w[2] & ~b.w[2], a.w[3] & ~b.w[3]}}; }   // a & ~b
+__host__ __device__ __forceinline__ bool q_any(B256 a) { return (a.w[0] | a.w[1] | a.w[2] | a.w[3]) != 0; }
+__host__ __device__ __forceinline__ B256 q_shr(B256 a, int s) {          // 0 < s < 256
+  const int ws = s >> 6, bs = s & 63;
+  B256 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = i + ws;
+    u64 lo = j < 4 ? a.w[j] : 0ull, hi = j + 1 < 4 ? a.w[j + 1] : 0ull;
+    r.w[i] = bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
+  }
+  return r;
+}
+__host__ __device__ __forceinline__ B256 q_shl(B256 a, int s) {          // 0 < s < 64
+  return {{a.w[0] << s, (a.w[1] << s) | (a.w[0] >> (64 - s)), (a.w[2] << s) | (a.w[1] >> (64 - s)), (a.w[3] << s) | (a.w[2] >> (64 - s))}};
+}
+__host__ __device__ __forceinline__ bool q_test(const B256& a, int i) { return (a.w[i >> 6] >> (i & 63)) & 1ull; }
+__host__ __device__ __forceinline__ void q_set(B256& a, int i) { a.w[i >> 6] |= 1ull << (i & 63); }
+__host__ __device__ __forceinline__ void q_clear(B256& a, int i) { a.w[i >> 6] &= ~(1ull << (i & 63)); }
+__device__ __forceinline__ int q_popc(const B256& a) { return __popcll(a.w[0]) + __popcll(a.w[1]) + __popcll(a.w[2]) + __popcll(a.w[3]); }
+
 }  // namespace b2s

@@ -11,26 +11,6 @@
 
 namespace b2s {
 
-struct B256 {
-  u64 w[4];
-};
-__host__ __device__ __forceinline__ B256 q_and(B256 a, B256 b) { return {{a.w[0] & b.w[0], a.w[1] & b.w[1], a.w[2] & b.w[2], a.w[3] & b.w[3]}}; }
-__host__ __device__ __forceinline__ B256 q_or(B256 a, B256 b) { return {{a.w[0] | b.w[0], a.w[1] | b.w[1], a.w[2] | b.w[2], a.w[3] | b.w[3]}}; }
-__host__ __device__ __forceinline__ bool q_any(B256 a) { return (a.w[0] | a.w[1] | a.w[2] | a.w[3]) != 0; }
-__host__ __device__ __forceinline__ B256 q_shr(B256 a, int s) {          // 0 < s < 256
-  const int ws = s >> 6, bs = s & 63;
-  B256 r;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int j = i + ws;
-    u64 lo = j < 4 ? a.w[j] : 0ull, hi = j + 1 < 4 ? a.w[j + 1] : 0ull;
-    r.w[i] = bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
-  }
-  return r;
-}
-__host__ __device__ __forceinline__ bool q_test(const B256& a, int i) { return (a.w[i >> 6] >> (i & 63)) & 1ull; }
-__host__ __device__ __forceinline__ void q_set(B256& a, int i) { a.w[i >> 6] |= 1ull << (i & 63); }
-
 struct MnkRules {
   static constexpr int kGameId = B2S_MNK;
   typedef uint4 Chunk;

@@ -13,7 +13,7 @@ kChancePlayerId = -1      # spiel_globals.h:26-56
 kTerminalPlayerId = -4
 kInvalidAction = -1
 
-_NAMES = ["tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk", "othello", "y"]
+_NAMES = ["tic_tac_toe", "connect_four", "breakthrough", "hex", "go", "kuhn_poker", "leduc_poker", "mnk", "othello", "y", "havannah"]
 
 
 def registered_names():
@@ -64,6 +64,7 @@ _PARAM_FIELDS = {
     "mnk": {"m": "columns", "n": "rows", "k": "x_in_row"},
     "othello": {},
     "y": {"board_size": "board_size"},
+    "havannah": {"board_size": "board_size", "swap": "swap"},
 }
 
 

@@ -104,6 +104,7 @@ std::unique_ptr<Game> MakeLeducPoker(const Params&);
 std::unique_ptr<Game> MakeMnk(const Params&);
 std::unique_ptr<Game> MakeOthello(const Params&);
 std::unique_ptr<Game> MakeY(const Params&);
+std::unique_ptr<Game> MakeHavannah(const Params&);
 
 }  // namespace oracle
 #endif  // B2S_ORACLE_H_

@@ -16,6 +16,7 @@ std::unique_ptr<Game> LoadGame(const std::string& name, const Params& p) {
   if (name == "mnk") return MakeMnk(p);
   if (name == "othello") return MakeOthello(p);
   if (name == "y") return MakeY(p);
+  if (name == "havannah") return MakeHavannah(p);
   return nullptr;
 }
 }  // namespace oracle

@@ -11,7 +11,7 @@ SRCS := spiel.cc spiel_utils.cc game_parameters.cc observer.cc policy.cc spiel_b
         action_view.cc utils/status.cc utils/usage_logging.cc \
         games/tic_tac_toe/tic_tac_toe.cc games/connect_four/connect_four.cc games/breakthrough/breakthrough.cc \
         games/hex/hex.cc games/kuhn_poker/kuhn_poker.cc games/leduc_poker/leduc_poker.cc \
-        games/go/go.cc games/go/go_board.cc games/mnk/mnk.cc games/othello/othello.cc games/y/y.cc \
+        games/go/go.cc games/go/go_board.cc games/mnk/mnk.cc games/othello/othello.cc games/y/y.cc games/havannah/havannah.cc \
         algorithms/mcts.cc algorithms/cfr.cc algorithms/evaluate_bots.cc algorithms/tabular_exploitability.cc \
         algorithms/best_response.cc algorithms/expected_returns.cc algorithms/history_tree.cc \
         algorithms/get_all_states.cc algorithms/trajectories.cc \

@@ -15,7 +15,7 @@ from open_spiel_b200.playthrough import recorded_params  # noqa: E402
 SRC = "/root/reference/open_spiel/integration_tests/playthroughs"
 NAMES = ["tic_tac_toe", "connect_four", "connect_four_start_at", "breakthrough", "hex(board_size=5)", "go", "kuhn_poker_2p",
          "kuhn_poker_3p", "leduc_poker_1540482260", "leduc_poker_3977671846", "leduc_poker_773740114", "leduc_poker_3p",
-         "leduc_poker_3p_single_tensor", "mnk", "othello", "y(board_size=9)"]
+         "leduc_poker_3p_single_tensor", "mnk", "othello", "y(board_size=9)", "havannah(board_size=4)", "havannah(board_size=4,swap=True)"]
 out = {}
 for n in NAMES:
     text = open(os.path.join(SRC, n + ".txt"), encoding="utf-8").read()

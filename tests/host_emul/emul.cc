@@ -34,6 +34,7 @@ static struct { unsigned x, y, z; } blockIdx, blockDim = {1, 1, 1}, threadIdx;
 #include "../../open_spiel_b200/csrc/rules_mnk.cuh"
 #include "../../open_spiel_b200/csrc/rules_othello.cuh"
 #include "../../open_spiel_b200/csrc/rules_y.cuh"
+#include "../../open_spiel_b200/csrc/rules_havannah.cuh"
 #include "../../open_spiel_b200/csrc/mcts.cuh"
 
 namespace {
@@ -237,6 +238,7 @@ void* emu_create(int game_id, const b2s_params* p, long long cap) {
     case B2S_MNK: return make<MnkRules>(*p, cap);
     case B2S_OTHELLO: return make<OthelloRules>(*p, cap);
     case B2S_Y: return make<YRules>(*p, cap);
+    case B2S_HAVANNAH: return make<HavannahRules>(*p, cap);
     case B2S_LEDUC_POKER: return p->players > 2 ? make<LeducNRules>(*p, cap) : make<LeducRules>(*p, cap);
   }
   g_err = "unknown game id";

@@ -16,5 +16,5 @@ def test_reference_harness_and_lockstep_on_all_seven_dropins():
     tail = out.stdout[-2000:] + out.stderr[-2000:]
     assert out.returncode == 0, tail
     assert "adapter_host_test ok" in out.stdout, tail
-    for g in ["tic_tac_toe", "connect_four", "breakthrough", "hex", "go(board_size=9,komi=7.5)", "kuhn_poker", "leduc_poker", "mnk", "othello", "y(board_size=9)"]:
+    for g in ["tic_tac_toe", "connect_four", "breakthrough", "hex", "go(board_size=9,komi=7.5)", "kuhn_poker", "leduc_poker", "mnk", "othello", "y(board_size=9)", "havannah(board_size=4)"]:
         assert "ok " + g + "\n" in out.stdout, g

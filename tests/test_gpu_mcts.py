@@ -61,6 +61,8 @@ CASES = [
     # next-tier games: pass moves inside the tree (othello), the three-edge flood (y), 256-bit boards (mnk)
     ("othello", 32, 30, 150, 1, True),
     ("othello", 24, 56, 300, 1, True),
+    ("havannah(board_size=3)", 32, 4, 300, 1, True),
+    ("havannah(board_size=4,swap=True)", 24, 10, 150, 1, True),
     ("y(board_size=5)", 32, 4, 300, 1, True),
     ("y(board_size=9)", 24, 12, 120, 2, False),
     ("mnk(m=5,n=5,k=4)", 32, 6, 200, 1, True),

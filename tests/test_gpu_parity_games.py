@@ -36,6 +36,10 @@ GAMES = [
     ("go(board_size=3,komi=0.5)", 256),
     ("go(board_size=4,komi=0.5)", 256),
     ("go(board_size=2,komi=0.5)", 128),
+    ("havannah", 96),
+    ("havannah(board_size=4)", 512),
+    ("havannah(board_size=4,swap=True)", 512),
+    ("havannah(board_size=2)", 64),
     ("y(board_size=9)", 512),
     ("y(board_size=11)", 128),
     ("y(board_size=2)", 64),
@@ -158,7 +162,7 @@ def test_rollout_matches_oracle_given_same_random_stream():
     """b2s_rollout = uniform-random playout; the oracle replays it with the same Philox words."""
     from philox_ref import philox_uniform
     for gs in ["connect_four", "tic_tac_toe", "breakthrough", "hex(board_size=5)", "go(board_size=5)", "kuhn_poker",
-               "leduc_poker", "mnk(m=6,n=6,k=4)", "othello", "y(board_size=7)"]:
+               "leduc_poker", "mnk(m=6,n=6,k=4)", "othello", "y(board_size=7)", "havannah(board_size=4)"]:
         game = b2.load_game(gs)
         n = 256
         b = game.new_batch(n)

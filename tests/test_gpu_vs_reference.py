@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 GAMES = [("tic_tac_toe", 128), ("connect_four", 128), ("breakthrough", 64), ("hex", 32), ("hex(board_size=4,swap=True)", 64),
          ("go(board_size=9)", 32), ("go(board_size=5)", 64), ("kuhn_poker", 128), ("leduc_poker", 256),
-         ("mnk", 16), ("mnk(m=5,n=4,k=3)", 64), ("othello", 64), ("y(board_size=9)", 64)]
+         ("mnk", 16), ("mnk(m=5,n=4,k=3)", 64), ("othello", 64), ("y(board_size=9)", 64), ("havannah(board_size=4,swap=True)", 64), ("havannah", 16)]
 
 
 @pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref not shipped")

@@ -18,6 +18,8 @@ GAMES = [
     ("go(board_size=9)", 25), ("go(board_size=5)", 60), ("go(board_size=7,komi=4.5)", 30),
     ("go(board_size=9,max_game_length=60)", 20), ("go(board_size=4,komi=0.5)", 80), ("go(board_size=3,komi=0.5)", 80),
     ("kuhn_poker", 100), ("kuhn_poker(players=3)", 100),
+    ("havannah", 12), ("havannah(board_size=4)", 150), ("havannah(board_size=4,swap=True)", 150), ("havannah(board_size=6)", 40),
+    ("havannah(board_size=2)", 100), ("havannah(board_size=3,swap=True)", 100), ("havannah(board_size=1)", 2),
     ("y(board_size=9)", 60), ("y(board_size=11)", 30), ("y(board_size=4)", 100), ("y(board_size=1)", 2), ("y", 5),
     ("othello", 60), ("mnk", 6), ("mnk(m=3,n=3,k=3)", 100), ("mnk(m=7,n=5,k=4)", 30), ("mnk(m=15,n=15,k=3)", 10), ("mnk(m=4,n=15,k=5)", 20),
     ("mnk(m=5,n=5,k=7)", 20), ("mnk(m=1,n=1,k=1)", 3),

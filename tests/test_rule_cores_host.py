@@ -117,6 +117,8 @@ GAMES = [
     ("go(board_size=9)", 12), ("go(board_size=5)", 32), ("go(board_size=3,komi=0.5)", 48), ("go(board_size=7,komi=4.5)", 16),
     ("go(board_size=5,max_game_length=30)", 24),
     ("kuhn_poker", 128), ("kuhn_poker(players=3)", 192), ("kuhn_poker(players=4)", 128), ("kuhn_poker(players=5)", 128),
+    ("havannah", 48), ("havannah(board_size=4)", 256), ("havannah(board_size=4,swap=True)", 256), ("havannah(board_size=6)", 64),
+    ("havannah(board_size=2)", 64), ("havannah(board_size=3,swap=True)", 128), ("havannah(board_size=1)", 4),
     ("y(board_size=9)", 128), ("y(board_size=11)", 64), ("y(board_size=1)", 8), ("y(board_size=2)", 32), ("y(board_size=4)", 128),
     ("othello", 96), ("mnk", 24), ("mnk(m=3,n=3,k=3)", 128), ("mnk(m=7,n=5,k=4)", 64), ("mnk(m=15,n=15,k=3)", 32), ("mnk(m=4,n=15,k=5)", 32),
     ("mnk(m=1,n=1,k=1)", 8), ("mnk(m=5,n=5,k=7)", 32),
@@ -199,7 +201,7 @@ def test_rule_core_rejects_illegal_and_post_terminal_actions():
 
 
 @pytest.mark.parametrize("gs", ["connect_four", "tic_tac_toe", "breakthrough", "breakthrough(rows=6,columns=6)", "hex(board_size=5)",
-                                "go(board_size=5)", "go(board_size=9)", "kuhn_poker", "leduc_poker", "mnk(m=6,n=6,k=4)", "othello", "y(board_size=7)"])
+                                "go(board_size=5)", "go(board_size=9)", "kuhn_poker", "leduc_poker", "mnk(m=6,n=6,k=4)", "othello", "y(board_size=7)", "havannah(board_size=4)"])
 def test_playout_step_matches_oracle_given_same_random_stream(gs):
     """common.cuh playout_step (legal-mask draw; candidate rejection sampling for go and breakthrough) on the host vs the
     oracle replaying the same Philox words — the CPU twin of the GPU test of b2s_rollout."""
@@ -241,6 +243,8 @@ MCTS_CASES = [("tic_tac_toe", 16, 3, 300, 2, True, False), ("connect_four", 12, 
               ("breakthrough(rows=5,columns=4)", 4, 3, 800, 1, False, False, 250),
               # next-tier games: pass moves in the tree (othello), wide boards (mnk)
               ("othello", 8, 30, 120, 1, True, False), ("othello", 6, 56, 400, 1, True, True), ("othello", 4, 10, 900, 1, False, False, 300),
+              ("havannah(board_size=3)", 8, 4, 300, 1, True, False), ("havannah(board_size=4,swap=True)", 6, 10, 150, 1, True, True),
+              ("havannah(board_size=3)", 6, 2, 1200, 1, True, False, 300), ("havannah", 4, 30, 40, 1, True, False),
               ("y(board_size=5)", 8, 4, 300, 1, True, False), ("y(board_size=9)", 6, 12, 100, 1, True, True),
               ("y(board_size=4)", 6, 2, 1200, 1, True, False, 300),
               ("mnk(m=5,n=5,k=4)", 8, 6, 200, 1, True, False), ("mnk", 4, 10, 60, 1, True, True),
@@ -324,3 +328,43 @@ def test_hex_swap_on_wide_boards_is_reference_undefined_behaviour():
     st.apply_action(5)                                   # r = 1, c = 2 -> mirrored cell 2 * 3 + 1 = 7 >= 6
     with pytest.raises(RuntimeError):
         st.apply_action(6)                               # the swap action
+
+
+def _havannah_lines(size):
+    """Hand-built havannah games (actions = x + y * diameter) with a known end: (moves of player 0, moves of player 1, winner)."""
+    d = 2 * size - 1
+    c = lambda x, y: x + y * d   # noqa: E731
+    far = [c(1, 1), c(5, 5), c(1, 2), c(5, 4), c(2, 1), c(4, 5)]                  # scattered, never connected to anything decisive
+    ring = [c(2, 2), c(3, 2), c(4, 3), c(4, 4), c(3, 4), c(2, 3)]                  # the six neighbours of (3, 3): a ring
+    bridge = [c(0, 0), c(1, 1), c(2, 2), c(3, 3), c(4, 4), c(5, 5), c(6, 6)]       # corner (0,0) to corner (6,6) along the diagonal
+    fork = [c(1, 0), c(1, 1), c(1, 2), c(1, 3), c(0, 2), c(2, 3), c(3, 4), c(3, 5), c(3, 6)]   # touches edges 0, 5 and 3/4
+    return {"ring": (ring, far, 0), "bridge": (bridge, [c(3, 0), c(6, 3), c(3, 6), c(0, 3), c(5, 6), c(1, 0), c(0, 1)], 0)}, fork
+
+
+def test_havannah_ring_and_bridge_known_answers():
+    """A ring (six stones around an empty cell, havannah.cc:394-409), a bridge (two corners) — decided on exactly the closing
+    move, by the oracle and by the host-compiled rule core; and a ring closed by the SECOND player."""
+    gs = "havannah(board_size=4)"
+    lines, _ = _havannah_lines(4)
+    for name, (mine, theirs, winner) in lines.items():
+        for first in (0, 1):                                   # the winning line played by player 0, then by player 1
+            og = OracleGame(gs)
+            st = og.new_initial_state()
+            emu = Emu(gs, 1)
+            seq = []
+            for k in range(len(mine)):
+                if first == 0:
+                    seq += [mine[k]] + ([theirs[k]] if k + 1 < len(mine) else [])
+                else:
+                    seq += [theirs[k], mine[k]]
+            for i, a in enumerate(seq):
+                assert not st.is_terminal(), (name, first, i)
+                assert emu.status()[1][0] == 0
+                st.apply_action(a)
+                emu.apply([a])
+            assert emu.errors() == 0
+            assert st.is_terminal(), (name, first)
+            want = [1.0, -1.0] if first == 0 else [-1.0, 1.0]
+            assert st.returns() == want
+            cur, term, rets = emu.status()
+            assert term[0] == 1 and rets[0].tolist() == want, (name, first, rets)
