@@ -287,6 +287,11 @@ int  b2s_cfr_import(void* solver, const double* regrets_h, const double* cum_pol
  * (tabular_exploitability.cc) for the CFR loop of examples/cfr_example.cc:37-46; exploitability = nash_conv / 2.
  * values_out (nullable): {best-response value p0, p1, on-policy value p0, p1}.  Synchronises `stream`. */
 int  b2s_cfr_nash_conv(void* solver, int use_average, double* nash_conv_out, double* values_out, void* stream);
+/* The pure best responses behind those values (TabularBestResponse::GetBestResponseActions, best_response.cc:194-228):
+ * best_action_index_h[I] = the best responder's choice at information state I (I in b2s_cfr_export order; the responder is
+ * the state's own player, responding to the other player's average / current policy) as an index into that state's
+ * legal actions — first maximum of the counterfactual-reach-weighted child values.  values_out as above (nullable). */
+int  b2s_cfr_best_response(void* solver, int use_average, int32_t* best_action_index_h, double* values_out, void* stream);
 /* Device pointers of the three per-entry tables. */
 int  b2s_cfr_tables(void* solver, double** regrets_d, double** cum_policy_d, double** cur_policy_d);
 /* Multi-GPU CFR (the path's one real exchange step).  One player-traversal of iteration `iteration`

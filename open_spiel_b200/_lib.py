@@ -94,6 +94,7 @@ SIGNATURES = {
     "b2s_cfr_info_get": (C.c_int, [_VP, C.POINTER(CfrInfo)]),
     "b2s_cfr_export": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "b2s_cfr_import": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, _VP]),
+    "b2s_cfr_best_response": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b2s_cfr_nash_conv": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), _VP]),
     "b2s_cfr_tables": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     "b2s_cfr_traverse_shard": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP]),

@@ -1486,8 +1486,10 @@ int b2s_cfr_set_iteration(void* solver, int iteration) {
 
 // NashConv of the average policy (use_average != 0) or of the current policy; exploitability = nash_conv / 2.
 // values_out (nullable, 4 doubles): best-response values of players 0 and 1, on-policy values of players 0 and 1.
-int b2s_cfr_nash_conv(void* solver, int use_average, double* nash_conv_out, double* values_out, void* stream) {
-  if (!solver || !nash_conv_out) return fail("cfr: null argument");
+// best_h (nullable, num_infosets ints): the best responder's choice at each of ITS information states, as an index into the
+// state's legal actions (TabularBestResponse::BestResponseAction, best_response.cc:194-228: first maximum).
+static int cfr_best_response_impl(void* solver, int use_average, double* nash_conv_out, double* values_out, int32_t* best_h, void* stream) {
+  if (!solver) return fail("cfr: null argument");
   CfrSolver* S = (CfrSolver*)solver;
   B2S_CU(cudaSetDevice(S->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1499,12 +1501,21 @@ int b2s_cfr_nash_conv(void* solver, int use_average, double* nash_conv_out, doub
   ++g_launches;
   double h[4];
   cudaError_t e = cudaMemcpyAsync(h, out, sizeof h, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && best_h) e = cudaMemcpyAsync(best_h, best, sizeof(int) * S->d.n_infosets, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFree(pol); cudaFree(best); cudaFree(out);
   if (e != cudaSuccess) return cuda_fail(e, "k_cfr_nashconv");
-  *nash_conv_out = (h[0] - h[2]) + (h[1] - h[3]);
+  if (nash_conv_out) *nash_conv_out = (h[0] - h[2]) + (h[1] - h[3]);
   if (values_out) memcpy(values_out, h, sizeof h);
   return 0;
+}
+int b2s_cfr_nash_conv(void* solver, int use_average, double* nash_conv_out, double* values_out, void* stream) {
+  if (!nash_conv_out) return fail("cfr: null argument");
+  return cfr_best_response_impl(solver, use_average, nash_conv_out, values_out, nullptr, stream);
+}
+int b2s_cfr_best_response(void* solver, int use_average, int32_t* best_action_index_h, double* values_out, void* stream) {
+  if (!best_action_index_h) return fail("cfr: null argument");
+  return cfr_best_response_impl(solver, use_average, nullptr, values_out, best_action_index_h, stream);
 }
 
 // Device pointers of the per-action tables (regrets, cumulative policy, current policy; num_entries doubles

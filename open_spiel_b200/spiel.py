@@ -648,6 +648,17 @@ class CFRSolver:
         self.last_values = list(vals)
         return nc.value
 
+    def best_response(self, average=True):
+        """TabularBestResponse of each player against the other's average (default) / current policy, on the device:
+        (actions, values) with actions[I] = the legal action chosen at information state I (table() order; first maximum, as
+        best_response.cc:194-228) and values = [BR value p0, BR value p1, on-policy value p0, on-policy value p1]."""
+        i = self._info
+        idx = np.empty(i.num_infosets, dtype=np.int32)
+        vals = (C.c_double * 4)()
+        check(lib().b2s_cfr_best_response(self._h, int(bool(average)), idx.ctypes.data_as(C.c_void_p), vals, None))
+        t = self.table()
+        return t["legal_actions"][t["offsets"][:-1] + idx], list(vals)
+
     def exploitability(self, average=True):
         """algorithms::Exploitability = NashConv / num_players."""
         return self.nash_conv(average) / 2.0

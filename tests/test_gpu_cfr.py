@@ -129,3 +129,36 @@ def test_device_nash_conv_matches_reference(gs, checkpoints):
         assert abs(dev.last_values[2] - (-1.0 / 18.0)) <= 1e-3   # game value for player 0 (cfr_test.cc:40-41)
     else:
         assert dev.nash_conv() <= 2.0                            # cfr_test.cc:299-301 (after >= 10 iterations)
+
+
+@pytest.mark.parametrize("gs,iters", [("kuhn_poker", 40), ("leduc_poker", 25)])
+def test_best_response_actions_achieve_the_best_response_values(gs, iters):
+    """b2s_cfr_best_response (TabularBestResponse::GetBestResponseActions, best_response.cc:194-228): for each player, the pure
+    policy made of the reported actions, played against the other player's average policy, earns exactly the best-response
+    value that NashConv is built from — checked on the device by evaluating that profile as a current policy."""
+    game = b2.load_game(gs)
+    s = b2.CFRSolver(game)
+    s.evaluate_and_update_policy(iters)
+    actions, vals = s.best_response(average=True)
+    nc = s.nash_conv(average=True)
+    assert nc == pytest.approx((vals[0] - vals[2]) + (vals[1] - vals[3]), abs=1e-15)
+    t = s.table()
+    off, players, legal = t["offsets"], t["players"], t["legal_actions"]
+    avg = np.empty_like(t["cum_policy"])
+    for i in range(len(players)):
+        lo, hi = off[i], off[i + 1]
+        tot = t["cum_policy"][lo:hi].sum()
+        avg[lo:hi] = t["cum_policy"][lo:hi] / tot if tot > 0 else 1.0 / (hi - lo)
+    for b in (0, 1):
+        prof = avg.copy()
+        for i in range(len(players)):
+            if players[i] == b:
+                lo, hi = off[i], off[i + 1]
+                assert actions[i] in legal[lo:hi]
+                prof[lo:hi] = (legal[lo:hi] == actions[i]).astype(np.float64)
+        probe = b2.CFRSolver(game)
+        probe.load_table(cur_policy=prof)
+        probe.nash_conv(average=False)
+        on_policy_value_of_b = probe.last_values[2 + b]
+        assert on_policy_value_of_b == pytest.approx(vals[b], abs=1e-12), (gs, b)
+        assert vals[b] >= vals[2 + b] - 1e-12                     # a best response is at least as good as the policy itself
