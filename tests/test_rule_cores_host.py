@@ -308,6 +308,14 @@ def _sweep_variants():
     for bs, komi in [(2, 0.5), (3, 7.5), (4, 0.0), (6, 5.5), (7, 7.5), (8, 0.5), (9, 0.0)]:
         v.append("go(board_size=%d,komi=%s)" % (bs, komi))
     v += ["go(board_size=4,max_game_length=12)", "go(board_size=9,max_game_length=40)"]
+    # next-tier games
+    for m, n, k in [(1, 5, 2), (2, 2, 2), (3, 15, 3), (15, 3, 3), (6, 6, 6), (9, 4, 4), (12, 13, 5), (15, 15, 15), (8, 8, 9)]:
+        v.append("mnk(m=%d,n=%d,k=%d)" % (m, n, k))
+    for bs in (1, 2, 3, 5, 6, 7, 8, 10, 11):
+        v.append("y(board_size=%d)" % bs)
+    for bs, swap in [(1, True), (2, True), (3, False), (5, False), (5, True), (6, True), (7, False), (8, True)]:
+        v.append("havannah(board_size=%d%s)" % (bs, ",swap=True" if swap else ""))
+    v += ["kuhn_poker(players=2)", "kuhn_poker(players=4)", "leduc_poker(players=4,starting_player=3)", "leduc_poker(players=3,starting_player=1)"]
     return v
 
 
