@@ -44,7 +44,7 @@ def test_device_tables_to_reference_and_back(name, iters):
 
 def test_state_serialize_round_trip_through_the_reference():
     rng = np.random.RandomState(5)
-    for gs in ("connect_four", "go(board_size=5)", "leduc_poker"):
+    for gs in ("connect_four", "go(board_size=5)", "leduc_poker", "othello", "havannah(board_size=4,swap=True)", "y(board_size=5)", "mnk(m=4,n=4,k=3)"):
         game, rg = b2.load_game(gs), ref_lib.RefGame(gs)
         st = game.new_initial_state()
         for _ in range(9):

@@ -23,6 +23,12 @@ CASES = [
     ("go(board_size=9)", 24, 0),
     ("kuhn_poker", 400, 0),
     ("leduc_poker", 400, 0),
+    ("kuhn_poker(players=3)", 200, 0),
+    ("leduc_poker(players=3)", 200, 0),
+    ("othello", 64, 0),
+    ("mnk(m=5,n=5,k=4)", 96, 0),
+    ("y(board_size=7)", 96, 0),
+    ("havannah(board_size=4,swap=True)", 96, 0),
     ("connect_four", 100, 20),         # explicit max_unroll_length shorter than max_game_length is an error if exceeded
 ]
 
