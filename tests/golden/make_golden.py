@@ -34,6 +34,7 @@ TRACES = [
     "tic_tac_toe", "connect_four", "breakthrough", "hex(board_size=5)", "go",
     "kuhn_poker_2p", "leduc_poker_1540482260", "leduc_poker_3977671846",
     "leduc_poker_773740114", "kuhn_poker_3p", "leduc_poker_3p",
+    "mnk", "othello", "y(board_size=9)", "havannah(board_size=4)", "havannah(board_size=4,swap=True)",
 ]
 
 CIRCLES = {"◯": 0.0, "◉": 1.0}
