@@ -24,6 +24,13 @@ CASES = [
     ("hex(board_size=5)", 3, 300, 1, True, 2),
     ("go(board_size=5)", 6, 150, 1, True, 9),
     ("go(board_size=9)", 10, 60, 1, True, 13),
+    # next-tier games: the oracle's rule restatements under the unmodified MCTSBot's search, bit for bit
+    ("othello", 20, 150, 1, True, 21),
+    ("othello", 54, 400, 1, True, 22),
+    ("mnk(m=5,n=5,k=4)", 6, 200, 1, True, 23),
+    ("y(board_size=5)", 4, 300, 1, True, 24),
+    ("havannah(board_size=3)", 4, 300, 1, True, 25),
+    ("havannah(board_size=4,swap=True)", 10, 150, 2, True, 26),
 ]
 
 
