@@ -376,3 +376,42 @@ def test_havannah_ring_and_bridge_known_answers():
             assert st.returns() == want
             cur, term, rets = emu.status()
             assert term[0] == 1 and rets[0].tolist() == want, (name, first, rets)
+
+
+import glob as _glob
+import json as _json
+
+_GOLD = sorted(_glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "playthroughs", "*.json")))
+
+
+@pytest.mark.parametrize("path", _GOLD, ids=[os.path.basename(p)[:-5] for p in _GOLD])
+def test_rule_core_replays_reference_playthrough(path):
+    """The reference's golden traces replayed on the host build of the rule cores (the CPU twin of
+    test_gpu_parity_games.py::test_device_replays_reference_playthrough): terminal flag, player to move, legal actions,
+    returns with the sign of zero, every printed tensor."""
+    gold = _json.load(open(path, encoding="utf-8"))
+    try:
+        emu = Emu(gold["game"], 1)
+    except Exception as e:   # a trace of a configuration the packed layouts do not hold
+        pytest.skip(str(e))
+    hdr = gold["header"]
+    assert emu.info.num_distinct_actions == int(hdr["NumDistinctActions"])
+    assert emu.info.max_game_length == int(hdr["MaxGameLength"])
+    for k, g in enumerate(gold["states"]):
+        if g["detailed"]:
+            cur, term, rets = emu.status()
+            assert bool(term[0]) == g["is_terminal"]
+            assert int(cur[0]) == g["current_player"]
+            if "legal_actions" in g:
+                assert emu.legal()[0] == g["legal_actions"]
+            if "returns" in g:
+                assert rets[0].tolist() == g["returns"]
+                assert [bool(np.signbit(x)) for x in rets[0]] == [t.startswith("-") for t in g["returns_text"]]
+            for name, vals in g["tensors"].items():
+                p = int(name[name.index("(") + 1:name.index(")")])
+                t = emu.tensor(p, 0 if name.startswith("Observation") else 1)[0]
+                np.testing.assert_array_equal(t, np.array(vals, dtype=np.float32), err_msg=name)
+        if k < len(gold["actions"]):
+            emu.apply([gold["actions"][k]])
+            assert emu.errors() == 0
+    assert emu.status()[1][0] == 1
