@@ -30,7 +30,7 @@ struct HavannahRules {
   static constexpr int kMinBlocks = 4;
   static constexpr bool kHasInfoState = false;
   static constexpr int kNoMove = 255;
-  static constexpr int kMaxStack = 128;    // ring search depth: a path of distinct own stones (at most 113 of 225 cells... 169 / 2 + 1)
+  static constexpr int kMaxStack = 128;    // ring search depth: a path of distinct stones of one colour (at most 85 of the 169 cells)
 
   struct Cfg {
     int size, d, cells, valid, swap;       // board_size, diameter, d * d, playable cells, swap rule
