@@ -124,10 +124,12 @@ Action B200MCTSBot::Step(const State& state) {
 }
 
 // ---- CFR -------------------------------------------------------------------------------------------------------
-B200CFRSolver::B200CFRSolver(const Game& game, bool cfr_plus) : game_(game.shared_from_this()), cfr_plus_(cfr_plus) {
+B200CFRSolver::B200CFRSolver(const Game& game, bool cfr_plus) : B200CFRSolver(game, cfr_plus, 0) {}
+
+B200CFRSolver::B200CFRSolver(const Game& game, bool cfr_plus, int extra_create_flags) : game_(game.shared_from_this()), cfr_plus_(cfr_plus) {
   b2s_params p;
   int gid = GameIdAndParams(game, &p);
-  Check(b2s_cfr_create(gid, &p, cfr_plus ? (B2S_CFR_LINEAR_AVERAGING | B2S_CFR_REGRET_MATCHING_PLUS) : 0, 0, &solver_));
+  Check(b2s_cfr_create(gid, &p, (cfr_plus ? (B2S_CFR_LINEAR_AVERAGING | B2S_CFR_REGRET_MATCHING_PLUS) : 0) | extra_create_flags, 0, &solver_));
   Check(b2s_cfr_info_get(solver_, &info_));
   const int I = info_.num_infosets, E = info_.num_entries, T = info_.key_floats;
   offsets_.resize(I + 1); legal_.resize(E);
@@ -205,6 +207,18 @@ void B200CFRSolver::Import(const Tables& t) {
       (int)t.current_policy.size() != info_.num_entries)
     SpielFatalError("b200: CFR checkpoint does not match this game's table size");
   Check(b2s_cfr_import(solver_, t.regrets.data(), t.cumulative_policy.data(), t.current_policy.data(), t.iteration, nullptr));
+  Check(b2s_stream_synchronize(0, nullptr));
+}
+
+B200MCCFRSolver::B200MCCFRSolver(const Game& game, Kind kind, uint64_t seed, bool full_average, double epsilon, int per_update)
+    : B200CFRSolver(game, false, B2S_CFR_MCCFR_TABLES), kind_(kind), seed_(seed), full_average_(full_average), epsilon_(epsilon),
+      per_update_(per_update < 1 ? 1 : per_update) {}
+
+void B200MCCFRSolver::RunIterations(int iterations) {
+  if (kind_ == Kind::kExternalSampling)
+    Check(b2s_mccfr_external_iterate_ex(solver_, iterations, per_update_, seed_, full_average_ ? B2S_MCCFR_FULL_AVERAGE : 0, nullptr));
+  else
+    Check(b2s_mccfr_outcome_iterate(solver_, iterations, per_update_, seed_, epsilon_, nullptr));
   Check(b2s_stream_synchronize(0, nullptr));
 }
 

@@ -58,6 +58,8 @@ class B200MCTSBot : public Bot {
 class B200CFRSolver {
  public:
   explicit B200CFRSolver(const Game& game, bool cfr_plus = false);
+  // extra_create_flags: b2s_cfr_create flags OR-ed in (the MCCFR solvers below create their tables with B2S_CFR_MCCFR_TABLES)
+  B200CFRSolver(const Game& game, bool cfr_plus, int extra_create_flags);
   ~B200CFRSolver();
   void EvaluateAndUpdatePolicy();                       // CFRSolverBase::EvaluateAndUpdatePolicy (cfr.cc:263-282)
   void EvaluateAndUpdatePolicy(int iterations);         // ... `iterations` times inside one kernel launch
@@ -72,14 +74,37 @@ class B200CFRSolver {
   const Game& game() const { return *game_; }
   int NumInfoStates() const { return info_.num_infosets; }
 
+ protected:
+  void* solver_ = nullptr;
+
  private:
   TabularPolicy PolicyFrom(const std::vector<double>& per_entry, bool normalise) const;
   std::shared_ptr<const Game> game_;
   bool cfr_plus_ = false;
-  void* solver_ = nullptr;
   b2s_cfr_info info_;
   std::vector<std::string> keys_;                       // information-state string of every device table row
   std::vector<int32_t> offsets_, legal_;
+};
+
+// ExternalSamplingMCCFRSolver (external_sampling_mccfr.h:40-95) / OutcomeSamplingMCCFRSolver (outcome_sampling_mccfr.h:40-66,
+// default uniform policy, no baseline) with device-resident tables.  `per_update` independent traversals / episodes run in
+// parallel per (iteration, player) phase against frozen tables; 1 = the reference's algorithm.  Randomness is the library's
+// position-keyed Philox stream (the reference consumes a std::mt19937 sequentially), so runs are reproducible for a seed but
+// not sample-path identical to the stock solvers; the table arithmetic is.
+class B200MCCFRSolver : public B200CFRSolver {
+ public:
+  enum class Kind { kExternalSampling, kOutcomeSampling };
+  B200MCCFRSolver(const Game& game, Kind kind, uint64_t seed, bool full_average = false, double epsilon = 0.6, int per_update = 1);
+  void RunIteration() { RunIterations(1); }             // ...::RunIteration() (external_sampling_mccfr.cc:71-80, outcome_sampling_mccfr.cc:60-67)
+  void RunIterations(int iterations);
+  Kind kind() const { return kind_; }
+
+ private:
+  Kind kind_;
+  uint64_t seed_;
+  bool full_average_;
+  double epsilon_;
+  int per_update_;
 };
 
 }  // namespace b200

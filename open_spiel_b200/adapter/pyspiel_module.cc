@@ -17,6 +17,8 @@
 #include "b200_games.h"
 #include "open_spiel/algorithms/cfr.h"
 #include "open_spiel/algorithms/mcts.h"
+#include "open_spiel/algorithms/external_sampling_mccfr.h"
+#include "open_spiel/algorithms/outcome_sampling_mccfr.h"
 #include "open_spiel/algorithms/tabular_exploitability.h"
 #include "open_spiel/observer.h"
 #include "open_spiel/policy.h"
@@ -356,6 +358,25 @@ PYBIND11_MODULE(pyspiel, m) {
             return solver;
           }));
   m.def("CFRPlusSolver", [](std::shared_ptr<Game> g) { return new b200::B200CFRSolver(*g, true); });
+
+  // ---- MCCFR (python/pybind11/policy.cc:282-335 names; extra keyword: traversals / trajectories per update) ------------
+  py::enum_<algorithms::AverageType>(m, "MCCFRAverageType")
+      .value("SIMPLE", algorithms::AverageType::kSimple).value("FULL", algorithms::AverageType::kFull);
+  py::class_<b200::B200MCCFRSolver>(m, "_B200MCCFRSolver")
+      .def("run_iteration", [](b200::B200MCCFRSolver& s) { s.RunIteration(); })
+      .def("run_iterations", &b200::B200MCCFRSolver::RunIterations, py::arg("iterations"))
+      .def("average_policy", [](const b200::B200MCCFRSolver& s) { return std::make_shared<TabularPolicy>(s.AveragePolicy()); })
+      .def("nash_conv", [](const b200::B200MCCFRSolver& s) { return s.NashConv(); })
+      .def("num_info_states", [](const b200::B200MCCFRSolver& s) { return s.NumInfoStates(); });
+  m.def("ExternalSamplingMCCFRSolver", [](std::shared_ptr<Game> g, int seed, algorithms::AverageType avg, int traversals_per_update) {
+          return new b200::B200MCCFRSolver(*g, b200::B200MCCFRSolver::Kind::kExternalSampling, (uint64_t)(int64_t)seed,
+                                           avg == algorithms::AverageType::kFull, 0.6, traversals_per_update);
+        }, py::arg("game"), py::arg("seed") = 0, py::arg("avg_type") = algorithms::AverageType::kSimple, py::arg("traversals_per_update") = 1);
+  m.def("OutcomeSamplingMCCFRSolver", [](std::shared_ptr<Game> g, double epsilon, int seed, int trajectories_per_update) {
+          return new b200::B200MCCFRSolver(*g, b200::B200MCCFRSolver::Kind::kOutcomeSampling, (uint64_t)(int64_t)seed, false, epsilon,
+                                           trajectories_per_update);
+        }, py::arg("game"), py::arg("epsilon") = algorithms::OutcomeSamplingMCCFRSolver::kDefaultEpsilon, py::arg("seed") = -1,
+        py::arg("trajectories_per_update") = 1);
 
   // ---- MCTS (bots.cc:106-149 names) --------------------------------------------------------------------------------
   py::enum_<algorithms::ChildSelectionPolicy>(m, "ChildSelectionPolicy")

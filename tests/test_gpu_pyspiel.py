@@ -64,3 +64,25 @@ def test_cfr_solver_matches_reference_bounds_and_pickles():
     plus = pyspiel.CFRPlusSolver(leduc)
     plus.iterate(50)
     assert plus.num_info_states() == 936 and pyspiel.nash_conv(leduc, plus.average_policy()) < 0.5
+
+
+def test_mccfr_solvers_through_the_module():
+    """pyspiel.ExternalSamplingMCCFRSolver / OutcomeSamplingMCCFRSolver (python/pybind11/policy.cc:282-335) on device tables:
+    the reference's own NashConv of the returned average policy agrees with the device's, and meets the bounds of
+    external_sampling_mccfr_test.cc:104-106 / outcome_sampling_mccfr_test.cc at the iteration counts used there."""
+    kuhn = pyspiel.load_game("kuhn_poker")
+    es = pyspiel.ExternalSamplingMCCFRSolver(kuhn, seed=230398247)
+    for _ in range(10):
+        es.run_iteration()
+    es.run_iterations(9990)
+    avg = es.average_policy()
+    nc = pyspiel.nash_conv(kuhn, avg)
+    assert abs(nc - es.nash_conv()) < 1e-9 and nc < 0.05 and es.num_info_states() == 12
+    full = pyspiel.ExternalSamplingMCCFRSolver(kuhn, seed=7, avg_type=pyspiel.MCCFRAverageType.FULL, traversals_per_update=64)
+    full.run_iterations(300)
+    assert pyspiel.nash_conv(kuhn, full.average_policy()) < 0.05
+    leduc = pyspiel.load_game("leduc_poker")
+    os_solver = pyspiel.OutcomeSamplingMCCFRSolver(leduc, epsilon=0.6, seed=3, trajectories_per_update=4096)
+    os_solver.run_iterations(200)
+    nc = pyspiel.nash_conv(leduc, os_solver.average_policy())
+    assert abs(nc - os_solver.nash_conv()) < 1e-9 and nc < 1.0
